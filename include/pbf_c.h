@@ -1,0 +1,174 @@
+/*
+ * pbf_c.h -- C ABI of libpbf_b200.so: the B200-native replacement of ekpyron/pbf's per-timestep PBF
+ * simulation (SPH::Run and the classes it owns).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class API of SPH (src/SPH.h:33-447),
+ * RadixSort (src/RadixSort.h:33-131) and NeighbourCellFinder (src/NeighbourCellFinder.h:35-115), called
+ * only by Simulation (src/Simulation.cpp).  Each entry point below cites the reference interface it
+ * replaces; include/pbf/*.h holds shim classes with the reference's class names and method signatures
+ * that forward to this ABI.
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative pbf_status otherwise; pbf_last_error() returns a
+ *    message for the calling thread.  No exception crosses the ABI (the reference throws
+ *    std::runtime_error / std::logic_error, src/ShaderProgram.cpp:44-116, src/RadixSort.cpp:41-42; the
+ *    shim classes rethrow).
+ *  - a handle is bound to one CUDA device and one stream; calls are asynchronous on that stream unless
+ *    they take or return HOST pointers (those synchronise).  Not thread safe per handle (the reference is
+ *    single threaded on the GL thread, src/main.cpp:337-344).
+ *  - there is no CPU fallback: every call fails with PBF_ERR_CUDA when no sm_100 device is usable.
+ *  - particle state visible to the caller is indexed by persistent particle id, N x float4 {x,y,z,0}
+ *    (src/SPH.cpp:119-133; consumed by src/PointSprite.cpp:64-73 at stride 16), highlight N x uint32.
+ */
+#ifndef PBF_C_H
+#define PBF_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef struct pbf_sim *pbf_handle;
+
+typedef enum {
+    PBF_OK = 0,
+    PBF_ERR_INVALID = -1,   /* bad argument (e.g. N not a multiple of 512: src/Simulation.cpp:202)   */
+    PBF_ERR_CUDA = -2,      /* CUDA runtime error, message in pbf_last_error                         */
+    PBF_ERR_NCCL = -3,
+    PBF_ERR_CAPACITY = -4,  /* slab overflow: more local + halo particles than the handle was sized for */
+    PBF_ERR_STATE = -5      /* call order violated (e.g. stage entry point before pbf_predict)       */
+} pbf_status;
+
+/* Constructor arguments of SPH (src/SPH.h:40 `SPH(numparticles, gridsize = (128,64,128))`) plus what the
+ * reference hard-codes: wall offsets (shaders/sph/updatepos.glsl:98 `vec3 wall = (16,0,16)`), and the
+ * restatement policy switch for findcells.glsl:39-43.  h = 2.0 is a constant of the
+ * kernels as in the reference (src/SPH.cpp:58). */
+typedef struct {
+    uint32_t num_particles;     /* local particle count at creation (multiple of 512)                 */
+    uint32_t capacity;          /* max particles this handle may hold incl. halo (0 = num_particles)  */
+    int32_t grid[3];            /* GRID_SIZE                                                          */
+    float wall[3];              /* wall offsets                                                        */
+    int32_t ref_quirks;         /* 1 = reproduce findcells thread-0 quirk (parity), 0 = corrected      */
+    int32_t device;             /* CUDA device ordinal, -1 = current                                   */
+    int32_t use_graph;          /* 1 = replay the step as a CUDA graph                                 */
+} pbf_config;
+
+/* sphparams_t (src/SPH.h:252-285), same order, + the non-UBO state of SPH: num_solveriterations
+ * (src/SPH.h:189-199), vorticityconfinement (:213-222), extforce uniform (src/SPH.cpp:242-244). */
+typedef struct {
+    float one_over_rho_0;
+    float epsilon;
+    float gravity;
+    float timestep;
+    float tensile_instability_k;
+    float tensile_instability_scale;
+    float xsph_viscosity_c;
+    float vorticity_epsilon;
+    int32_t num_solver_iterations;
+    int32_t vorticity_confinement;
+    int32_t external_force;
+} pbf_params;
+
+const char *pbf_last_error(void);
+int pbf_version(void);
+
+/* SPH::Wpoly6 (src/SPH.cpp:159-164), host side; used for tensile_instability_scale = 1/Wpoly6(0.2, 2). */
+float pbf_wpoly6(float r, float h);
+/* defaults of SPH::SPH (src/SPH.cpp:26, :25, :137-144): K = 5, vorticity off, extforce off */
+void pbf_default_params(pbf_params *p);
+/* RadixSort's numbits/pass count (src/RadixSort.cpp:24-30, :44, :127): number of low key bits sorted */
+int pbf_sort_bits(const int32_t grid[3]);
+
+/* SPH::SPH / SPH::~SPH (src/SPH.cpp:24-156) */
+int pbf_create(const pbf_config *cfg, pbf_handle *out);
+int pbf_destroy(pbf_handle h);
+
+/* setters/getters of SPH (src/SPH.cpp:166-216, src/SPH.h:57-222) */
+int pbf_set_params(pbf_handle h, const pbf_params *p);
+int pbf_get_params(pbf_handle h, pbf_params *p);
+
+/* Simulation::ResetParticleBuffer's upload (src/Simulation.cpp:249-272): HOST arrays of N float4 by id.
+ * vel may be NULL (zero), highlight is cleared.  pbf_download_state copies back (any pointer may be NULL). */
+int pbf_upload_state(pbf_handle h, const float *pos4, const float *vel4, uint32_t n);
+int pbf_download_state(pbf_handle h, float *pos4, float *vel4, uint32_t *highlight);
+/* SPH::GetPositionBuffer / GetVelocityBuffer / GetHighlightBuffer (src/SPH.h:49, :181, :205): DEVICE
+ * pointers of the by-id buffers; callers may write them between steps (src/Simulation.cpp:160-195). */
+int pbf_device_buffers(pbf_handle h, float **pos4, float **vel4, uint32_t **highlight);
+/* Use caller-owned DEVICE memory (e.g. a CUDA-GL interop mapping of the renderer's buffers) for the by-id
+ * state instead of the handle's own allocations; NULL restores the internal buffer. */
+int pbf_bind_device_buffers(pbf_handle h, float *pos4, float *vel4, uint32_t *highlight);
+uint32_t pbf_num_particles(pbf_handle h);
+
+/* SPH::Run (src/SPH.cpp:246-334), nsteps times. */
+int pbf_step(pbf_handle h, int nsteps);
+/* One step from HOST buffers and back (h2d pos+vel, step, d2h pos+vel): the end-to-end call. */
+int pbf_step_host(pbf_handle h, float *pos4, float *vel4, int nsteps);
+int pbf_sync(pbf_handle h);
+
+/* Stage-level entry points, in the order SPH::Run issues them; used by the RadixSort /
+ * NeighbourCellFinder shims and by the parity tests.
+ *   pbf_predict          predictpos.glsl (src/SPH.cpp:247-261) + cell keys + clearhighlight
+ *   pbf_sort             RadixSort::Run (src/RadixSort.cpp:124-133)
+ *   pbf_build_cells      NeighbourCellFinder::FindNeighbourCells (src/NeighbourCellFinder.cpp:113-148)
+ *   pbf_highlight        highlight.glsl (src/SPH.cpp:288-296)
+ *   pbf_calc_lambda      calclambda.glsl (src/SPH.cpp:304-307)
+ *   pbf_update_positions updatepos.glsl (src/SPH.cpp:308-310)
+ *   pbf_finalize         update.glsl (src/SPH.cpp:318-324)
+ *   pbf_vorticity        vorticity.glsl (src/SPH.cpp:325-331) */
+int pbf_predict(pbf_handle h);
+int pbf_sort(pbf_handle h);
+int pbf_build_cells(pbf_handle h);
+int pbf_highlight(pbf_handle h);
+int pbf_calc_lambda(pbf_handle h);
+int pbf_update_positions(pbf_handle h);
+int pbf_finalize(pbf_handle h);
+int pbf_vorticity(pbf_handle h);
+
+/* Standalone RadixSort (src/RadixSort.h:33-131): stable sort of n (key, value) pairs on the low `bits`
+ * bits of the key, DEVICE pointers, on the handle's stream (n <= capacity). */
+int pbf_sort_pairs(pbf_handle h, const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out,
+                   uint32_t *vals_out, uint32_t n, int bits);
+
+/* Debug read-back into HOST arrays (any pointer may be NULL).
+ *   keys[N]     full cell key of each sorted slot (bit 31: outside the cell images)
+ *   perm[N]     particle id at each sorted slot
+ *   records[4N] sorted {pos, id-bits} records = RadixSort::GetBuffer (src/RadixSort.h:45-53)
+ *   start/end   dense gx*gy*gz tables = gridtexture / gridendtexture (src/NeighbourCellFinder.cpp:59-90)
+ *   runs        per particle 9 x {start,count} = the neighbour buffer of neighbourcells.glsl:62-90, unpacked */
+int pbf_get_predicted(pbf_handle h, float *records, uint32_t *keys);
+int pbf_get_sorted(pbf_handle h, uint32_t *keys, uint32_t *perm, float *records);
+int pbf_get_cell_ranges(pbf_handle h, int32_t *start, int32_t *end);
+int pbf_get_neighbour_runs(pbf_handle h, int32_t *run_start, int32_t *run_count);
+int pbf_get_lambda(pbf_handle h, float *lambda);
+int pbf_get_vorticity(pbf_handle h, float *vorticity);
+
+/* SPH::OutputTiming (src/SPH.cpp:218-240): last step's five phases in ms: predict, sort, neighbour cells,
+ * solver, vorticity.  Timing needs pbf_enable_timing(h, 1), which runs steps outside the CUDA graph. */
+int pbf_enable_timing(pbf_handle h, int on);
+int pbf_get_timings(pbf_handle h, float ms[5]);
+
+/* Aggregates the north star's long-run criterion needs (not in the reference): mean |rho_i/rho_0 - 1| at
+ * the current positions (one extra density sweep) and sum 0.5 |v|^2. */
+int pbf_get_diagnostics(pbf_handle h, double *density_error, double *kinetic_energy);
+
+/* how many kernels the handle has launched (graph replays count their kernel nodes) */
+uint64_t pbf_kernel_launches(pbf_handle h);
+/* stream the handle launches on (a cudaStream_t), for callers that time with CUDA events */
+void *pbf_stream(pbf_handle h);
+
+/* Seeded restatement of Simulation::ResetParticleBuffer's block fill (src/Simulation.cpp:216-230): HOST
+ * arrays, nx*ny*nz particles, loop order x,z,y, ids from id0. */
+int pbf_scene_dam_break(int nx, int ny, int nz, const float origin[3], float spacing, int mirror_xz,
+                        uint32_t seed, uint32_t id0, float *pos4, float *vel4);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBF_C_H */

@@ -1,0 +1,538 @@
+// api.cu -- the C ABI of include/pbf_c.h: handle life cycle, step orchestration (SPH::Run, reference
+// src/SPH.cpp:246-334), CUDA-graph replay, phase timing (SPH::OutputTiming, src/SPH.cpp:218-240) and debug read-back.
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "pbf_internal.cuh"
+
+static thread_local std::string g_err;
+void pbf_set_error(const std::string &msg) { g_err = msg; }
+
+namespace {
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+int bitlength(uint64_t v) {   // count_sortbits, src/RadixSort.cpp:24-30
+    int r = 1;
+    while (v >>= 1) r++;
+    return r;
+}
+
+template <class T>
+cudaError_t dalloc(T **p, size_t count) {
+    return cudaMalloc((void **)p, count * sizeof(T) + 16);
+}
+
+struct DeviceGuard {   // every entry point runs on the handle's device and restores the caller's
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void invalidate_graph(pbf_sim *s) {
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    s->graph_exec = nullptr;
+    s->graph = nullptr;
+    s->graph_valid = false;
+}
+
+// SPH::Run, src/SPH.cpp:246-334.  ev != nullptr records the five phase boundaries of the reference's timer queries.
+int enqueue_step(pbf_sim *s, bool with_events) {
+    int k = 0;
+    cudaStream_t st = s->stream;
+    if (with_events) cudaEventRecord(s->ev[0], st);
+    // [predict] :247-261   (+ reset of last step's cell starts, + histograms, + clearhighlight)
+    cudaMemsetAsync(s->flags, 0, sizeof(u32), st);
+    k += launch_unclear_cells(s);
+    k += launch_predict(s);
+    if (with_events) cudaEventRecord(s->ev[1], st);
+    // [sort] :263-268
+    k += launch_sort_scan(s);
+    k += launch_sort_passes(s);
+    if (with_events) cudaEventRecord(s->ev[2], st);
+    // [neighbour cells] :270-275
+    k += launch_reorder_cells(s);
+    if (with_events) cudaEventRecord(s->ev[3], st);
+    // [solver] :277-313
+    k += launch_highlight(s);
+    for (int it = 0; it < s->params.num_solver_iterations; it++) {
+        k += launch_lambda(s);
+        k += launch_delta_p(s);
+    }
+    if (with_events) cudaEventRecord(s->ev[4], st);
+    // [vorticity] :315-333
+    k += launch_update(s);
+    if (s->params.vorticity_confinement) k += launch_vorticity(s);
+    if (with_events) cudaEventRecord(s->ev[5], st);
+    return k;
+}
+
+int check_handle(pbf_handle h) {
+    if (!h) return fail(PBF_ERR_INVALID, "null handle");
+    return PBF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pbf_last_error(void) { return g_err.c_str(); }
+int pbf_version(void) { return 100; }
+
+float pbf_wpoly6(float r, float h) {   // SPH::Wpoly6, src/SPH.cpp:159-164
+    if (r > h) return 0.0f;
+    float tmp = h * h - r * r;
+    return 1.56668147106f * tmp * tmp * tmp / (h * h * h * h * h * h * h * h * h);
+}
+
+void pbf_default_params(pbf_params *p) {   // src/SPH.cpp:25-26, :137-144
+    p->one_over_rho_0 = 1.0f;
+    p->epsilon = 5.0f;
+    p->gravity = 10.0f;
+    p->timestep = 0.016f;
+    p->tensile_instability_k = 0.1f;
+    p->tensile_instability_scale = 1.0f / pbf_wpoly6(0.2f, 2.0f);
+    p->xsph_viscosity_c = 0.01f;
+    p->vorticity_epsilon = 5.0f;
+    p->num_solver_iterations = 5;
+    p->vorticity_confinement = 0;
+    p->external_force = 0;
+}
+
+int pbf_sort_bits(const int32_t grid[3]) {   // src/RadixSort.cpp:44, :127
+    int numbits = bitlength((uint64_t)grid[0] * (uint64_t)grid[1] * (uint64_t)grid[2] - 1);
+    return 2 * ((numbits + 1) >> 1);
+}
+
+int pbf_create(const pbf_config *cfg, pbf_handle *out) {
+    if (!cfg || !out) return fail(PBF_ERR_INVALID, "pbf_create: null argument");
+    *out = nullptr;
+    if (cfg->num_particles == 0 || (cfg->num_particles & 511u))   // src/Simulation.cpp:202, src/SPH.cpp:25 (N >> 9 blocks)
+        return fail(PBF_ERR_INVALID, "pbf_create: num_particles must be a non-zero multiple of 512");
+    if (cfg->grid[0] < 1 || cfg->grid[1] < 1 || cfg->grid[2] < 1)
+        return fail(PBF_ERR_INVALID, "pbf_create: grid dimensions must be positive");
+    const uint64_t ncell = (uint64_t)cfg->grid[0] * cfg->grid[1] * cfg->grid[2];
+    const int sortbits = pbf_sort_bits(cfg->grid);
+    if (ncell > (1ull << 30) || sortbits > 30) return fail(PBF_ERR_INVALID, "pbf_create: grid larger than 2^30 cells");
+    const int bx = bitlength((uint64_t)cfg->grid[0] + 3), bz = bitlength((uint64_t)cfg->grid[2] + 3),
+              by = bitlength((uint64_t)cfg->grid[1] + 3);
+    if (bx + by + bz > 32) return fail(PBF_ERR_INVALID, "pbf_create: grid extents do not pack into a 32-bit home cell");
+    u32 cap = cfg->capacity ? cfg->capacity : cfg->num_particles;
+    if (cap < cfg->num_particles) return fail(PBF_ERR_INVALID, "pbf_create: capacity < num_particles");
+    if (cap >= (1u << 30)) return fail(PBF_ERR_INVALID, "pbf_create: capacity must be < 2^30");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(PBF_ERR_CUDA, std::string("pbf_create: no CUDA device (") + cudaGetErrorString(e) +
+                                      "); libpbf_b200 has no CPU fallback");
+    int dev = cfg->device;
+    if (dev < 0) PBF_CUDA(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PBF_ERR_INVALID, "pbf_create: device ordinal out of range");
+    cudaDeviceProp prop;
+    PBF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(PBF_ERR_CUDA, std::string("pbf_create: device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
+
+    pbf_sim *s = new (std::nothrow) pbf_sim();
+    if (!s) return fail(PBF_ERR_INVALID, "pbf_create: out of host memory");
+    memset((void *)s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    s->device = dev;
+    s->sm_count = prop.multiProcessorCount;
+    s->n = cfg->num_particles;
+    s->cap = cap;
+    s->ncell = (size_t)ncell;
+    s->grid.gx = cfg->grid[0]; s->grid.gy = cfg->grid[1]; s->grid.gz = cfg->grid[2];
+    s->grid.gxgz = cfg->grid[0] * cfg->grid[2];
+    for (int a = 0; a < 3; a++) {
+        s->grid.wlo[a] = 0.0f + cfg->wall[a];                      // updatepos.glsl:100
+        s->grid.whi[a] = (float)cfg->grid[a] - cfg->wall[a];
+    }
+    s->grid.ref_quirks = cfg->ref_quirks;
+    s->grid.bx = bx; s->grid.bz = bz;
+    s->plan = make_sort_plan(sortbits);
+    pbf_default_params(&s->params);
+
+    DeviceGuard guard(dev);
+#define ALLOC(ptr, count)                                                                                       \
+    do {                                                                                                        \
+        cudaError_t e2 = dalloc(&(ptr), (count));                                                              \
+        if (e2 != cudaSuccess) {                                                                                \
+            std::string m = std::string("pbf_create: cudaMalloc " #ptr ": ") + cudaGetErrorString(e2);        \
+            pbf_destroy(s);                                                                                     \
+            return fail(PBF_ERR_CUDA, m);                                                                       \
+        }                                                                                                       \
+    } while (0)
+    e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete s; return fail(PBF_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    ALLOC(s->pos_own, cap); ALLOC(s->vel_own, cap); ALLOC(s->hl_own, cap);
+    ALLOC(s->pred, cap); ALLOC(s->keys, cap);
+    ALLOC(s->ktmp[0], cap); ALLOC(s->ktmp[1], cap); ALLOC(s->vtmp[0], cap); ALLOC(s->vtmp[1], cap);
+    ALLOC(s->skey, cap); ALLOC(s->perm, cap); ALLOC(s->home, cap);
+    s->max_tiles = sort_max_tiles(cap);
+    ALLOC(s->hist, 4 * PBF_RADIX); ALLOC(s->gbase, 4 * PBF_RADIX); ALLOC(s->tile_counter, 4);
+    ALLOC(s->status, (size_t)4 * s->max_tiles * PBF_RADIX);
+    ALLOC(s->cells, s->ncell);
+    ALLOC(s->bufA, cap); ALLOC(s->bufB, cap); ALLOC(s->svel, cap); ALLOC(s->vprime, cap); ALLOC(s->omega, cap);
+    ALLOC(s->flags, 4); ALLOC(s->diag, 2);
+#undef ALLOC
+    s->pos = s->pos_own; s->vel = s->vel_own; s->hl = s->hl_own;
+    cudaMemsetAsync(s->pos_own, 0, (size_t)cap * 16, s->stream);
+    cudaMemsetAsync(s->vel_own, 0, (size_t)cap * 16, s->stream);
+    cudaMemsetAsync(s->hl_own, 0, (size_t)cap * 4, s->stream);
+    cudaMemsetAsync(s->hist, 0, 4 * PBF_RADIX * 4, s->stream);
+    cudaMemsetAsync(s->tile_counter, 0, 16, s->stream);
+    cudaMemsetAsync(s->flags, 0, 16, s->stream);
+    // start = -1 (gridtexture clear, src/NeighbourCellFinder.cpp:116-126), end = -1 likewise so a whole-table memset works
+    cudaMemsetAsync(s->cells, 0xff, s->ncell * sizeof(int2), s->stream);
+    for (int i = 0; i < 6; i++) cudaEventCreate(&s->ev[i]);
+    e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) {
+        std::string m = std::string("pbf_create: ") + cudaGetErrorString(e);
+        pbf_destroy(s);
+        return fail(PBF_ERR_CUDA, m);
+    }
+    *out = s;
+    return PBF_OK;
+}
+
+int pbf_destroy(pbf_handle s) {
+    if (!s) return PBF_OK;
+    DeviceGuard guard(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    invalidate_graph(s);
+    void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
+                    s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->bufA, s->bufB,
+                    s->svel, s->vprime, s->omega, s->flags, s->diag};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < 6; i++)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return PBF_OK;
+}
+
+int pbf_set_params(pbf_handle s, const pbf_params *p) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!p) return fail(PBF_ERR_INVALID, "pbf_set_params: null");
+    if (p->num_solver_iterations < 0) return fail(PBF_ERR_INVALID, "pbf_set_params: negative iteration count");
+    if (memcmp(&s->params, p, sizeof(*p)) != 0) {
+        s->params = *p;
+        invalidate_graph(s);   // kernel arguments are baked into the captured graph
+    }
+    return PBF_OK;
+}
+
+int pbf_get_params(pbf_handle s, pbf_params *p) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!p) return fail(PBF_ERR_INVALID, "pbf_get_params: null");
+    *p = s->params;
+    return PBF_OK;
+}
+
+uint32_t pbf_num_particles(pbf_handle s) { return s ? s->n : 0; }
+
+int pbf_upload_state(pbf_handle s, const float *pos4, const float *vel4, uint32_t n) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!pos4) return fail(PBF_ERR_INVALID, "pbf_upload_state: null positions");
+    if (n != s->n) return fail(PBF_ERR_INVALID, "pbf_upload_state: n differs from the handle's particle count");
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    if (vel4) PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    else PBF_CUDA(cudaMemsetAsync(s->vel, 0, (size_t)n * 16, s->stream));
+    PBF_CUDA(cudaMemsetAsync(s->hl, 0, (size_t)n * 4, s->stream));   // src/Simulation.cpp:271-272
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    s->stage = 0;
+    return PBF_OK;
+}
+
+int pbf_download_state(pbf_handle s, float *pos4, float *vel4, uint32_t *highlight) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    DeviceGuard guard(s->device);
+    if (pos4) PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (vel4) PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (highlight) PBF_CUDA(cudaMemcpyAsync(highlight, s->hl, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    return PBF_OK;
+}
+
+int pbf_device_buffers(pbf_handle s, float **pos4, float **vel4, uint32_t **highlight) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (pos4) *pos4 = (float *)s->pos;
+    if (vel4) *vel4 = (float *)s->vel;
+    if (highlight) *highlight = s->hl;
+    return PBF_OK;
+}
+
+int pbf_bind_device_buffers(pbf_handle s, float *pos4, float *vel4, uint32_t *highlight) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    float4 *np = pos4 ? (float4 *)pos4 : s->pos_own, *nv = vel4 ? (float4 *)vel4 : s->vel_own;
+    u32 *nh = highlight ? highlight : s->hl_own;
+    if (((uintptr_t)np | (uintptr_t)nv) & 15u) return fail(PBF_ERR_INVALID, "pbf_bind_device_buffers: buffers must be 16-byte aligned");
+    if (np != s->pos || nv != s->vel || nh != s->hl) {
+        s->pos = np; s->vel = nv; s->hl = nh;
+        invalidate_graph(s);
+    }
+    return PBF_OK;
+}
+
+int pbf_step(pbf_handle s, int nsteps) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (nsteps < 0) return fail(PBF_ERR_INVALID, "pbf_step: negative step count");
+    DeviceGuard guard(s->device);
+    const bool use_graph = s->cfg.use_graph && !s->timing;
+    for (int i = 0; i < nsteps; i++) {
+        if (use_graph) {
+            // the very first step has no previous cell table to reset, so its launch list differs: run it directly
+            if (!s->graph_valid && s->n_prev_sorted == s->n) {
+                PBF_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+                int k = enqueue_step(s, false);
+                cudaError_t e = cudaStreamEndCapture(s->stream, &s->graph);
+                if (e != cudaSuccess) { s->graph = nullptr; return fail(PBF_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e)); }
+                PBF_CUDA(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+                s->graph_kernels = (u32)k;
+                s->graph_valid = true;
+            }
+            if (s->graph_valid) {
+                PBF_CUDA(cudaGraphLaunch(s->graph_exec, s->stream));
+                s->launches += s->graph_kernels;
+                continue;
+            }
+        }
+        s->launches += (uint64_t)enqueue_step(s, s->timing);
+        s->ev_valid = s->timing;
+        PBF_CUDA(cudaGetLastError());
+    }
+    s->stage = 0;
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
+int pbf_step_host(pbf_handle s, float *pos4, float *vel4, int nsteps) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!pos4 || !vel4) return fail(PBF_ERR_INVALID, "pbf_step_host: null buffer");
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, (size_t)s->n * 16, cudaMemcpyHostToDevice, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, (size_t)s->n * 16, cudaMemcpyHostToDevice, s->stream));
+    int r = pbf_step(s, nsteps);
+    if (r) return r;
+    PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    return PBF_OK;
+}
+
+int pbf_sync(pbf_handle s) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    return PBF_OK;
+}
+
+// ---- stage-level entry points -------------------------------------------------------------------------------------
+#define STAGE_PROLOGUE(need, name)                                                                       \
+    if (check_handle(s)) return PBF_ERR_INVALID;                                                         \
+    if (s->stage < (need)) return fail(PBF_ERR_STATE, name ": called before the stages it depends on"); \
+    DeviceGuard guard(s->device);
+
+int pbf_predict(pbf_handle s) {
+    STAGE_PROLOGUE(0, "pbf_predict");
+    cudaMemsetAsync(s->flags, 0, sizeof(u32), s->stream);
+    s->launches += launch_unclear_cells(s);
+    s->n_prev_sorted = 0;   // table is clean until pbf_build_cells refills it
+    s->launches += launch_predict(s);
+    PBF_CUDA(cudaGetLastError());
+    s->stage = 1;
+    return PBF_OK;
+}
+
+int pbf_sort(pbf_handle s) {
+    STAGE_PROLOGUE(1, "pbf_sort");
+    s->launches += launch_sort_scan(s);
+    s->launches += launch_sort_passes(s);
+    PBF_CUDA(cudaGetLastError());
+    s->stage = 2;
+    return PBF_OK;
+}
+
+int pbf_build_cells(pbf_handle s) {
+    STAGE_PROLOGUE(2, "pbf_build_cells");
+    s->launches += launch_reorder_cells(s);
+    PBF_CUDA(cudaGetLastError());
+    s->stage = 3;
+    return PBF_OK;
+}
+
+int pbf_highlight(pbf_handle s) {
+    STAGE_PROLOGUE(3, "pbf_highlight");
+    s->launches += launch_highlight(s);
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
+int pbf_calc_lambda(pbf_handle s) {
+    STAGE_PROLOGUE(3, "pbf_calc_lambda");
+    s->launches += launch_lambda(s);
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
+int pbf_update_positions(pbf_handle s) {
+    STAGE_PROLOGUE(3, "pbf_update_positions");
+    s->launches += launch_delta_p(s);
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
+int pbf_finalize(pbf_handle s) {
+    STAGE_PROLOGUE(3, "pbf_finalize");
+    s->launches += launch_update(s);
+    PBF_CUDA(cudaGetLastError());
+    s->stage = 4;
+    return PBF_OK;
+}
+
+int pbf_vorticity(pbf_handle s) {
+    STAGE_PROLOGUE(4, "pbf_vorticity");
+    if (!s->params.vorticity_confinement)
+        return fail(PBF_ERR_STATE, "pbf_vorticity: vorticity_confinement was off in pbf_finalize (sorted velocities missing)");
+    s->launches += launch_vorticity(s);
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
+int pbf_sort_pairs(pbf_handle s, const uint32_t *keys_in, const uint32_t *vals_in, uint32_t *keys_out,
+                   uint32_t *vals_out, uint32_t n, int bits) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!keys_in || !keys_out || !vals_out) return fail(PBF_ERR_INVALID, "pbf_sort_pairs: null buffer");
+    if (n > s->cap) return fail(PBF_ERR_CAPACITY, "pbf_sort_pairs: n exceeds the handle's capacity");
+    if (bits < 1 || bits > 32) return fail(PBF_ERR_INVALID, "pbf_sort_pairs: bits must be in [1,32]");
+    DeviceGuard guard(s->device);
+    s->launches += launch_sort_pairs(s, keys_in, vals_in, keys_out, vals_out, n, bits);
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
+// ---- debug read-back --------------------------------------------------------------------------------------------------
+int pbf_get_predicted(pbf_handle s, float *records, uint32_t *keys) {
+    STAGE_PROLOGUE(1, "pbf_get_predicted");
+    if (records) PBF_CUDA(cudaMemcpyAsync(records, s->pred, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (keys) PBF_CUDA(cudaMemcpyAsync(keys, s->keys, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    return PBF_OK;
+}
+
+int pbf_get_sorted(pbf_handle s, uint32_t *keys, uint32_t *perm, float *records) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (s->n_prev_sorted != s->n && s->stage < 2) return fail(PBF_ERR_STATE, "pbf_get_sorted: nothing sorted yet");
+    DeviceGuard guard(s->device);
+    if (keys) PBF_CUDA(cudaMemcpyAsync(keys, s->skey, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (perm) PBF_CUDA(cudaMemcpyAsync(perm, s->perm, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
+    if (records) {
+        if (s->n_prev_sorted != s->n) return fail(PBF_ERR_STATE, "pbf_get_sorted: records need pbf_build_cells");
+        // compose {pos, id} = RadixSort::GetBuffer's record layout (predictpos.glsl:3-6) in scratch (bufB is free between sweeps
+        // only after lambda has been consumed; use vprime, which only the vorticity kernels touch)
+        s->launches += launch_compose_records(s, s->vprime);
+        PBF_CUDA(cudaMemcpyAsync(records, s->vprime, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    }
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    return PBF_OK;
+}
+
+int pbf_get_cell_ranges(pbf_handle s, int32_t *start, int32_t *end) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    DeviceGuard guard(s->device);
+    std::vector<int2> tmp(s->ncell);
+    PBF_CUDA(cudaMemcpyAsync(tmp.data(), s->cells, s->ncell * sizeof(int2), cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t c = 0; c < s->ncell; c++) {
+        if (start) start[c] = tmp[c].x;
+        if (end) end[c] = tmp[c].y;
+    }
+    return PBF_OK;
+}
+
+int pbf_get_neighbour_runs(pbf_handle s, int32_t *run_start, int32_t *run_count) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (s->n_prev_sorted != s->n) return fail(PBF_ERR_STATE, "pbf_get_neighbour_runs: needs pbf_build_cells");
+    if (!run_start || !run_count) return fail(PBF_ERR_INVALID, "pbf_get_neighbour_runs: null buffer");
+    DeviceGuard guard(s->device);
+    int *rs = nullptr, *rc = nullptr;
+    PBF_CUDA(cudaMalloc(&rs, (size_t)s->n * 36));
+    cudaError_t e = cudaMalloc(&rc, (size_t)s->n * 36);
+    if (e != cudaSuccess) { cudaFree(rs); return fail(PBF_ERR_CUDA, cudaGetErrorString(e)); }
+    s->launches += launch_neighbour_runs(s, rs, rc);
+    cudaMemcpyAsync(run_start, rs, (size_t)s->n * 36, cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(run_count, rc, (size_t)s->n * 36, cudaMemcpyDeviceToHost, s->stream);
+    e = cudaStreamSynchronize(s->stream);
+    cudaFree(rs); cudaFree(rc);
+    if (e != cudaSuccess) return fail(PBF_ERR_CUDA, cudaGetErrorString(e));
+    return PBF_OK;
+}
+
+static int get_w(pbf_handle s, float *out, const char *what) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!out) return fail(PBF_ERR_INVALID, std::string(what) + ": null buffer");
+    DeviceGuard guard(s->device);
+    std::vector<float4> tmp(s->n);
+    PBF_CUDA(cudaMemcpyAsync(tmp.data(), s->bufB, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    for (u32 i = 0; i < s->n; i++) out[i] = tmp[i].w;
+    return PBF_OK;
+}
+// lambda of the last pbf_calc_lambda / |omega| of the last vorticity sweep, by sorted slot (both live in bufB.w)
+int pbf_get_lambda(pbf_handle s, float *lambda) { return get_w(s, lambda, "pbf_get_lambda"); }
+int pbf_get_vorticity(pbf_handle s, float *vorticity) { return get_w(s, vorticity, "pbf_get_vorticity"); }
+
+int pbf_enable_timing(pbf_handle s, int on) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    s->timing = on != 0;
+    return PBF_OK;
+}
+
+int pbf_get_timings(pbf_handle s, float ms[5]) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!ms) return fail(PBF_ERR_INVALID, "pbf_get_timings: null");
+    if (!s->ev_valid) return fail(PBF_ERR_STATE, "pbf_get_timings: no timed step (pbf_enable_timing first)");
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaEventSynchronize(s->ev[5]));
+    for (int i = 0; i < 5; i++) PBF_CUDA(cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
+    return PBF_OK;
+}
+
+int pbf_get_diagnostics(pbf_handle s, double *density_error, double *kinetic_energy) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaMemsetAsync(s->diag, 0, 2 * sizeof(double), s->stream));
+    if (density_error) {
+        if (s->n_prev_sorted != s->n) return fail(PBF_ERR_STATE, "pbf_get_diagnostics: density needs a completed step");
+        s->launches += launch_density_diag(s);
+    }
+    if (kinetic_energy) s->launches += launch_kinetic_diag(s);
+    double host[2];
+    PBF_CUDA(cudaMemcpyAsync(host, s->diag, sizeof(host), cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    if (density_error) *density_error = host[0] / (double)s->n;
+    if (kinetic_energy) *kinetic_energy = host[1];
+    return PBF_OK;
+}
+
+uint64_t pbf_kernel_launches(pbf_handle s) { return s ? s->launches : 0; }
+void *pbf_stream(pbf_handle s) { return s ? (void *)s->stream : nullptr; }
+
+}  // extern "C"

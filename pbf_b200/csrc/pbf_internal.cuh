@@ -1,0 +1,110 @@
+// pbf_internal.cuh -- handle layout, kernel-side parameter blocks and launch prototypes shared by the
+// translation units of libpbf_b200.so.  sm_100a only; there is no CPU path in this library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pbf_c.h"
+
+typedef uint32_t u32;
+
+#define PBF_KEY_NOCELL 0x80000000u   // bit 31 of a cell key: the clamped cell lies outside the cell images
+#define PBF_RADIX 256
+
+// what the reference injects into every shader as GLSL header constants (src/SPH.cpp:28-60)
+struct GridInfo {
+    int gx, gy, gz;        // GRID_SIZE
+    int gxgz;              // GRID_HASHWEIGHTS.y = gx*gz; hash = x + z*gx + y*gx*gz
+    float wlo[3], whi[3];  // clamp bounds of updatepos.glsl:98-100: wall, GRID_SIZE - wall
+    int ref_quirks;
+    int bx, bz;            // bit widths of the packed home cell (x | z << bx | y << (bx+bz))
+};
+
+// the std140 SPHParameters block (src/SPH.cpp:46-56) + the extforce uniform (predictpos.glsl:13)
+struct SimParams {
+    float one_over_rho_0, epsilon, gravity, timestep;
+    float tensile_k, tensile_scale, xsph_c, vort_eps;
+    int extforce;
+};
+
+struct SortPlan {
+    int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
+    int passes;      // 8-bit onesweep passes
+    int shift[4];
+    u32 mask[4];
+};
+
+struct pbf_sim {
+    pbf_config cfg;
+    pbf_params params;
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    u32 n;           // particles held
+    u32 cap;
+    GridInfo grid;
+    SortPlan plan;
+    size_t ncell;
+
+    // by-id state (SPH::positionbuffer / velocitybuffer / highlightbuffer, src/SPH.cpp:106-133)
+    float4 *pos_own, *vel_own; u32 *hl_own;
+    float4 *pos, *vel; u32 *hl;          // bound (own or caller's)
+
+    // predicted records by id {p*, id} (RadixSort::buffer as written by predictpos.glsl:37) and their keys
+    float4 *pred; u32 *keys;
+    // sort scratch
+    u32 *ktmp[2], *vtmp[2];
+    u32 *skey, *perm;                     // sorted cell keys, particle id per sorted slot
+    u32 *home;                            // packed unclamped cell of the predicted position per sorted slot
+    u32 *hist, *gbase, *tile_counter, *status;
+    u32 max_tiles;
+    // cell table {start,end} per cell (gridtexture / gridendtexture, src/NeighbourCellFinder.cpp:59-90)
+    int2 *cells;
+    u32 n_prev_sorted;                    // slots of skey that describe the current table contents
+    // solver state in sorted order
+    float4 *bufA;                         // {x,y,z,-}   positions (Jacobi ping)
+    float4 *bufB;                         // {x,y,z,lambda} resp. {x,y,z,|omega|}
+    float4 *svel, *vprime, *omega;
+    u32 *flags;                           // [0] = any highlight bit0 set this step
+    double *diag;                         // [0] density error sum, [1] kinetic energy
+
+    // graph replay of the whole step
+    cudaGraph_t graph; cudaGraphExec_t graph_exec; bool graph_valid; u32 graph_kernels;
+    bool timing; cudaEvent_t ev[6]; bool ev_valid;
+    uint64_t launches;
+    int stage;                            // 0 idle, 1 predicted, 2 sorted, 3 cells built
+};
+
+// error plumbing (api.cu)
+void pbf_set_error(const std::string &msg);
+#define PBF_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            pbf_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+            return PBF_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+// ---- launchers (each returns the number of kernels it enqueued; errors surface at the next PBF_CUDA) ----
+// sim_kernels.cu
+int launch_unclear_cells(pbf_sim *s);
+int launch_predict(pbf_sim *s);
+int launch_reorder_cells(pbf_sim *s);
+int launch_highlight(pbf_sim *s);
+int launch_lambda(pbf_sim *s);
+int launch_delta_p(pbf_sim *s);
+int launch_update(pbf_sim *s);
+int launch_vorticity(pbf_sim *s);
+int launch_density_diag(pbf_sim *s);
+int launch_kinetic_diag(pbf_sim *s);
+int launch_compose_records(pbf_sim *s, float4 *out);
+int launch_neighbour_runs(pbf_sim *s, int *run_start, int *run_count);
+// sort.cu
+SortPlan make_sort_plan(int bits);
+u32 sort_max_tiles(u32 cap);
+int launch_sort_scan(pbf_sim *s);
+int launch_sort_passes(pbf_sim *s);
+int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, int bits);

@@ -1,0 +1,223 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bit-exact: predicted records, cell keys, sort permutation, cell start/end, neighbour runs.
+Tolerance (north star): positions within 1e-5 x domain extent (128) = 1.28e-3 after one step; velocities are
+(p_new - p_old)/dt so they inherit 1.28e-3/dt = 0.08.  Observed differences are ~1e-6 (FMA + rsqrt.approx vs the
+oracle's uncontracted IEEE arithmetic).
+"""
+import numpy as np
+import pytest
+
+import oracle
+import pbf_b200
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-5 * 128.0
+VEL_TOL = POS_TOL / 0.016
+
+
+def make(n3=(32, 32, 32), grid=(128, 64, 128), quirks=True, two_blocks=False, **kw):
+    pos, vel = oracle.dam_break(*n3)
+    if two_blocks:   # the reference's own scene: second block mirrored (src/Simulation.cpp:232-246)
+        p2, v2 = oracle.dam_break(*n3, origin=(32.5 + 63.0, 0.5, 32.5 + 63.0), mirror=True, id0=pos.shape[0])
+        pos, vel = np.concatenate([pos, p2]), np.concatenate([vel, v2])
+    g = oracle.make_grid(*grid, ref_quirks=int(quirks))
+    sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=quirks, **kw)
+    sph.upload(pos, vel)
+    return sph, g, pos, vel
+
+
+def oracle_params(sph):
+    P = oracle.default_params()
+    p = sph._get()
+    for k in ("one_over_rho_0", "epsilon", "gravity", "timestep", "tensile_instability_k",
+              "tensile_instability_scale", "xsph_viscosity_c", "vorticity_epsilon"):
+        setattr(P, k, getattr(p, k))
+    return P
+
+
+def test_scene_generator_bit_exact(built_lib):
+    a, _ = oracle.dam_break(16, 8, 4, seed=7)
+    b, _ = pbf_b200.dam_break(16, 8, 4, seed=7)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    a, _ = oracle.dam_break(5, 3, 2, origin=(95.5, 0.5, 95.5), mirror=True, id0=100)
+    b, _ = pbf_b200.dam_break(5, 3, 2, origin=(95.5, 0.5, 95.5), mirror=True, id0=100)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("extforce", [False, True])
+def test_predict_and_keys_bit_exact(built_lib, extforce):
+    sph, g, pos, vel = make(two_blocks=True)
+    vel[:, :3] = np.random.default_rng(1).normal(0, 3, (pos.shape[0], 3)).astype(np.float32)
+    sph.upload(pos, vel)
+    sph.SetExternalForce(extforce)
+    sph.predict()
+    rec, keys = sph.get_predicted()
+    P = oracle_params(sph)
+    orec = oracle.predict(pos, vel, P, g, extforce)
+    assert np.array_equal(rec.view(np.uint32), orec.view(np.uint32))
+    assert np.array_equal(keys, oracle.keys(orec, g))
+
+
+def staged(sph):
+    sph.predict(); sph.sort(); sph.build_cells()
+
+
+@pytest.mark.parametrize("quirks", [True, False])
+@pytest.mark.parametrize("grid,n3", [((128, 64, 128), (32, 32, 32)), ((100, 50, 90), (24, 16, 24))])
+def test_sort_cells_runs_bit_exact(built_lib, quirks, grid, n3):
+    sph, g, pos, vel = make(n3, grid, quirks)
+    staged(sph)
+    keys, perm, rec = sph.get_sorted()
+    P = oracle_params(sph)
+    orec = oracle.predict(pos, vel, P, g)
+    osorted, okeys = oracle.sort(orec, g)
+    assert np.array_equal(keys, okeys)
+    assert np.array_equal(perm, osorted[:, 3].view(np.int32).astype(np.uint32))
+    assert np.array_equal(rec.view(np.uint32), osorted.view(np.uint32))
+    # sortedness on the sorted bits + stability
+    bits = oracle.sortbits(g)
+    mk = keys & np.uint32((1 << bits) - 1)
+    assert np.all(mk[1:] >= mk[:-1])
+    same = mk[1:] == mk[:-1]
+    assert np.all(perm[1:][same] > perm[:-1][same])
+    start, end = sph.get_cell_ranges()
+    ostart, oend = oracle.findcells(osorted, g)
+    assert np.array_equal(start, ostart)
+    occ = ostart != -1
+    if quirks:
+        occ[0] = False    # start[(0,0,0)] = 0 is always written, its end never is (findcells.glsl:39-43)
+    assert np.array_equal(end[occ], oend[occ])
+    rs, rc = sph.get_neighbour_runs()
+    ors, orc = oracle.neighbourcells(osorted, g, ostart, oend)
+    assert np.array_equal(rc, orc)
+    assert np.array_equal(rs[rc > 0], ors[orc > 0])
+
+
+def test_lambda_and_delta_p(built_lib):
+    sph, g, pos, vel = make(two_blocks=True)
+    P = oracle_params(sph)
+    staged(sph)
+    _, _, rec = sph.get_sorted()
+    start, end = oracle.findcells(rec, g)
+    rs, rc = oracle.neighbourcells(rec, g, start, end)
+    cur = rec
+    for it in range(3):
+        sph.calc_lambda()
+        lam = sph.get_lambda()
+        olam, _ = oracle.calclambda(cur, rs, rc, P)
+        assert np.max(np.abs(lam - olam)) < 1e-5 * max(1.0, np.max(np.abs(olam)))
+        sph.update_positions()
+        _, _, new = sph.get_sorted()
+        onew = oracle.updatepos(cur, rs, rc, olam, P, g)
+        assert np.max(np.abs(new[:, :3] - onew[:, :3])) < 1e-4     # ~100x tighter than POS_TOL
+        assert np.array_equal(new[:, 3].view(np.int32), onew[:, 3].view(np.int32))
+        cur = new      # keep both sides on identical inputs per iteration
+
+
+@pytest.mark.parametrize("vort", [False, True])
+@pytest.mark.parametrize("graph", [False, True])
+def test_one_step(built_lib, vort, graph):
+    sph, g, pos, vel = make(two_blocks=True, use_graph=graph)
+    sph.SetNumSolverIterations(3)
+    sph.SetVorticityConfinementEnabled(vort)
+    P = oracle_params(sph)
+    sim = oracle.Sim(pos.shape[0], g)
+    opos, ovel = pos.copy(), vel.copy()
+    for step in range(3):      # step 2+ exercises the cell-table reset and (graph=True) the captured graph
+        sph.Run()
+        sim.step(opos, ovel, P, 3, vorticity=vort)
+        gpos, gvel = sph.download()
+        assert np.max(np.abs(gpos - opos)) < POS_TOL, step
+        assert np.max(np.abs(gvel - ovel)) < VEL_TOL, step
+        assert np.all(gpos[:, 3] == 0) and np.all(gvel[:, 3] == 0)
+        sph.upload(opos, ovel)   # resynchronise so every step compares one step of drift only
+
+
+def test_vorticity_stage(built_lib):
+    sph, g, pos, vel = make()
+    sph.SetNumSolverIterations(2)
+    sph.SetVorticityConfinementEnabled(True)
+    vel[:, :3] = np.random.default_rng(3).normal(0, 1, (pos.shape[0], 3)).astype(np.float32)
+    sph.upload(pos, vel)
+    P = oracle_params(sph)
+    sim = oracle.Sim(pos.shape[0], g)
+    opos, ovel = pos.copy(), vel.copy()
+    sim.step(opos, ovel, P, 2, vorticity=True)
+    sph.Run()
+    gpos, gvel = sph.download()
+    assert np.max(np.abs(gvel - ovel)) < 1e-2
+    w = sph.get_vorticity()
+    assert np.max(np.abs(w - sim.vort)) < 1e-2 * max(1.0, np.max(sim.vort))
+
+
+def test_highlight(built_lib):
+    import ctypes as C
+    sph, g, pos, vel = make()
+    hl = np.zeros(pos.shape[0], np.uint32)
+    hl[[5, 777, 20000]] = 1
+    hl[[9, 10]] = 2       # stale neighbour marks must be cleared
+    import torch
+    t = torch.from_numpy(hl.view(np.int32)).cuda()
+    sph.bind_device_buffers(highlight=t)
+    sph.SetNumSolverIterations(1)
+    sph.Run()
+    out = t.cpu().numpy().view(np.uint32)
+    sim = oracle.Sim(pos.shape[0], g)
+    P = oracle_params(sph)
+    ohl = hl.copy()
+    sim.step(pos.copy(), vel.copy(), P, 1, highlight=ohl)
+    assert np.array_equal(out, ohl)
+    assert (out == 2).sum() > 30
+
+
+@pytest.mark.parametrize("n,bits", [(1, 8), (511, 20), (4096, 8), (4097, 13), (100000, 24), (1 << 20, 30), (3000001, 32)])
+def test_sort_pairs_stable(built_lib, n, bits):
+    import torch
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 1000:
+        keys[: n // 2] &= np.uint32(0xFF)   # heavy duplicates
+    vals = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    cap = max(512, (n + 511) // 512 * 512)
+    sph = pbf_b200.SPH(cap, (8, 8, 8))
+    kin = torch.from_numpy(keys.view(np.int32)).cuda(); vin = torch.from_numpy(vals.view(np.int32)).cuda()
+    kout = torch.empty_like(kin); vout = torch.empty_like(vin)
+    sph.sort_pairs(kin, vin, kout, vout, n, bits)
+    sph.sync()
+    mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
+    order = np.argsort(keys & mask, kind="stable")
+    assert np.array_equal(kout.cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(vout.cpu().numpy().view(np.uint32), vals[order])
+
+
+def test_long_run_traces(built_lib):
+    """100 steps of C1 (32^3, K=3): aggregate density error and kinetic energy traces within 1 %."""
+    sph, g, pos, vel = make()
+    sph.SetNumSolverIterations(3)
+    P = oracle_params(sph)
+    sim = oracle.Sim(pos.shape[0], g)
+    opos, ovel = pos.copy(), vel.copy()
+    ke_g, ke_o, de_g, de_o = [], [], [], []
+    for step in range(100):
+        sph.Run()
+        sim.step(opos, ovel, P, 3)
+        d, k = sph.diagnostics()
+        ke_g.append(k); de_g.append(d)
+        ke_o.append(oracle.kinetic_energy(ovel))
+        _, rho = oracle.calclambda(sim.sorted.copy(), sim.run_start.copy(), sim.run_count.copy(), P)
+        de_o.append(oracle.density_error(rho, P))
+    ke_g, ke_o, de_g, de_o = map(np.array, (ke_g, ke_o, de_g, de_o))
+    assert np.max(np.abs(ke_g - ke_o) / ke_o) < 0.01
+    assert np.max(np.abs(de_g - de_o) / de_o) < 0.01
+
+
+def test_errors(built_lib):
+    with pytest.raises(RuntimeError):
+        pbf_b200.SPH(1000)            # not a multiple of 512 (src/Simulation.cpp:202)
+    sph = pbf_b200.SPH(512, (16, 16, 16))
+    with pytest.raises(RuntimeError):
+        sph.sort()                    # stage order
+    with pytest.raises(RuntimeError):
+        sph.upload(np.zeros((100, 4), np.float32))
