@@ -186,7 +186,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     s->max_tiles = sort_max_tiles(cap);
     ALLOC(s->hist, 4 * PBF_RADIX); ALLOC(s->gbase, 4 * PBF_RADIX); ALLOC(s->tile_counter, 4);
     ALLOC(s->status, (size_t)4 * s->max_tiles * PBF_RADIX);
-    ALLOC(s->cells, s->ncell);
+    ALLOC(s->cells, s->ncell); ALLOC(s->runs3, s->ncell);
     ALLOC(s->bufA, cap); ALLOC(s->bufB, cap); ALLOC(s->svel, cap); ALLOC(s->vprime, cap); ALLOC(s->omega, cap);
     ALLOC(s->flags, 4); ALLOC(s->diag, 2);
 #undef ALLOC
@@ -197,8 +197,9 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     cudaMemsetAsync(s->hist, 0, 4 * PBF_RADIX * 4, s->stream);
     cudaMemsetAsync(s->tile_counter, 0, 16, s->stream);
     cudaMemsetAsync(s->flags, 0, 16, s->stream);
-    // start = -1 (gridtexture clear, src/NeighbourCellFinder.cpp:116-126), end = -1 likewise so a whole-table memset works
-    cudaMemsetAsync(s->cells, 0xff, s->ncell * sizeof(int2), s->stream);
+    for (float4 *b : {s->pred, s->bufA, s->bufB, s->svel, s->vprime, s->omega})   // pair loads may touch one slot of padding
+        cudaMemsetAsync(b, 0, (size_t)cap * 16 + 16, s->stream);
+    launch_fill_tables(s);   // start = -1 (gridtexture clear, src/NeighbourCellFinder.cpp:116-126), end = 0, runs empty
     for (int i = 0; i < 6; i++) cudaEventCreate(&s->ev[i]);
     e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) {
@@ -216,7 +217,7 @@ int pbf_destroy(pbf_handle s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     invalidate_graph(s);
     void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
-                    s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->bufA, s->bufB,
+                    s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->runs3, s->bufA, s->bufB,
                     s->svel, s->vprime, s->omega, s->flags, s->diag};
     for (void *p : ptrs)
         if (p) cudaFree(p);

@@ -62,6 +62,7 @@ struct pbf_sim {
     u32 max_tiles;
     // cell table {start,end} per cell (gridtexture / gridendtexture, src/NeighbourCellFinder.cpp:59-90)
     int2 *cells;
+    int2 *runs3;                          // per cell: cells x-1,x,x+1 merged {start,count} (neighbourcells.glsl:62-84)
     u32 n_prev_sorted;                    // slots of skey that describe the current table contents
     // solver state in sorted order
     float4 *bufA;                         // {x,y,z,-}   positions (Jacobi ping)
@@ -90,6 +91,7 @@ void pbf_set_error(const std::string &msg);
 
 // ---- launchers (each returns the number of kernels it enqueued; errors surface at the next PBF_CUDA) ----
 // sim_kernels.cu
+int launch_fill_tables(pbf_sim *s);
 int launch_unclear_cells(pbf_sim *s);
 int launch_predict(pbf_sim *s);
 int launch_reorder_cells(pbf_sim *s);
