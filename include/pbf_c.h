@@ -165,6 +165,26 @@ void *pbf_stream(pbf_handle h);
 int pbf_scene_dam_break(int nx, int ny, int nz, const float origin[3], float spacing, int mirror_xz,
                         uint32_t seed, uint32_t id0, float *pos4, float *vel4);
 
+/* ---- slab decomposition (multi GPU).  No counterpart in the reference (single GPU): this is
+ * the north star's slab runtime.  One handle per rank owns the particles whose cell layer z lies in [z_lo, z_hi); the
+ * handle must have been created with grid z = (z_hi - z_lo) + 2 (one ghost layer per face), positions stay global.
+ * pbf_slab_step runs SPH::Run with particle migration and halo exchange over NCCL send/recv on the handle's stream. */
+/* rank 0: create the 128-byte NCCL unique id; the host runtime broadcasts it (torch.distributed / MPI / files) */
+int pbf_slab_unique_id(void *out128);
+int pbf_slab_init(pbf_handle h, const void *id128, int rank, int nranks, int z_lo, int z_hi, int gz_global,
+                  uint32_t halo_capacity);
+/* "virtual ranks": n handles of ONE process on one device, stepped in lock step with device copies instead of
+ * NCCL (tests on a single GPU).  Rank r owns layers [z_planes[r], z_planes[r+1]). */
+int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_global, uint32_t halo_capacity);
+/* local particles of the slab (HOST arrays by slot) with their global ids; download returns the current owners */
+int pbf_slab_upload(pbf_handle h, const float *pos4, const float *vel4, const uint32_t *gid, uint32_t n);
+int pbf_slab_download(pbf_handle h, float *pos4, float *vel4, uint32_t *gid, uint32_t *n);
+/* with a virtual group, stepping any member steps the whole group */
+int pbf_slab_step(pbf_handle h, int nsteps);
+/* out: local particles, ghosts from z-, ghosts from z+, boundary sent to z-, to z+, migrated away (total),
+ * exchanges (total), bytes sent (total) */
+int pbf_slab_stats(pbf_handle h, uint64_t out[8]);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -74,6 +74,13 @@ def lib():
         L.pbf_scene_dam_break.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.pbf_sort_bits.argtypes = [C.POINTER(C.c_int32)]
+        L.pbf_slab_unique_id.argtypes = [C.c_void_p]
+        L.pbf_slab_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
+        L.pbf_slab_init_group.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_uint32]
+        L.pbf_slab_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.pbf_slab_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.pbf_slab_step.argtypes = [C.c_void_p, C.c_int]
+        L.pbf_slab_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 

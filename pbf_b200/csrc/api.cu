@@ -164,6 +164,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     }
     s->grid.ref_quirks = cfg->ref_quirks;
     s->grid.bx = bx; s->grid.bz = bz;
+    s->grid.zoff = 0; s->grid.gz_global = cfg->grid[2];
     s->plan = make_sort_plan(sortbits);
     pbf_default_params(&s->params);
 
@@ -214,7 +215,10 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
 int pbf_destroy(pbf_handle s) {
     if (!s) return PBF_OK;
     DeviceGuard guard(s->device);
+    const bool shared_stream = slab_borrows_stream(s);   // virtual ranks > 0 borrow rank 0's stream
+    if (shared_stream) { cudaDeviceSynchronize(); s->stream = nullptr; }
     if (s->stream) cudaStreamSynchronize(s->stream);
+    slab_free(s);
     invalidate_graph(s);
     void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
                     s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->runs3, s->bufA, s->bufB,

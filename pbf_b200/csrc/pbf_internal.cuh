@@ -20,6 +20,9 @@ struct GridInfo {
     float wlo[3], whi[3];  // clamp bounds of updatepos.glsl:98-100: wall, GRID_SIZE - wall
     int ref_quirks;
     int bx, bz;            // bit widths of the packed home cell (x | z << bx | y << (bx+bz))
+    // slab window (multi GPU): this handle's cell images cover global cell layers [zoff, zoff + gz) of a domain that is
+    // gz_global layers deep; a single-GPU handle has zoff = 0, gz_global = gz.  Positions are always global.
+    int zoff, gz_global;
 };
 
 // the std140 SPHParameters block (src/SPH.cpp:46-56) + the extforce uniform (predictpos.glsl:13)
@@ -76,6 +79,7 @@ struct pbf_sim {
     bool timing; cudaEvent_t ev[6]; bool ev_valid;
     uint64_t launches;
     int stage;                            // 0 idle, 1 predicted, 2 sorted, 3 cells built
+    struct pbf_slab_state *slab;          // non-null once pbf_slab_init has run (slab.cu)
 };
 
 // error plumbing (api.cu)
@@ -94,19 +98,27 @@ void pbf_set_error(const std::string &msg);
 int launch_fill_tables(pbf_sim *s);
 int launch_unclear_cells(pbf_sim *s);
 int launch_predict(pbf_sim *s);
+int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist);
+int launch_keys_only(pbf_sim *s, u32 first, u32 count);
 int launch_reorder_cells(pbf_sim *s);
 int launch_highlight(pbf_sim *s);
 int launch_lambda(pbf_sim *s);
 int launch_delta_p(pbf_sim *s);
 int launch_update(pbf_sim *s);
 int launch_vorticity(pbf_sim *s);
+int launch_vorticity_a(pbf_sim *s);
+int launch_vorticity_b(pbf_sim *s);
 int launch_density_diag(pbf_sim *s);
 int launch_kinetic_diag(pbf_sim *s);
 int launch_compose_records(pbf_sim *s, float4 *out);
 int launch_neighbour_runs(pbf_sim *s, int *run_start, int *run_count);
+// slab.cu
+void slab_free(pbf_sim *s);
+bool slab_borrows_stream(const pbf_sim *s);
 // sort.cu
 SortPlan make_sort_plan(int bits);
 u32 sort_max_tiles(u32 cap);
 int launch_sort_scan(pbf_sim *s);
 int launch_sort_passes(pbf_sim *s);
+int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n);
 int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, int bits);

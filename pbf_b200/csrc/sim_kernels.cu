@@ -37,15 +37,16 @@ __device__ __forceinline__ u32 cell_key(float x, float y, float z, const GridInf
     // ivec3(clamp(pos, 0, GRID_SIZE)) . (1, gx*gz, gx)   (counting.glsl:53-57); clamp is inclusive
     int cx = (int)fminf(fmaxf(x, 0.0f), (float)g.gx);
     int cy = (int)fminf(fmaxf(y, 0.0f), (float)g.gy);
-    int cz = (int)fminf(fmaxf(z, 0.0f), (float)g.gz);
+    const int czg = (int)fminf(fmaxf(z, 0.0f), (float)g.gz_global);   // global cell layer
+    const int cz = min(max(czg - g.zoff, 0), g.gz);                  // layer inside this handle's window
     u32 k = (u32)cx + (u32)cz * (u32)g.gx + (u32)cy * (u32)g.gxgz;
-    if (cx >= g.gx || cy >= g.gy || cz >= g.gz) k |= PBF_KEY_NOCELL;
+    if (cx >= g.gx || cy >= g.gy || cz >= g.gz || czg >= g.gz_global || czg < g.zoff) k |= PBF_KEY_NOCELL;
     return k;
 }
 
 // ---- K1 predictpos.glsl:18-38 + cell key + digit histograms of every sort pass + clearhighlight.glsl ----------
 __global__ void __launch_bounds__(256)
-k_predict(u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
+k_predict(u32 first, u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
           float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ hist, u32 *__restrict__ flags,
           GridInfo g, SimParams P, SortPlan plan) {
     __shared__ u32 sh[4 * PBF_RADIX];
@@ -55,8 +56,9 @@ k_predict(u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
     const u32 stride = gridDim.x * blockDim.x;
     const u32 nround = (n + 31u) & ~31u;
     bool any_hl = false;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        const bool valid = i < n;
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += stride) {
+        const bool valid = j < n;
+        const u32 i = first + j;
         u32 key = 0;
         if (valid) {
             float4 p = pos[i];
@@ -77,7 +79,7 @@ k_predict(u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
             if (h & ~1u) hl[i] = h & 1u;
             any_hl |= (h & 1u) != 0;
         }
-        for (int p = 0; p < plan.passes; p++) {
+        for (int p = 0; p < plan.passes; p++) {    // plan.passes = 0: the caller histograms later (slab mode)
             u32 d = valid ? ((key >> plan.shift[p]) & plan.mask[p]) : 0xffffffffu;
             u32 m = __match_any_sync(0xffffffffu, d);
             if (valid && lane == (u32)(__ffs(m) - 1)) atomicAdd(&sh[p * PBF_RADIX + d], (u32)__popc(m));
@@ -87,6 +89,15 @@ k_predict(u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel,
     __syncthreads();
     for (int i = threadIdx.x; i < plan.passes * PBF_RADIX; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+// appended halo records already hold p*: cell keys only
+__global__ void __launch_bounds__(256)
+k_keys_only(u32 first, u32 count, const float4 *__restrict__ pred, u32 *__restrict__ keys, GridInfo g) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    float4 p = pred[first + j];
+    keys[first + j] = cell_key(p.x, p.y, p.z, g);
 }
 
 // ---- cell tables ------------------------------------------------------------------------------------------------------
@@ -120,7 +131,7 @@ k_unclear_cells(u32 n, const u32 *__restrict__ skey, int2 *__restrict__ cells, i
 __device__ __forceinline__ u32 pack_home(float x, float y, float z, const GridInfo &g) {
     int cx = min(max((int)x, -2), g.gx + 1) + 2;
     int cy = min(max((int)y, -2), g.gy + 1) + 2;
-    int cz = min(max((int)z, -2), g.gz + 1) + 2;
+    int cz = min(max((int)z - g.zoff, -2), g.gz + 1) + 2;
     return (u32)cx | ((u32)cz << g.bx) | ((u32)cy << (g.bx + g.bz));
 }
 
@@ -560,12 +571,23 @@ int launch_unclear_cells(pbf_sim *s) {
     return 1;
 }
 
-int launch_predict(pbf_sim *s) {
-    int blocks = nblocks(s->n, 256);
+int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist) {
+    if (count == 0) return 0;
+    int blocks = nblocks(count, 256);
     int maxb = s->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
-    k_predict<<<blocks, 256, 0, s->stream>>>(s->n, s->pos, s->vel, s->hl, s->pred, s->keys, s->hist, s->flags, s->grid,
-                                             sim_params(s), s->plan);
+    SortPlan plan = s->plan;
+    if (!with_hist) plan.passes = 0;
+    k_predict<<<blocks, 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->hist, s->flags,
+                                             s->grid, sim_params(s), plan);
+    return 1;
+}
+
+int launch_predict(pbf_sim *s) { return launch_predict_range(s, 0, s->n, true); }
+
+int launch_keys_only(pbf_sim *s, u32 first, u32 count) {
+    if (count == 0) return 0;
+    k_keys_only<<<nblocks(count, 256), 256, 0, s->stream>>>(first, count, s->pred, s->keys, s->grid);
     return 1;
 }
 
@@ -605,15 +627,21 @@ int launch_update(pbf_sim *s) {
     return 1;
 }
 
-int launch_vorticity(pbf_sim *s) {
+int launch_vorticity_a(pbf_sim *s) {
     k_vorticity_a<<<nblocks(s->n, NB_BLOCK), NB_BLOCK, 0, s->stream>>>(s->n, s->bufA, s->svel, s->home, s->runs3,
                                                                        s->cells, s->bufB, s->vprime, s->omega, s->grid,
                                                                        sim_params(s));
+    return 1;
+}
+
+int launch_vorticity_b(pbf_sim *s) {
     k_vorticity_b<<<nblocks(s->n, NB_BLOCK), NB_BLOCK, 0, s->stream>>>(s->n, s->bufB, s->vprime, s->omega, s->perm,
                                                                        s->home, s->runs3, s->cells, s->vel, s->grid,
                                                                        sim_params(s));
-    return 2;
+    return 1;
 }
+
+int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s) + launch_vorticity_b(s); }
 
 int launch_density_diag(pbf_sim *s) {
     k_lambda<true><<<nblocks(s->n, NB_BLOCK), NB_BLOCK, 0, s->stream>>>(s->n, s->bufA, s->home, s->runs3, s->cells,

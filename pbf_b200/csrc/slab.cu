@@ -1,0 +1,702 @@
+// slab.cu -- multi-GPU runtime: 1-D slab decomposition along z with one-cell-layer halos and particle migration.
+//
+// The reference is single GPU; this is the north star's "slab-decomposed across the 8xB200 box, with
+// halo particle exchange and migration over NVLink via NCCL send/recv between solver iterations".  Facts it rests on:
+//  * the neighbour stencil is exactly +-1 cell (neighbourcells.glsl:37-50), so ONE ghost layer per slab face reproduces
+//    the single-GPU arithmetic;
+//  * the cell key is y-major with x minor (GRID_HASHWEIGHTS = (1, gx*gz, gx), src/SPH.cpp:31), so cutting along z keeps
+//    every 3-cell x-window contiguous and the merged-run machinery of sim_kernels.cu works unchanged inside a slab.
+//
+// A rank owns the global cell layers [z_lo, z_hi); its cell tables cover [z_lo-1, z_hi+1) (GridInfo::zoff).  Per step:
+//   predict -> migrate (particles whose predicted cell left the slab move to the +-1 neighbour, 64 B records)
+//           -> ghosts  (owners send the predicted + old position of their boundary-layer particles, 32 B records;
+//                       the receiver appends them after its local particles and sorts them with everything else)
+//           -> sort, cells -> K x [lambda, halo lambda (4 B), delta-p, halo position (16 B)]
+//           -> update -> vorticity A, halo |omega| (4 B), vorticity B.
+// Ghost slots are computed like any other particle and then overwritten by the owner's values, so every kernel of the
+// single-GPU path is reused as is.  Two host synchronisations per step (the migration and ghost counts size the
+// launches); everything else is stream ordered.
+//
+// Transport: NCCL send/recv on the handle's stream (one process per GPU, communicator bootstrapped from a unique id the
+// host runtime broadcasts), or -- for tests on one GPU -- "virtual ranks": several handles of one process stepped in
+// lock step with device-to-device copies in place of NCCL.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include <vector>
+
+#include "pbf_internal.cuh"
+
+#define LEAVER 0xffffffffu
+
+struct MigRec {   // 64 B
+    float4 pos, vel, pred;
+    u32 gid, hl, pad0, pad1;
+};
+struct GhostRec {   // 32 B
+    float4 pred, old;
+};
+
+struct NcclApi {
+    void *lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
+    const char *(*GetErrorString)(ncclResult_t);
+};
+
+struct pbf_slab_state {
+    int rank, nranks, z_lo, z_hi;
+    bool has[2];                 // neighbour on the z- / z+ side
+    u32 halo_cap;
+    ncclComm_t comm;
+    pbf_sim **group;             // virtual ranks (same process, same stream); null with NCCL
+    int group_size;
+    u32 n_local, n_ghost[2], n_bnd[2];
+    u32 *gid, *btag;
+    u32 *list[4];                // leave lo/hi, boundary lo/hi: slot indices
+    u32 *movers, *holes;
+    u32 *counters, *h_counters;  // [0..3] list counts, [4] movers, [5] holes, [8..9] incoming (from lo, from hi)
+    char *send[2], *recv[2];
+    u32 *send_idx[2], *ghost_sorted;
+    uint64_t migrated, exchanges, bytes_sent;
+};
+
+namespace {
+
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.lib) return PBF_OK;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        pbf_set_error(std::string("slab: cannot load libnccl.so.2: ") + dlerror());
+        return PBF_ERR_NCCL;
+    }
+#define SYM(field, name)                                                          \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                                 \
+    if (!g_nccl.field) { pbf_set_error("slab: libnccl lacks " name); return PBF_ERR_NCCL; }
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = lib;
+    return PBF_OK;
+}
+
+#define PBF_NCCL(call)                                                                          \
+    do {                                                                                        \
+        ncclResult_t r_ = (call);                                                               \
+        if (r_ != ncclSuccess) {                                                                \
+            pbf_set_error(std::string(#call) + ": " + g_nccl.GetErrorString(r_));               \
+            return PBF_ERR_NCCL;                                                                \
+        }                                                                                       \
+    } while (0)
+
+__device__ __forceinline__ int global_layer(float z, const GridInfo &g) {
+    return (int)fminf(fmaxf(z, 0.0f), (float)g.gz_global);
+}
+
+// which local particles left the slab with their predicted position (predictpos.glsl:34)
+__global__ void __launch_bounds__(256)
+k_mark_leavers(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, int z_hi, bool has_lo, bool has_hi,
+               u32 *__restrict__ btag, u32 *__restrict__ leave_lo, u32 *__restrict__ leave_hi, u32 *__restrict__ cnt,
+               u32 cap) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int cz = global_layer(pred[s].z, g);
+    u32 tag = 0;
+    if (has_lo && cz < z_lo) {
+        u32 k = atomicAdd(&cnt[0], 1u);
+        if (k < cap) leave_lo[k] = s;
+        tag = LEAVER;
+    } else if (has_hi && cz >= z_hi) {
+        u32 k = atomicAdd(&cnt[1], 1u);
+        if (k < cap) leave_hi[k] = s;
+        tag = LEAVER;
+    }
+    btag[s] = tag;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_migrants(const u32 *__restrict__ cnt, u32 cap, const u32 *__restrict__ list, const float4 *__restrict__ pos,
+                const float4 *__restrict__ vel, const float4 *__restrict__ pred, const u32 *__restrict__ gid,
+                const u32 *__restrict__ hl, MigRec *__restrict__ out) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min(*cnt, cap)) return;
+    u32 s = list[k];
+    MigRec r;
+    r.pos = pos[s]; r.vel = vel[s]; r.pred = pred[s]; r.gid = gid[s]; r.hl = hl[s]; r.pad0 = r.pad1 = 0;
+    out[k] = r;
+}
+
+// compaction after the leavers are gone: stayers of the tail [n_stay, n) fill the holes below n_stay
+__global__ void __launch_bounds__(256)
+k_find_movers(u32 n_stay, u32 n, const u32 *__restrict__ btag, u32 *__restrict__ movers, u32 *__restrict__ cnt) {
+    u32 s = n_stay + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    if (btag[s] != LEAVER) movers[atomicAdd(&cnt[4], 1u)] = s;
+}
+__global__ void __launch_bounds__(256)
+k_find_holes(u32 n_stay, u32 count, const u32 *__restrict__ list, u32 *__restrict__ holes, u32 *__restrict__ cnt) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    u32 s = list[k];
+    if (s < n_stay) holes[atomicAdd(&cnt[5], 1u)] = s;
+}
+__global__ void __launch_bounds__(256)
+k_fill_holes(const u32 *__restrict__ cnt, const u32 *__restrict__ holes, const u32 *__restrict__ movers, float4 *pos,
+             float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt[5]) return;
+    u32 d = holes[k], s = movers[k];
+    pos[d] = pos[s]; vel[d] = vel[s]; gid[d] = gid[s]; hl[d] = hl[s]; keys[d] = keys[s];
+    float4 p = pred[s];
+    p.w = __int_as_float((int)d);
+    pred[d] = p;
+}
+
+__device__ __forceinline__ u32 window_key(float x, float y, float z, const GridInfo &g) {   // = cell_key of sim_kernels.cu
+    int cx = (int)fminf(fmaxf(x, 0.0f), (float)g.gx);
+    int cy = (int)fminf(fmaxf(y, 0.0f), (float)g.gy);
+    const int czg = global_layer(z, g);
+    const int cz = min(max(czg - g.zoff, 0), g.gz);
+    u32 k = (u32)cx + (u32)cz * (u32)g.gx + (u32)cy * (u32)g.gxgz;
+    if (cx >= g.gx || cy >= g.gy || cz >= g.gz || czg >= g.gz_global || czg < g.zoff) k |= PBF_KEY_NOCELL;
+    return k;
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_migrants(u32 count, u32 base, const MigRec *__restrict__ in, float4 *pos, float4 *vel, float4 *pred, u32 *gid,
+                  u32 *hl, u32 *keys, GridInfo g) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    MigRec r = in[k];
+    u32 s = base + k;
+    pos[s] = r.pos; vel[s] = r.vel; gid[s] = r.gid; hl[s] = r.hl;
+    r.pred.w = __int_as_float((int)s);
+    pred[s] = r.pred;
+    keys[s] = window_key(r.pred.x, r.pred.y, r.pred.z, g);
+}
+
+// boundary layers z_lo and z_hi-1: their particles are the neighbours' ghosts
+__global__ void __launch_bounds__(256)
+k_mark_boundary(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, int z_hi, bool has_lo, bool has_hi,
+                u32 *__restrict__ btag, u32 *__restrict__ bnd_lo, u32 *__restrict__ bnd_hi, u32 *__restrict__ cnt, u32 cap) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int cz = global_layer(pred[s].z, g);
+    u32 tag = 0;
+    if (has_lo && cz == z_lo) {
+        u32 k = atomicAdd(&cnt[2], 1u);
+        if (k < cap) { bnd_lo[k] = s; tag = k + 1u; }
+    } else if (has_hi && cz == z_hi - 1) {
+        u32 k = atomicAdd(&cnt[3], 1u);
+        if (k < cap) { bnd_hi[k] = s; tag = 0x80000000u | (k + 1u); }
+    }
+    btag[s] = tag;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_ghosts(u32 count, const u32 *__restrict__ list, const float4 *__restrict__ pred, const float4 *__restrict__ pos,
+              GhostRec *__restrict__ out) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    u32 s = list[k];
+    GhostRec r;
+    r.pred = pred[s];
+    r.old = pos[s];
+    out[k] = r;
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *pos, float4 *vel, float4 *pred, u32 *hl,
+                u32 *keys, GridInfo g) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    GhostRec r = in[k];
+    u32 s = base + k;
+    pos[s] = r.old;                          // so that k_update derives the ghost's velocity like any other particle's
+    vel[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    hl[s] = 0u;
+    r.pred.w = __int_as_float((int)s);
+    pred[s] = r.pred;
+    keys[s] = window_key(r.pred.x, r.pred.y, r.pred.z, g);
+}
+
+// after the sort: where did the boundary particles (to pack) and the ghosts (to overwrite) land?
+__global__ void __launch_bounds__(256)
+k_halo_index(u32 n, u32 n_local, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
+             u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, GridInfo g) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 k = skey[i] & ~PBF_KEY_NOCELL;
+    const int cz = (int)((k % (u32)g.gxgz) / (u32)g.gx);
+    if (cz > 1 && cz < g.gz - 2) return;     // interior layer: neither ghost nor boundary
+    const u32 id = perm[i];
+    if (id >= n_local) { ghost_sorted[id - n_local] = i; return; }
+    const u32 t = btag[id];
+    if (t == 0) return;
+    if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
+    else send_lo[t - 1u] = i;
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_w(u32 n, const u32 *__restrict__ idx, const float4 *__restrict__ buf, float *__restrict__ out) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = buf[idx[k]].w;
+}
+__global__ void __launch_bounds__(256)
+k_scatter_w(u32 n, const u32 *__restrict__ idx, const float *__restrict__ in, float4 *__restrict__ buf) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) buf[idx[k]].w = in[k];
+}
+__global__ void __launch_bounds__(256)
+k_gather_p(u32 n, const u32 *__restrict__ idx, const float4 *__restrict__ buf, float4 *__restrict__ out) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = buf[idx[k]];
+}
+__global__ void __launch_bounds__(256)
+k_scatter_p(u32 n, const u32 *__restrict__ idx, const float4 *__restrict__ in, float4 *__restrict__ buf) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) buf[idx[k]] = in[k];
+}
+
+inline int nb(u32 n) { return (int)((n + 255) / 256); }
+
+// ---- transport -------------------------------------------------------------------------------------------------------
+// every rank of `grp` has packed send[0] (to z-) / send[1] (to z+); deliver into the neighbours' recv[1] / recv[0]
+int exchange(pbf_sim **grp, int ng, const size_t sbytes[][2], const size_t rbytes[][2]) {
+    if (grp[0]->slab->group) {                     // virtual ranks: one stream, plain copies
+        for (int r = 0; r < ng; r++) {
+            pbf_slab_state *b = grp[r]->slab;
+            if (b->has[0] && rbytes[r][0])
+                PBF_CUDA(cudaMemcpyAsync(b->recv[0], grp[r - 1]->slab->send[1], rbytes[r][0], cudaMemcpyDeviceToDevice, grp[r]->stream));
+            if (b->has[1] && rbytes[r][1])
+                PBF_CUDA(cudaMemcpyAsync(b->recv[1], grp[r + 1]->slab->send[0], rbytes[r][1], cudaMemcpyDeviceToDevice, grp[r]->stream));
+            b->exchanges++;
+            b->bytes_sent += sbytes[r][0] + sbytes[r][1];
+        }
+        return PBF_OK;
+    }
+    pbf_sim *s = grp[0];
+    pbf_slab_state *b = s->slab;
+    PBF_NCCL(g_nccl.GroupStart());
+    for (int side = 0; side < 2; side++) {
+        if (!b->has[side]) continue;
+        const int peer = b->rank + (side ? 1 : -1);
+        if (sbytes[0][side]) PBF_NCCL(g_nccl.Send(b->send[side], sbytes[0][side], ncclChar, peer, b->comm, s->stream));
+        if (rbytes[0][side]) PBF_NCCL(g_nccl.Recv(b->recv[side], rbytes[0][side], ncclChar, peer, b->comm, s->stream));
+    }
+    PBF_NCCL(g_nccl.GroupEnd());
+    b->exchanges++;
+    b->bytes_sent += sbytes[0][0] + sbytes[0][1];
+    return PBF_OK;
+}
+
+// host-visible counts: out[r] = {to lo, to hi}, in[r] = {from lo, from hi}; `which` selects counters [0,1] or [2,3]
+int exchange_counts(pbf_sim **grp, int ng, int which, u32 out[][2], u32 in[][2]) {
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        if (!b->group) {
+            PBF_NCCL(g_nccl.GroupStart());
+            for (int side = 0; side < 2; side++) {
+                if (!b->has[side]) continue;
+                const int peer = b->rank + (side ? 1 : -1);
+                PBF_NCCL(g_nccl.Send(b->counters + 2 * which + side, 1, ncclUint32, peer, b->comm, s->stream));
+                PBF_NCCL(g_nccl.Recv(b->counters + 8 + side, 1, ncclUint32, peer, b->comm, s->stream));
+            }
+            PBF_NCCL(g_nccl.GroupEnd());
+        }
+        PBF_CUDA(cudaMemcpyAsync(b->h_counters + 16 * 0, b->counters, 16 * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    }
+    for (int r = 0; r < ng; r++) PBF_CUDA(cudaStreamSynchronize(grp[r]->stream));
+    for (int r = 0; r < ng; r++) {
+        pbf_slab_state *b = grp[r]->slab;
+        for (int side = 0; side < 2; side++) {
+            out[r][side] = b->has[side] ? b->h_counters[2 * which + side] : 0;
+            if (out[r][side] > b->halo_cap) {
+                pbf_set_error("slab: halo capacity exceeded (raise halo_capacity in pbf_slab_init)");
+                return PBF_ERR_CAPACITY;
+            }
+        }
+    }
+    for (int r = 0; r < ng; r++) {
+        pbf_slab_state *b = grp[r]->slab;
+        if (b->group) {
+            in[r][0] = b->has[0] ? out[r - 1][1] : 0;
+            in[r][1] = b->has[1] ? out[r + 1][0] : 0;
+        } else {
+            in[r][0] = b->has[0] ? b->h_counters[8] : 0;
+            in[r][1] = b->has[1] ? b->h_counters[9] : 0;
+        }
+        if (in[r][0] > b->halo_cap || in[r][1] > b->halo_cap) {
+            pbf_set_error("slab: incoming halo exceeds capacity");
+            return PBF_ERR_CAPACITY;
+        }
+    }
+    return PBF_OK;
+}
+
+// refresh one 4-byte (.w of bufB) or 16-byte (bufA) quantity of every ghost from its owner
+int halo_refresh(pbf_sim **grp, int ng, bool wide) {
+    const size_t esz = wide ? 16 : 4;
+    std::vector<size_t> sb(2 * ng), rb(2 * ng);
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        for (int side = 0; side < 2; side++) {
+            const u32 n = b->n_bnd[side];
+            sb[2 * r + side] = n * esz;
+            rb[2 * r + side] = b->n_ghost[side] * esz;
+            if (!n) continue;
+            if (wide) k_gather_p<<<nb(n), 256, 0, s->stream>>>(n, b->send_idx[side], s->bufA, (float4 *)b->send[side]);
+            else k_gather_w<<<nb(n), 256, 0, s->stream>>>(n, b->send_idx[side], s->bufB, (float *)b->send[side]);
+            s->launches++;
+        }
+    }
+    int rc = exchange(grp, ng, (const size_t(*)[2])sb.data(), (const size_t(*)[2])rb.data());
+    if (rc) return rc;
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        u32 off = 0;
+        for (int side = 0; side < 2; side++) {
+            const u32 n = b->n_ghost[side];
+            if (n) {
+                if (wide) k_scatter_p<<<nb(n), 256, 0, s->stream>>>(n, b->ghost_sorted + off, (const float4 *)b->recv[side], s->bufA);
+                else k_scatter_w<<<nb(n), 256, 0, s->stream>>>(n, b->ghost_sorted + off, (const float *)b->recv[side], s->bufB);
+                s->launches++;
+            }
+            off += n;
+        }
+    }
+    return PBF_OK;
+}
+
+int slab_step(pbf_sim **grp, int ng) {
+    std::vector<u32> out(2 * ng), in(2 * ng);
+    u32(*O)[2] = (u32(*)[2])out.data();
+    u32(*I)[2] = (u32(*)[2])in.data();
+    std::vector<size_t> sb(2 * ng), rb(2 * ng);
+    int rc;
+    // ---- predict + who leaves -----------------------------------------------------------------------------------
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        cudaMemsetAsync(s->flags, 0, sizeof(u32), s->stream);
+        cudaMemsetAsync(b->counters, 0, 16 * sizeof(u32), s->stream);
+        s->launches += launch_unclear_cells(s);
+        s->n = b->n_local;
+        s->launches += launch_predict_range(s, 0, b->n_local, false);
+        if (b->n_local) {
+            k_mark_leavers<<<nb(b->n_local), 256, 0, s->stream>>>(b->n_local, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0],
+                                                                   b->has[1], b->btag, b->list[0], b->list[1], b->counters,
+                                                                   b->halo_cap);
+            for (int side = 0; side < 2; side++)
+                if (b->has[side])
+                    k_pack_migrants<<<nb(b->halo_cap), 256, 0, s->stream>>>(b->counters + side, b->halo_cap, b->list[side], s->pos,
+                                                                             s->vel, s->pred, b->gid, s->hl, (MigRec *)b->send[side]);
+            s->launches += 3;
+        }
+    }
+    if ((rc = exchange_counts(grp, ng, 0, O, I))) return rc;
+    for (int r = 0; r < ng; r++)
+        for (int side = 0; side < 2; side++) {
+            sb[2 * r + side] = (size_t)O[r][side] * sizeof(MigRec);
+            rb[2 * r + side] = (size_t)I[r][side] * sizeof(MigRec);
+        }
+    if ((rc = exchange(grp, ng, (const size_t(*)[2])sb.data(), (const size_t(*)[2])rb.data()))) return rc;
+    // ---- compact, append arrivals, mark the boundary layers ---------------------------------------------------------
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        const u32 n_leave = O[r][0] + O[r][1], n_arrive = I[r][0] + I[r][1];
+        const u32 n_stay = b->n_local - n_leave;
+        if (n_stay + n_arrive > s->cap) {
+            pbf_set_error("slab: particle capacity exceeded after migration");
+            return PBF_ERR_CAPACITY;
+        }
+        if (n_leave) {
+            k_find_movers<<<nb(n_leave), 256, 0, s->stream>>>(n_stay, b->n_local, b->btag, b->movers, b->counters);
+            for (int side = 0; side < 2; side++)
+                if (O[r][side])
+                    k_find_holes<<<nb(O[r][side]), 256, 0, s->stream>>>(n_stay, O[r][side], b->list[side], b->holes, b->counters);
+            k_fill_holes<<<nb(n_leave), 256, 0, s->stream>>>(b->counters, b->holes, b->movers, s->pos, s->vel, s->pred, b->gid,
+                                                             s->hl, s->keys);
+            s->launches += 4;
+        }
+        u32 base = n_stay;
+        for (int side = 0; side < 2; side++) {
+            if (I[r][side]) {
+                k_unpack_migrants<<<nb(I[r][side]), 256, 0, s->stream>>>(I[r][side], base, (const MigRec *)b->recv[side], s->pos,
+                                                                          s->vel, s->pred, b->gid, s->hl, s->keys, s->grid);
+                s->launches++;
+            }
+            base += I[r][side];
+        }
+        b->n_local = n_stay + n_arrive;
+        b->migrated += n_leave;
+        if (b->n_local) {
+            k_mark_boundary<<<nb(b->n_local), 256, 0, s->stream>>>(b->n_local, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0],
+                                                                    b->has[1], b->btag, b->list[2], b->list[3], b->counters,
+                                                                    b->halo_cap);
+            s->launches++;
+        }
+    }
+    if ((rc = exchange_counts(grp, ng, 1, O, I))) return rc;
+    // ---- ghosts -----------------------------------------------------------------------------------------------------------
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        for (int side = 0; side < 2; side++) {
+            b->n_bnd[side] = O[r][side];
+            b->n_ghost[side] = I[r][side];
+            sb[2 * r + side] = (size_t)O[r][side] * sizeof(GhostRec);
+            rb[2 * r + side] = (size_t)I[r][side] * sizeof(GhostRec);
+            if (O[r][side]) {
+                k_pack_ghosts<<<nb(O[r][side]), 256, 0, s->stream>>>(O[r][side], b->list[2 + side], s->pred, s->pos,
+                                                                      (GhostRec *)b->send[side]);
+                s->launches++;
+            }
+        }
+        if (b->n_local + I[r][0] + I[r][1] > s->cap) {
+            pbf_set_error("slab: particle capacity exceeded by the halo");
+            return PBF_ERR_CAPACITY;
+        }
+    }
+    if ((rc = exchange(grp, ng, (const size_t(*)[2])sb.data(), (const size_t(*)[2])rb.data()))) return rc;
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        u32 base = b->n_local;
+        for (int side = 0; side < 2; side++) {
+            if (b->n_ghost[side]) {
+                k_unpack_ghosts<<<nb(b->n_ghost[side]), 256, 0, s->stream>>>(b->n_ghost[side], base, (const GhostRec *)b->recv[side],
+                                                                              s->pos, s->vel, s->pred, s->hl, s->keys, s->grid);
+                s->launches++;
+            }
+            base += b->n_ghost[side];
+        }
+        // ---- sort + cells over local + ghost particles ------------------------------------------------------------------
+        s->n = base;
+        s->launches += launch_sort_hist(s, s->keys, s->n);
+        s->launches += launch_sort_scan(s);
+        s->launches += launch_sort_passes(s);
+        s->launches += launch_reorder_cells(s);
+        if (b->n_ghost[0] + b->n_ghost[1] + b->n_bnd[0] + b->n_bnd[1]) {
+            k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(s->n, b->n_local, s->skey, s->perm, b->btag, b->send_idx[0],
+                                                          b->send_idx[1], b->ghost_sorted, s->grid);
+            s->launches++;
+        }
+        s->launches += launch_highlight(s);
+    }
+    // ---- solver: K x [lambda, halo lambda, delta-p, halo positions] ---------------------------------------------------------
+    const int K = grp[0]->params.num_solver_iterations;
+    for (int it = 0; it < K; it++) {
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_lambda(grp[r]);
+        if ((rc = halo_refresh(grp, ng, false))) return rc;
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_delta_p(grp[r]);
+        if ((rc = halo_refresh(grp, ng, true))) return rc;
+    }
+    // ---- update, vorticity ----------------------------------------------------------------------------------------------------
+    for (int r = 0; r < ng; r++) grp[r]->launches += launch_update(grp[r]);
+    if (grp[0]->params.vorticity_confinement) {
+        for (int r = 0; r < ng; r++) {
+            pbf_sim *s = grp[r];
+            launch_vorticity_a(s);
+            s->launches++;
+        }
+        if ((rc = halo_refresh(grp, ng, false))) return rc;     // |omega| lives in bufB.w like lambda did
+        for (int r = 0; r < ng; r++) {
+            launch_vorticity_b(grp[r]);
+            grp[r]->launches++;
+        }
+    }
+    for (int r = 0; r < ng; r++) {
+        grp[r]->n = grp[r]->slab->n_local;
+        grp[r]->stage = 0;
+        PBF_CUDA(cudaGetLastError());
+    }
+    return PBF_OK;
+}
+
+int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_global, u32 halo_cap) {
+    if (s->slab) { pbf_set_error("slab: already initialised"); return PBF_ERR_STATE; }
+    if (z_hi - z_lo < 2) { pbf_set_error("slab: a slab must own at least 2 cell layers"); return PBF_ERR_INVALID; }
+    if (z_hi - z_lo + 2 != s->grid.gz) {
+        pbf_set_error("slab: the handle's grid z extent must be (z_hi - z_lo) + 2 ghost layers");
+        return PBF_ERR_INVALID;
+    }
+    if (rank < 0 || rank >= nranks || halo_cap == 0) { pbf_set_error("slab: bad rank or halo capacity"); return PBF_ERR_INVALID; }
+    pbf_slab_state *b = new pbf_slab_state();
+    memset((void *)b, 0, sizeof(*b));
+    b->rank = rank; b->nranks = nranks; b->z_lo = z_lo; b->z_hi = z_hi;
+    b->has[0] = rank > 0; b->has[1] = rank + 1 < nranks;
+    b->halo_cap = halo_cap;
+    b->n_local = s->n;
+    s->grid.zoff = z_lo - 1;
+    s->grid.gz_global = gz_global;
+    s->grid.ref_quirks = 0;     // the lowest-key-cell quirk is a single-domain artefact (findcells.glsl:39-43)
+    s->grid.whi[2] = (float)gz_global - s->cfg.wall[2];
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void **)&b->gid, (size_t)s->cap * 4); A((void **)&b->btag, (size_t)s->cap * 4);
+    for (int i = 0; i < 4; i++) A((void **)&b->list[i], (size_t)halo_cap * 4);
+    A((void **)&b->movers, (size_t)2 * halo_cap * 4); A((void **)&b->holes, (size_t)2 * halo_cap * 4);
+    A((void **)&b->counters, 16 * 4);
+    for (int i = 0; i < 2; i++) {
+        A((void **)&b->send[i], (size_t)halo_cap * sizeof(MigRec));
+        A((void **)&b->recv[i], (size_t)halo_cap * sizeof(MigRec));
+        A((void **)&b->send_idx[i], (size_t)halo_cap * 4);
+    }
+    A((void **)&b->ghost_sorted, (size_t)2 * halo_cap * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_counters, 16 * 4);
+    if (e != cudaSuccess) { pbf_set_error(std::string("slab: allocation failed: ") + cudaGetErrorString(e)); return PBF_ERR_CUDA; }
+    cudaMemsetAsync(b->gid, 0, (size_t)s->cap * 4, s->stream);
+    s->slab = b;
+    if (s->graph_valid) { cudaGraphExecDestroy(s->graph_exec); cudaGraphDestroy(s->graph); s->graph_valid = false; s->graph = nullptr; s->graph_exec = nullptr; }
+    return PBF_OK;
+}
+
+}  // namespace
+
+bool slab_borrows_stream(const pbf_sim *s) { return s->slab && s->slab->group && s->slab->rank != 0; }
+
+void slab_free(pbf_sim *s) {
+    pbf_slab_state *b = s->slab;
+    if (!b) return;
+    if (b->comm && g_nccl.lib) g_nccl.CommDestroy(b->comm);
+    void *ptrs[] = {b->gid, b->btag, b->list[0], b->list[1], b->list[2], b->list[3], b->movers, b->holes, b->counters, b->send[0],
+                    b->send[1], b->recv[0], b->recv[1], b->send_idx[0], b->send_idx[1], b->ghost_sorted};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (b->h_counters) cudaFreeHost(b->h_counters);
+    delete[] b->group;
+    delete b;
+    s->slab = nullptr;
+}
+
+extern "C" {
+
+int pbf_slab_unique_id(void *out128) {
+    if (!out128) { pbf_set_error("pbf_slab_unique_id: null"); return PBF_ERR_INVALID; }
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    PBF_NCCL(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return PBF_OK;
+}
+
+int pbf_slab_init(pbf_handle s, const void *id128, int rank, int nranks, int z_lo, int z_hi, int gz_global,
+                  uint32_t halo_capacity) {
+    if (!s || !id128) { pbf_set_error("pbf_slab_init: null"); return PBF_ERR_INVALID; }
+    int rc = nccl_load();
+    if (rc) return rc;
+    int prev;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    rc = slab_alloc(s, rank, nranks, z_lo, z_hi, gz_global, halo_capacity);
+    if (rc == PBF_OK && nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, id128, 128);
+        ncclResult_t r = g_nccl.CommInitRank(&s->slab->comm, nranks, id, rank);
+        if (r != ncclSuccess) { pbf_set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); rc = PBF_ERR_NCCL; }
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// virtual ranks: n handles of this process (same device), rank r owns layers [z_planes[r], z_planes[r+1])
+int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_global, uint32_t halo_capacity) {
+    if (!hs || n < 1 || !z_planes) { pbf_set_error("pbf_slab_init_group: bad argument"); return PBF_ERR_INVALID; }
+    for (int r = 0; r < n; r++) {
+        int rc = slab_alloc(hs[r], r, n, z_planes[r], z_planes[r + 1], gz_global, halo_capacity);
+        if (rc) return rc;
+        hs[r]->slab->group = new pbf_sim *[n];
+        hs[r]->slab->group_size = n;
+        for (int k = 0; k < n; k++) hs[r]->slab->group[k] = hs[k];
+        if (r > 0) {   // one stream for the whole group keeps the copies ordered without events
+            cudaStreamSynchronize(hs[r]->stream);
+            cudaStreamDestroy(hs[r]->stream);
+            hs[r]->stream = hs[0]->stream;
+        }
+    }
+    return PBF_OK;
+}
+
+// local particles of a slab: HOST arrays by slot + their global ids
+int pbf_slab_upload(pbf_handle s, const float *pos4, const float *vel4, const uint32_t *gid, uint32_t n) {
+    if (!s || !s->slab) { pbf_set_error("pbf_slab_upload: slab not initialised"); return PBF_ERR_STATE; }
+    if (n > s->cap) { pbf_set_error("pbf_slab_upload: n exceeds capacity"); return PBF_ERR_CAPACITY; }
+    if (n && (!pos4 || !gid)) { pbf_set_error("pbf_slab_upload: null buffer"); return PBF_ERR_INVALID; }
+    int prev;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    if (vel4) PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
+    else PBF_CUDA(cudaMemsetAsync(s->vel, 0, (size_t)n * 16, s->stream));
+    PBF_CUDA(cudaMemsetAsync(s->hl, 0, (size_t)n * 4, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(s->slab->gid, gid, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    s->n = n;
+    s->slab->n_local = n;
+    cudaSetDevice(prev);
+    return PBF_OK;
+}
+
+int pbf_slab_download(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, uint32_t *n) {
+    if (!s || !s->slab) { pbf_set_error("pbf_slab_download: slab not initialised"); return PBF_ERR_STATE; }
+    int prev;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    const u32 m = s->slab->n_local;
+    if (n) *n = m;
+    if (pos4) PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)m * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (vel4) PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, (size_t)m * 16, cudaMemcpyDeviceToHost, s->stream));
+    if (gid) PBF_CUDA(cudaMemcpyAsync(gid, s->slab->gid, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    cudaSetDevice(prev);
+    return PBF_OK;
+}
+
+// SPH::Run on this rank's slab (NCCL transport), or on every virtual rank of the handle's group
+int pbf_slab_step(pbf_handle s, int nsteps) {
+    if (!s || !s->slab) { pbf_set_error("pbf_slab_step: slab not initialised"); return PBF_ERR_STATE; }
+    int prev;
+    cudaGetDevice(&prev);
+    cudaSetDevice(s->device);
+    int rc = PBF_OK;
+    for (int i = 0; i < nsteps && rc == PBF_OK; i++) {
+        if (s->slab->group) rc = slab_step(s->slab->group, s->slab->group_size);
+        else { pbf_sim *one[1] = {s}; rc = slab_step(one, 1); }
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+// out[0] local particles, [1] ghosts from z-, [2] ghosts from z+, [3] boundary sent to z-, [4] sent to z+,
+// [5] particles migrated away so far, [6] exchanges so far, [7] bytes sent so far (low 32 bits)
+int pbf_slab_stats(pbf_handle s, uint64_t out[8]) {
+    if (!s || !s->slab || !out) { pbf_set_error("pbf_slab_stats: slab not initialised"); return PBF_ERR_STATE; }
+    pbf_slab_state *b = s->slab;
+    out[0] = b->n_local; out[1] = b->n_ghost[0]; out[2] = b->n_ghost[1]; out[3] = b->n_bnd[0]; out[4] = b->n_bnd[1];
+    out[5] = b->migrated; out[6] = b->exchanges; out[7] = b->bytes_sent;
+    return PBF_OK;
+}
+
+}  // extern "C"

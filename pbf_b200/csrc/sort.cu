@@ -228,6 +228,16 @@ int launch_sort_passes(pbf_sim *s) {
     return run_passes(s, s->plan, s->keys, nullptr, s->skey, s->perm, s->n);
 }
 
+// digit histograms of every pass of the handle's plan over keys[0..n) (slab mode: keys change after k_predict)
+int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n) {
+    int blocks = (int)((n + 255) / 256);
+    int maxb = s->sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    k_sort_hist<<<blocks, 256, 0, s->stream>>>(keys, n, s->plan, s->hist);
+    return 1;
+}
+
 int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, int bits) {
     SortPlan plan = make_sort_plan(bits);
     int blocks = (int)((n + 255) / 256);

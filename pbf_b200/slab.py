@@ -1,0 +1,251 @@
+"""Host runtime of the slab decomposition (multi GPU): partitioning, NCCL bootstrap over torch.distributed, and the
+weak-scaling benchmark.  The device side lives in csrc/slab.cu behind the pbf_slab_* entry points of include/pbf_c.h.
+
+One process per GPU (torchrun).  torch.distributed is plumbing only: it broadcasts the 128-byte NCCL unique id and
+reduces timings; the halo/migration traffic itself goes through the library's own communicator on its own stream.
+"""
+import ctypes as C
+import json
+import time
+
+import numpy as np
+
+from . import SPH, _check, _ptr, dam_break, lib
+
+
+def plan_slabs(cell_z, gz_global, nranks):
+    """Cut [0, gz_global) into nranks contiguous ranges of whole cell layers holding about the same number of particles.
+
+    cell_z: integer cell layer (int(clamp(z))) of every particle.  Returns z_planes (nranks + 1 ints); every slab
+    owns at least 2 layers (the halo scheme needs boundary layers z_lo and z_hi-1 to be distinct)."""
+    cell_z = np.asarray(cell_z)
+    hist = np.bincount(np.clip(cell_z, 0, gz_global - 1), minlength=gz_global)
+    cum = np.concatenate([[0], np.cumsum(hist)])
+    planes = [0]
+    for r in range(1, nranks):
+        target = cum[-1] * r / nranks
+        z = int(np.searchsorted(cum, target, side="left"))
+        z = max(z, planes[-1] + 2)
+        z = min(z, gz_global - 2 * (nranks - r))
+        planes.append(z)
+    planes.append(gz_global)
+    if any(b - a < 2 for a, b in zip(planes[:-1], planes[1:])):
+        raise ValueError("domain too shallow for %d slabs of >= 2 layers" % nranks)
+    return planes
+
+
+def cell_layer(pos, gz_global):
+    return np.clip(pos[:, 2], 0.0, float(gz_global)).astype(np.int32)
+
+
+def split_scene(pos, vel, z_planes, gz_global):
+    """Global scene -> per-rank (pos, vel, gid); gid = index in the global arrays."""
+    cz = cell_layer(pos, gz_global)
+    out = []
+    for r in range(len(z_planes) - 1):
+        m = np.nonzero((cz >= z_planes[r]) & (cz < z_planes[r + 1]))[0].astype(np.uint32)
+        out.append((np.ascontiguousarray(pos[m]), np.ascontiguousarray(vel[m]), m))
+    return out
+
+
+class SlabSPH(SPH):
+    """One rank's slab: an SPH handle whose cell tables cover layers [z_lo-1, z_hi+1) of the global domain."""
+
+    def __init__(self, rank, nranks, z_planes, grid_xy, gz_global, capacity, halo_capacity, wall=(16.0, 0.0, 16.0),
+                 device=-1):
+        self.rank, self.nranks = rank, nranks
+        self.z_lo, self.z_hi = int(z_planes[rank]), int(z_planes[rank + 1])
+        self.gz_global = gz_global
+        self.halo_capacity = halo_capacity
+        capacity = (capacity + 511) // 512 * 512
+        super().__init__(capacity, (grid_xy[0], grid_xy[1], self.z_hi - self.z_lo + 2), wall=wall, ref_quirks=False,
+                         device=device, use_graph=False, capacity=capacity)
+        self.capacity = capacity
+
+    def init_nccl(self, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib().pbf_slab_init(self._h, buf, self.rank, self.nranks, self.z_lo, self.z_hi, self.gz_global,
+                                   self.halo_capacity))
+
+    def upload_slab(self, pos, vel, gid):
+        pos = np.ascontiguousarray(pos, np.float32)
+        vel = np.ascontiguousarray(vel, np.float32)
+        gid = np.ascontiguousarray(gid, np.uint32)
+        _check(lib().pbf_slab_upload(self._h, _ptr(pos), _ptr(vel), _ptr(gid), pos.shape[0]))
+
+    def download_slab(self):
+        n = C.c_uint32()
+        _check(lib().pbf_slab_download(self._h, None, None, None, C.byref(n)))
+        pos = np.empty((n.value, 4), np.float32)
+        vel = np.empty((n.value, 4), np.float32)
+        gid = np.empty(n.value, np.uint32)
+        _check(lib().pbf_slab_download(self._h, _ptr(pos), _ptr(vel), _ptr(gid), C.byref(n)))
+        return pos, vel, gid
+
+    def Run(self, nsteps=1):
+        _check(lib().pbf_slab_step(self._h, nsteps))
+
+    def stats(self):
+        out = (C.c_uint64 * 8)()
+        _check(lib().pbf_slab_stats(self._h, out))
+        keys = ("n_local", "ghosts_lo", "ghosts_hi", "boundary_lo", "boundary_hi", "migrated", "exchanges", "bytes_sent")
+        return dict(zip(keys, [int(v) for v in out]))
+
+
+def unique_id():
+    buf = (C.c_char * 128)()
+    _check(lib().pbf_slab_unique_id(buf))
+    return bytes(buf)
+
+
+def broadcast_unique_id(dist, rank, device=None):
+    """Rank 0 creates the NCCL unique id, everybody receives it through torch.distributed (any backend)."""
+    import torch
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(unique_id()), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+class VirtualGroup:
+    """nranks slabs inside ONE process on one GPU, exchanged with device copies (tests of the slab logic)."""
+
+    def __init__(self, pos, vel, nranks, grid, wall=(16.0, 0.0, 16.0), halo_capacity=1 << 16, slack=1.5, device=-1):
+        gz_global = grid[2]
+        self.z_planes = plan_slabs(cell_layer(pos, gz_global), gz_global, nranks)
+        parts = split_scene(pos, vel, self.z_planes, gz_global)
+        self.ranks = []
+        for r, (p, v, g) in enumerate(parts):
+            cap = int(max(p.shape[0], 512) * slack) + 2 * halo_capacity
+            self.ranks.append(SlabSPH(r, nranks, self.z_planes, grid[:2], gz_global, cap, halo_capacity, wall, device))
+        hs = (C.c_void_p * nranks)(*[s._h for s in self.ranks])
+        _check(lib().pbf_slab_init_group(hs, nranks, (C.c_int32 * (nranks + 1))(*self.z_planes), gz_global, halo_capacity))
+        for s, (p, v, g) in zip(self.ranks, parts):
+            s.upload_slab(p, v, g)
+        self.n = pos.shape[0]
+
+    def set_params(self, **kw):
+        for s in self.ranks:
+            s._set(**kw)
+
+    def Run(self, nsteps=1):
+        self.ranks[0].Run(nsteps)
+
+    def gather(self):
+        pos = np.zeros((self.n, 4), np.float32)
+        vel = np.zeros((self.n, 4), np.float32)
+        seen = np.zeros(self.n, np.int32)
+        for s in self.ranks:
+            p, v, g = s.download_slab()
+            pos[g], vel[g] = p, v
+            seen[g] += 1
+        assert np.all(seen == 1), "every particle must be owned by exactly one rank"
+        return pos, vel
+
+    def close(self):
+        for s in reversed(self.ranks):
+            s.close()
+
+
+def weak_scene(rank, nranks, n3, grid_local_z=512, origin=(32.5, 0.5, 32.5), spacing=0.94):
+    """Rank's share of a dam-break block of n3[0] x n3[1] x (n3[2]*nranks) particles in a domain nranks*grid_local_z deep.
+
+    Slab planes follow the lattice so that every rank starts with n3[0]*n3[1]*n3[2] particles (+- one lattice layer)."""
+    gz_global = grid_local_z * nranks
+    planes = [0] + [int(origin[2] + spacing * n3[2] * r) for r in range(1, nranks)] + [gz_global]
+    k0 = max(0, n3[2] * rank - 2)
+    k1 = min(n3[2] * nranks, n3[2] * (rank + 1) + 2)
+    per_layer = n3[0] * n3[1]
+    # dam_break walks x, z, y with y innermost: generate the k-range as its own block (ids stay unique per rank)
+    pos, vel = dam_break(n3[0], n3[1], k1 - k0, origin=(origin[0], origin[1], origin[2] + spacing * k0), spacing=spacing,
+                         seed=12345 + rank, id0=0)
+    cz = cell_layer(pos, gz_global)
+    m = (cz >= planes[rank]) & (cz < planes[rank + 1])
+    gid = (np.nonzero(m)[0] + k0 * per_layer).astype(np.uint32)
+    return np.ascontiguousarray(pos[m]), np.ascontiguousarray(vel[m]), gid, planes, gz_global
+
+
+def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algorithmic_bytes):
+    """Weak scaling: every rank holds one C3-sized slab of a dam-break block that is `world` times deeper."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    pos, vel, gid, planes, gz_global = weak_scene(rank, world, cfg["n3"], cfg["grid"][2])
+    n0 = pos.shape[0]
+    halo_cap = 1 << 18
+    s = SlabSPH(rank, world, planes, cfg["grid"][:2], gz_global, int(n0 * 1.2) + 2 * halo_cap, halo_cap, device=local)
+    s.init_nccl(broadcast_unique_id(dist, rank, dev))
+    s.SetNumSolverIterations(cfg["iters"])
+    s.SetVorticityConfinementEnabled(bool(cfg["vort"]))
+    s.upload_slab(pos, vel, gid)
+    stream = torch.cuda.ExternalStream(s.stream, device=local)
+    s.Run(args.warmup)
+    s.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = s.kernel_launches
+    with torch.cuda.stream(stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        s.Run(args.steps)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+    launches = s.kernel_launches - l0
+    st = s.stats()
+    t = torch.tensor([ms, float(st["n_local"]), float(st["migrated"]), float(st["ghosts_lo"] + st["ghosts_hi"])],
+                     dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone()
+    dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    # end to end: host buffers in and out every step (download/upload of the local slab around one step)
+    hp, hv, hg = s.download_slab()
+    dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 3
+    for _ in range(e2e_steps):
+        s.upload_slab(hp, hv, hg)
+        s.Run(1)
+        hp, hv, hg = s.download_slab()
+    dist.barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join()
+        n_total = tsum[1].item()
+        ms_step = tmax[0].item()
+        value = n_total / (ms_step * 1e-3)
+        peak, peak_src = peaks()
+        step_bytes = algorithmic_bytes((cfg["grid"][0], cfg["grid"][1], cfg["grid"][2]), cfg["iters"], cfg["vort"])
+        print(json.dumps({
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "dam-break %dx%dx%d particles per GPU (block %d x deeper along z), grid %dx%dx%d per GPU, %d solver iters, vorticity+XSPH %s; z-slabs with 1-layer halos"
+                                   % (cfg["n3"] + (world,) + cfg["grid"] + (cfg["iters"], "on" if cfg["vort"] else "off")),
+                       "parallelism": "slab%d" % world, "particles_total": int(n_total),
+                       "migrated_particles_total": int(tsum[2].item()), "ghost_particles_total": int(tsum[3].item()),
+                       "exchanges_per_step": st["exchanges"] // max(1, args.steps + args.warmup),
+                       "l2": "per-GPU working set (~2 GB) far exceeds the 126 MB L2",
+                       "step_algorithmic_bytes_per_particle": step_bytes,
+                       "step_hbm_frac_of_peak": step_bytes * value / world / 1e9 / peak},
+            "clocks": sampler.summary(), "gpu_launches": int(launches),
+            "e2e": {"value": n_total / (e2e_ms.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": int(n_total * 36),
+                    "d2h_bytes_per_step": int(n_total * 36), "ms_per_step": e2e_ms.item(),
+                    "call": "pbf_slab_upload + pbf_slab_step + pbf_slab_download per step (host pos+vel+gid)"},
+            "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_bytes * value / world / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": step_bytes * value / world / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "note": "per-GPU algorithmic bytes / step time; see the N=1 line for the dominant kernel"},
+        }))
+    dist.barrier()
+    s.close()
+    dist.destroy_process_group()
