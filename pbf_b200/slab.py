@@ -153,19 +153,18 @@ class VirtualGroup:
 def weak_scene(rank, nranks, n3, grid_local_z=512, origin=(32.5, 0.5, 32.5), spacing=0.94):
     """Rank's share of a dam-break block of n3[0] x n3[1] x (n3[2]*nranks) particles in a domain nranks*grid_local_z deep.
 
-    Slab planes follow the lattice so that every rank starts with n3[0]*n3[1]*n3[2] particles (+- one lattice layer)."""
+    Rank r generates lattice layers k in [n3[2]*r, n3[2]*(r+1)) -- exactly n3[0]*n3[1]*n3[2] particles, no overlap --
+    and the slab planes are the cell layers those ranges start in.  The few particles of the last lattice layer that
+    fall on the far side of a plane are handed over by the runtime's migration in the first step."""
     gz_global = grid_local_z * nranks
     planes = [0] + [int(origin[2] + spacing * n3[2] * r) for r in range(1, nranks)] + [gz_global]
-    k0 = max(0, n3[2] * rank - 2)
-    k1 = min(n3[2] * nranks, n3[2] * (rank + 1) + 2)
-    per_layer = n3[0] * n3[1]
-    # dam_break walks x, z, y with y innermost: generate the k-range as its own block (ids stay unique per rank)
-    pos, vel = dam_break(n3[0], n3[1], k1 - k0, origin=(origin[0], origin[1], origin[2] + spacing * k0), spacing=spacing,
+    k0 = n3[2] * rank
+    pos, vel = dam_break(n3[0], n3[1], n3[2], origin=(origin[0], origin[1], origin[2] + spacing * k0), spacing=spacing,
                          seed=12345 + rank, id0=0)
-    cz = cell_layer(pos, gz_global)
-    m = (cz >= planes[rank]) & (cz < planes[rank + 1])
-    gid = (np.nonzero(m)[0] + k0 * per_layer).astype(np.uint32)
-    return np.ascontiguousarray(pos[m]), np.ascontiguousarray(vel[m]), gid, planes, gz_global
+    j = np.arange(pos.shape[0], dtype=np.int64)          # dam_break walks x, z, y with y innermost
+    x, zk, y = j // (n3[2] * n3[1]), (j // n3[1]) % n3[2], j % n3[1]
+    gid = ((x * (n3[2] * nranks) + (k0 + zk)) * n3[1] + y).astype(np.uint32)
+    return pos, vel, gid, planes, gz_global
 
 
 def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algorithmic_bytes):

@@ -260,3 +260,25 @@ def test_virtual_slabs_match_single_domain(built_lib, nranks):
     ghosts = sum(s.stats()["ghosts_lo"] + s.stats()["ghosts_hi"] for s in grp.ranks)
     assert migrated > 0 and ghosts > 0
     grp.close()
+
+
+def test_golden_vectors_cuda(built_lib):
+    """CUDA path against the committed golden file minted by the independent NumPy restatement (tests/golden)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_small.npz"))
+    pos, vel = pbf_b200.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
+    assert np.array_equal(pos.view(np.uint32), G["pos0"].view(np.uint32))
+    sph = pbf_b200.SPH(pos.shape[0], tuple(G["grid"].tolist()), ref_quirks=bool(G["ref_quirks"]))
+    sph.SetNumSolverIterations(int(G["iters"]))
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    sph.Run()
+    keys, perm, _ = sph.get_sorted(records=False)
+    assert np.array_equal(keys, G["skey"])
+    start, _ = sph.get_cell_ranges()
+    assert np.array_equal(start, G["start"])
+    _, rc = sph.get_neighbour_runs()
+    assert np.array_equal(rc, G["run_count"])
+    gpos, gvel = sph.download()
+    assert np.max(np.abs(gpos - G["pos1"])) < 2e-5
+    assert np.max(np.abs(gvel - G["vel1"])) < 2e-3
