@@ -179,6 +179,7 @@ def main():
 
     # ---- per-kernel durations of the four neighbour sweeps (stage entry points, same stream, CUDA events) ---------------
     sph.predict(); sph.sort(); sph.build_cells()
+    tiles, tiled = sph.tile_stats()
     stage_ms = {}
     reps = 5
     stage_ms["lambda"] = timed(sph.calc_lambda, reps)
@@ -218,7 +219,7 @@ def main():
                    "step_algorithmic_bytes_per_particle": step_bytes,
                    "step_hbm_frac_of_peak": step_bytes * value / 1e9 / peak,
                    "phase_ms": dict(zip(["predict", "sort", "neighbour_cells", "solver", "vorticity"], phases)),
-                   "stage_ms": stage_ms},
+                   "stage_ms": stage_ms, "tiles": tiles, "tiles_on_tiled_path": tiled},
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * n * 16, "d2h_bytes_per_step": 2 * n * 16,

@@ -155,6 +155,11 @@ int pbf_get_timings(pbf_handle h, float ms[5]);
  * the current positions (one extra density sweep) and sum 0.5 |v|^2. */
 int pbf_get_diagnostics(pbf_handle h, double *density_error, double *kinetic_energy);
 
+/* Tiles (256 consecutive sorted particles) of the last pbf_build_cells / step, and how many of them run the
+ * shared-memory tiled sweep path; the rest walk their neighbour runs from global memory ("sweeps").
+ * why (may be NULL): [0] tiled, [1] ranges do not fit the shared-memory image; the rest is reserved. */
+int pbf_get_tile_stats(pbf_handle h, uint32_t *tiles, uint32_t *tiled, uint32_t why[8]);
+
 /* how many kernels the handle has launched (graph replays count their kernel nodes) */
 uint64_t pbf_kernel_launches(pbf_handle h);
 /* stream the handle launches on (a cudaStream_t), for callers that time with CUDA events */

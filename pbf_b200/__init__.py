@@ -45,6 +45,7 @@ def lib():
         L.pbf_wpoly6.argtypes = [C.c_float, C.c_float]
         L.pbf_num_particles.restype = C.c_uint32
         L.pbf_num_particles.argtypes = [C.c_void_p]
+        L.pbf_get_tile_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.pbf_kernel_launches.restype = C.c_uint64
         L.pbf_kernel_launches.argtypes = [C.c_void_p]
         L.pbf_stream.restype = C.c_void_p
@@ -295,5 +296,12 @@ class SPH:
 
     @property
     def kernel_launches(self): return lib().pbf_kernel_launches(self._h)
+
+    def tile_stats(self):
+        """(tiles, tiles on the shared-memory tiled sweep path) of the last build_cells / step."""
+        a, b, why = C.c_uint32(0), C.c_uint32(0), (C.c_uint32 * 8)()
+        _check(lib().pbf_get_tile_stats(self._h, C.byref(a), C.byref(b), why))
+        self.tile_fallback_reasons = list(why)
+        return a.value, b.value
     @property
     def stream(self): return lib().pbf_stream(self._h)

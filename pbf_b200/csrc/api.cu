@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of include/pbf_c.h: handle life cycle, step orchestration (SPH::Run, reference
 // src/SPH.cpp:246-334), CUDA-graph replay, phase timing (SPH::OutputTiming, src/SPH.cpp:218-240) and debug read-back.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -166,6 +167,8 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     s->grid.bx = bx; s->grid.bz = bz;
     s->grid.zoff = 0; s->grid.gz_global = cfg->grid[2];
     s->plan = make_sort_plan(sortbits);
+    const char *gs = getenv("PBF_GENERAL_SWEEPS");
+    s->tiled_sweeps = !(gs && gs[0] == '1');
     pbf_default_params(&s->params);
 
     DeviceGuard guard(dev);
@@ -190,7 +193,12 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     ALLOC(s->cells, s->ncell); ALLOC(s->runs3, s->ncell);
     ALLOC(s->bufA, cap); ALLOC(s->bufB, cap); ALLOC(s->svel, cap); ALLOC(s->vprime, cap); ALLOC(s->omega, cap);
     ALLOC(s->flags, 4); ALLOC(s->diag, 2);
+    ALLOC(s->tile_desc, plan_desc_ints(cap)); ALLOC(s->tile_runs, plan_run_words(cap));
 #undef ALLOC
+    if (sweeps_init() != 0) {
+        pbf_destroy(s);
+        return fail(PBF_ERR_CUDA, "pbf_create: the sweep kernels need 90 KB of opt-in shared memory per block");
+    }
     s->pos = s->pos_own; s->vel = s->vel_own; s->hl = s->hl_own;
     cudaMemsetAsync(s->pos_own, 0, (size_t)cap * 16, s->stream);
     cudaMemsetAsync(s->vel_own, 0, (size_t)cap * 16, s->stream);
@@ -222,7 +230,7 @@ int pbf_destroy(pbf_handle s) {
     invalidate_graph(s);
     void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
                     s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->runs3, s->bufA, s->bufB,
-                    s->svel, s->vprime, s->omega, s->flags, s->diag};
+                    s->svel, s->vprime, s->omega, s->flags, s->diag, s->tile_desc, s->tile_runs};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)
@@ -534,6 +542,27 @@ int pbf_get_diagnostics(pbf_handle s, double *density_error, double *kinetic_ene
     PBF_CUDA(cudaStreamSynchronize(s->stream));
     if (density_error) *density_error = host[0] / (double)s->n;
     if (kinetic_energy) *kinetic_energy = host[1];
+    return PBF_OK;
+}
+
+int pbf_get_tile_stats(pbf_handle s, uint32_t *tiles, uint32_t *tiled, uint32_t why[8]) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (s->n_prev_sorted != s->n) return fail(PBF_ERR_STATE, "pbf_get_tile_stats: needs pbf_build_cells");
+    DeviceGuard guard(s->device);
+    const size_t nt = plan_desc_ints(s->n);
+    std::vector<int> tmp(nt);
+    PBF_CUDA(cudaMemcpyAsync(tmp.data(), s->tile_desc, nt * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    const size_t stride = plan_desc_ints(1);
+    uint32_t a = 0, b = 0;
+    if (why) memset(why, 0, 8 * sizeof(uint32_t));
+    for (size_t t = 0; t < nt; t += stride) {
+        a++;
+        b += tmp[t] != 0;
+        if (why) why[tmp[t] != 0 ? 0 : 1]++;
+    }
+    if (tiles) *tiles = a;
+    if (tiled) *tiled = b;
     return PBF_OK;
 }
 

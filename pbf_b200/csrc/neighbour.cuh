@@ -1,0 +1,134 @@
+// neighbour.cuh -- device helpers shared by the neighbour sweeps (sweeps.cu) and the table/debug kernels
+// (sim_kernels.cu): kernel constants, the merged-run lookup of neighbourcells.glsl:52-91, 256-bit candidate-pair loads
+// and the packed f32x2 pair geometry.
+#pragma once
+#include "pbf_internal.cuh"
+
+namespace {
+
+constexpr int NB_BLOCK = 256;   // threads per block of the neighbour kernels (= BLOCKSIZE of src/SPH.cpp:60)
+
+constexpr float H = 2.0f;                                // src/SPH.cpp:58
+constexpr float H2 = 4.0f;
+constexpr float POLY6 = 1.56668147106f / 512.0f;         // calclambda.glsl:46, /h^9
+constexpr float SPIKY_GRAD = -3.0f * 4.774648292756860f / 64.0f;   // calclambda.glsl:63, /h^6
+constexpr float FAR = 1.0e8f;       // a masked candidate is moved here: r2 = 1e16 -> both kernels vanish, no inf/nan
+constexpr float TINY = 1.0e-24f;    // r2 clamp: rsqrt stays finite and c*d = 0 for coincident particles (l == 0 branch)
+
+// neighbourcells.glsl:62-84 for the window x-1..x+1 of one row: first existing start, summed sizes
+__device__ __forceinline__ int2 merge3(const int2 *__restrict__ cells, int base, int x, int gx) {
+    int cell = -1, entries = 0;
+#pragma unroll
+    for (int j = -1; j <= 1; j++) {
+        const int xx = x + j;
+        if (xx >= 0 && xx < gx) {
+            int2 c = cells[base + xx];
+            if (cell == -1) cell = c.x;
+            if (c.x != -1) entries += c.y - c.x;
+        }
+    }
+    return make_int2(cell, cell == -1 ? 0 : entries);
+}
+
+// ---- K7 neighbourcells.glsl:52-91: the nine merged runs {start, count} of a particle whose unclamped cell is `home` ---
+__device__ __forceinline__ void fetch_runs(const u32 home, const GridInfo &g, const int2 *__restrict__ runs3,
+                                           const int2 *__restrict__ cells, int2 r[9]) {
+    const int cx = (int)(home & ((1u << g.bx) - 1u)) - 2;
+    const int cz = (int)((home >> g.bx) & ((1u << g.bz) - 1u)) - 2;
+    const int cy = (int)(home >> (g.bx + g.bz)) - 2;
+    const bool fast = cx >= 0 && cx < g.gx;
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+        const int yy = cy + (o / 3 - 1), zz = cz + (o % 3 - 1);   // gridoffsets[o] = (0, dy, dz)
+        r[o] = make_int2(-1, 0);
+        if (yy >= 0 && yy < g.gy && zz >= 0 && zz < g.gz) {
+            const int base = yy * g.gxgz + zz * g.gx;
+            if (fast) r[o] = __ldg(runs3 + base + cx);
+            else r[o] = merge3(cells, base, cx, g.gx);             // particle outside the grid in x: rare
+        }
+    }
+}
+
+// The thread's non-empty runs {start,end} into shared memory.  Returns their number; *slots = number of aligned
+// candidate pairs over all runs; *self_in = whether the particle's own slot lies in run 4 (its own row), i.e. whether
+// FOR_EACH_NEIGHBOUR would have skipped `self`.
+template <int BLOCK>
+__device__ __forceinline__ int load_runs(const u32 home, const u32 i, const GridInfo &g, const int2 *__restrict__ runs3,
+                                         const int2 *__restrict__ cells, int2 *srun, int tid, int *slots, bool *self_in) {
+    int2 r[9];
+    fetch_runs(home, g, runs3, cells, r);
+    int cnt = 0, tot = 0;
+    *self_in = (int)i >= r[4].x && (int)i < r[4].x + r[4].y;
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+        if (r[o].y > 0) {
+            const int s = r[o].x, e = r[o].x + r[o].y;
+            srun[cnt * BLOCK + tid] = make_int2(s, e);
+            cnt++;
+            tot += ((e + 1) >> 1) - (s >> 1);
+        }
+    }
+    *slots = tot;
+    return cnt;
+}
+
+struct Pair {   // candidates 2m (.x of each float2) and 2m+1 (.y)
+    float2 x, y, z, w;
+};
+
+__device__ __forceinline__ Pair ldg_pair(const float4 *p) {   // one 256-bit read-only load, p is 32-byte aligned
+    Pair r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.x.x), "=f"(r.y.x), "=f"(r.z.x), "=f"(r.w.x), "=f"(r.x.y), "=f"(r.y.y), "=f"(r.z.y), "=f"(r.w.y)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float rsqrt_ftz(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// geometry of one candidate pair against particle p: d = p - c, r2, 1/l, and the two NEGATED clamped factors
+// tn = min(r^2 - h^2, 0) = -(h^2 - r^2)+ and t2n = min(l - h, 0) = -(h - l)+.  Odd powers of them carry a minus sign the
+// callers fold into their final constants (one FADD2 with an immediate each instead of FFMA2 + FADD2 + FMUL2).
+struct PairGeom {
+    float2 dx, dy, dz, r2, il, t, t2;
+};
+
+__device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bool v0, bool v1) {
+    PairGeom q;
+    const float x0 = v0 ? c.x.x : FAR, x1 = v1 ? c.x.y : FAR;     // out-of-run members leave kernel support
+    q.dx = make_float2(p.x - x0, p.x - x1);
+    q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
+    q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
+    q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));
+    // the clamp keeps rsqrt finite at r = 0 (self, coincident): there c*d = 0 like the l == 0 branch of gradWspiky
+    q.il = make_float2(rsqrt_ftz(fmaxf(q.r2.x, TINY)), rsqrt_ftz(fmaxf(q.r2.y, TINY)));
+    const float2 l = __fmul2_rn(q.r2, q.il);
+    const float2 a = __fadd2_rn(l, make_float2(-H, -H)), b = __fadd2_rn(q.r2, make_float2(-H2, -H2));
+    q.t2 = make_float2(fminf(a.x, 0.0f), fminf(a.y, 0.0f));         // gradWspiky = 0 for l > h
+    q.t = make_float2(fminf(b.x, 0.0f), fminf(b.y, 0.0f));          // Wpoly6 = 0 for r > h
+    return q;
+}
+
+// flattened walk over the aligned candidate pairs of all runs; body(pair index m, valid0, valid1)
+template <int BLOCK, class F>
+__device__ __forceinline__ void for_each_pair(const int2 *srun, int tid, int slots, F body) {
+    const int2 *sp = srun + tid;
+    int m = 0, mend = 0, s = 0, e = 0;
+#pragma unroll 1
+    for (int k = 0; k < slots; k++) {
+        if (m >= mend) {
+            const int2 r = *sp;
+            sp += BLOCK;
+            s = r.x; e = r.y;
+            m = s >> 1; mend = (e + 1) >> 1;
+        }
+        body(m, 2 * m >= s, 2 * m + 1 < e);
+        m++;
+    }
+}
+
+}  // namespace

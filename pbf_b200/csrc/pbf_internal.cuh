@@ -67,6 +67,10 @@ struct pbf_sim {
     int2 *cells;
     int2 *runs3;                          // per cell: cells x-1,x,x+1 merged {start,count} (neighbourcells.glsl:62-84)
     u32 n_prev_sorted;                    // slots of skey that describe the current table contents
+    // plan of the tiled sweeps (sweeps.cu): per 256-particle tile the nine sorted-index ranges that hold all its
+    // candidates, per particle its nine neighbour runs relative to the tile's shared-memory image
+    int *tile_desc; u32 *tile_runs;
+    bool tiled_sweeps;                    // false (env PBF_GENERAL_SWEEPS=1, debugging): every tile takes the general path
     // solver state in sorted order
     float4 *bufA;                         // {x,y,z,-}   positions (Jacobi ping)
     float4 *bufB;                         // {x,y,z,lambda} resp. {x,y,z,|omega|}
@@ -112,6 +116,12 @@ int launch_density_diag(pbf_sim *s);
 int launch_kinetic_diag(pbf_sim *s);
 int launch_compose_records(pbf_sim *s, float4 *out);
 int launch_neighbour_runs(pbf_sim *s, int *run_start, int *run_count);
+// sweeps.cu
+int sweeps_init(void);                   // opt-in shared-memory sizes of the sweep kernels (once per device)
+size_t plan_desc_ints(u32 cap);
+size_t plan_run_words(u32 cap);
+int launch_plan(pbf_sim *s);
+SimParams sim_params(const pbf_sim *s);
 // slab.cu
 void slab_free(pbf_sim *s);
 bool slab_borrows_stream(const pbf_sim *s);

@@ -1,0 +1,414 @@
+// sweeps.cu -- the four neighbour sweeps of SPH::Run (K8 calclambda.glsl, K9 updatepos.glsl, K11 vorticity.glsl as two
+// kernels) and the per-step plan they run on.
+//
+// Candidate set = FOR_EACH_NEIGHBOUR (shaders/sph/foreachneighbour.glsl:1-10): for a particle in cell (x,y,z) the nine
+// rows (y+dy, z+dz), each the cells x-1..x+1 merged into one run (neighbourcells.glsl:37-47, :62-84).  Cells are ordered
+// x-fastest (key = x + z*gx + y*gx*gz), so for a TILE of 256 consecutive sorted particles the runs of row offset
+// o = (dy,dz) of all its particles lie inside ONE contiguous range of the sorted array, about 256 + 3 records long.
+//   * k_plan (once per step, after the cell tables): per particle its nine runs (this is K7, evaluated once per step
+//     as in the reference), per tile the nine ranges [S_o, S_o + n_o) that cover them; the runs are stored relative to
+//     the tile's shared-memory image (16-bit start, 15-bit count: 36 B per particle).
+//   * every sweep: one thread issues nine 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) that
+//     bring the tile's nine ranges into shared memory verbatim -- no per-record instructions, no LSU wavefronts for
+//     staging; meanwhile the other threads fetch their runs.  A thread then walks its nine runs in the image, two
+//     candidates per iteration (two LDS.128, packed f32x2 arithmetic).  Neighbouring lanes read neighbouring records
+//     of the same row, so the loads are free of bank conflicts.
+// What bounds the sweeps is the L1/shared-memory data pipe (one 128-byte wavefront per clock per SM; a 16-byte load by
+// 32 lanes takes four) together with the FP32 pipe, not HBM: see DESIGN.md and profiles/.
+//
+// A tile whose ranges do not fit the image (TL_CAP records: sparse scenes where 256 consecutive particles span many
+// rows) takes the general path: every thread walks its nine runs straight from global memory through L1 (the first
+// version of these kernels).  Both paths visit exactly the same candidate set.
+#include <limits.h>
+
+#include "neighbour.cuh"
+
+namespace {
+
+constexpr int TL = NB_BLOCK;     // particles per tile = threads per block
+constexpr int TL_CAP = 3328;     // most records a tile stages, 16 B each: 12 lattice lines of 256 + slack; 52 KB
+constexpr int TL_DESC = 32;      // ints per tile descriptor: mode, records, nine range starts, nine range lengths
+constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11;
+constexpr size_t TL_IMG = (size_t)(TL_CAP + 1) * sizeof(float4);   // one image (+1 finite pad record)
+constexpr size_t TL_SMEM1 = TL_IMG;                                // 4 blocks per SM
+constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays: 2 blocks per SM
+
+// ---- the plan: one block per tile ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TL)
+k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
+       int *__restrict__ desc, u32 *__restrict__ runs, GridInfo g, int allow) {
+    __shared__ int sS[9], sE[9];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 i = blockIdx.x * (u32)TL + tid;
+    if (tid < 9) { sS[tid] = INT_MAX; sE[tid] = -1; }
+    __syncthreads();
+    int2 r[9];
+#pragma unroll
+    for (int o = 0; o < 9; o++) r[o] = make_int2(-1, 0);
+    if (i < n) fetch_runs(home[i], g, runs3, cells, r);
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+        const bool has = r[o].y > 0;
+        const int a = __reduce_min_sync(0xffffffffu, has ? r[o].x : INT_MAX);
+        const int b = __reduce_max_sync(0xffffffffu, has ? r[o].x + r[o].y : -1);
+        if (lane == 0 && b >= 0) { atomicMin(&sS[o], a); atomicMax(&sE[o], b); }
+    }
+    __syncthreads();
+    int total = 0;
+    bool fits = true;
+    u32 *out = runs + (size_t)blockIdx.x * 9 * TL + tid;
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+        const int no = sE[o] >= 0 ? sE[o] - sS[o] : 0;
+        // image index of the run's first record | count; an empty run is 0
+        u32 v = r[o].y > 0 ? (u32)(r[o].x - sS[o] + total) | ((u32)r[o].y << 16) : 0u;
+        if (o == 4 && (int)i >= r[4].x && (int)i < r[4].x + r[4].y) v |= 0x80000000u;   // the run holds the particle itself
+        out[o * TL] = v;
+        fits = fits && r[o].y < 32768;
+        total += no;
+    }
+    fits = __syncthreads_and(fits && total <= TL_CAP && allow);
+    int *d = desc + (size_t)blockIdx.x * TL_DESC;
+    if (tid == 0) { d[D_MODE] = fits ? 1 : 0; d[D_TOTAL] = total; }
+    if (tid < 9) { d[D_S + tid] = sE[tid] >= 0 ? sS[tid] : 0; d[D_N + tid] = sE[tid] >= 0 ? sE[tid] - sS[tid] : 0; }
+}
+
+// ---- tile frame of the sweeps -------------------------------------------------------------------------------------------
+struct TileCtx {
+    int mode;            // 1 tiled, 0 general
+    bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
+    const float4 *sm0, *sm1;
+    const u32 *runs;     // this thread's nine packed runs, stride TL
+};
+
+__device__ __forceinline__ Pair make_pair(const float4 &a, const float4 &b) {
+    Pair p;
+    p.x = make_float2(a.x, b.x); p.y = make_float2(a.y, b.y); p.z = make_float2(a.z, b.z); p.w = make_float2(a.w, b.w);
+    return p;
+}
+
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// All threads of the block call this.  Thread 0 reads the tile descriptor and issues the bulk copies of the nine
+// ranges of NSRC arrays; everybody then waits on the mbarrier (the caller overlaps its own loads before tile_wait).
+template <int NSRC>
+__device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
+                                              const float4 *__restrict__ src1, const int *__restrict__ desc,
+                                              const u32 *__restrict__ runs, int tid) {
+    float4 *sm0 = reinterpret_cast<float4 *>(dsm);
+    float4 *sm1 = sm0 + (TL_CAP + 1);
+    const int *dg = desc + (size_t)blockIdx.x * TL_DESC;
+    TileCtx c;
+    c.mode = __ldg(dg + D_MODE);
+    c.sm0 = sm0; c.sm1 = sm1; c.self_in = false;
+    c.runs = runs + (size_t)blockIdx.x * 9 * TL + tid;
+    if (c.mode) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+        if (tid == 0) {
+            // the whole descriptor in five independent 16-byte loads, before anything waits on it
+            const int4 *d4 = reinterpret_cast<const int4 *>(dg);
+            const int4 q0 = __ldg(d4), q1 = __ldg(d4 + 1), q2 = __ldg(d4 + 2), q3 = __ldg(d4 + 3), q4 = __ldg(d4 + 4);
+            const int dv[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w,
+                                q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const int total = dv[D_TOTAL];
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(total * 16 * NSRC)) : "memory");
+            const unsigned a0 = (unsigned)__cvta_generic_to_shared(sm0), a1 = (unsigned)__cvta_generic_to_shared(sm1);
+            int at = 0;
+#pragma unroll
+            for (int o = 0; o < 9; o++) {
+                const int so = dv[D_S + o], no = dv[D_N + o];
+                if (no > 0) {
+                    bulk_g2s(a0 + 16u * at, src0 + so, 16u * no, mb);
+                    if (NSRC == 2) bulk_g2s(a1 + 16u * at, src1 + so, 16u * no, mb);
+                }
+                at += no;
+            }
+            sm0[total] = make_float4(0.f, 0.f, 0.f, 0.f);      // the record after the last run: read, then masked
+            if (NSRC == 2) sm1[total] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    return c;
+}
+
+__device__ __forceinline__ void tile_wait(const TileCtx &c, unsigned long long *mbar) {
+    __syncthreads();                                       // the barrier is initialised, the pad record written
+    if (c.mode) {
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+            "@!p bra WAIT_%=;\n"
+            "}\n" ::"r"(mb) : "memory");
+    }
+}
+
+// Tiled walk of one particle: nine runs in the shared image, two candidates per iteration.
+// body(candidate pair of array 0, same pair of array 1, valid0, valid1)
+template <int NSRC, class F>
+__device__ __forceinline__ void tile_walk(TileCtx &c, u32 i, F body) {
+    u32 cur = __ldg(c.runs);
+#pragma unroll 1
+    for (int o = 0; o < 9; o++) {
+        const u32 nxt = o < 8 ? __ldg(c.runs + (o + 1) * TL) : 0u;
+        const int cnt = (int)((cur >> 16) & 0x7fffu);
+        if (o == 4) c.self_in = (cur >> 31) != 0u;
+        const float4 *p0 = c.sm0 + (cur & 0xffffu), *p1 = c.sm1 + (cur & 0xffffu);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k += 2) {
+            const Pair p = make_pair(p0[k], p0[k + 1]);
+            if (NSRC == 2) body(p, make_pair(p1[k], p1[k + 1]), true, k + 1 < cnt);
+            else body(p, p, true, k + 1 < cnt);
+        }
+        cur = nxt;
+    }
+}
+
+// General walk of one particle: its nine merged runs from global memory (aligned pairs, masked edges).
+template <int NSRC, class F>
+__device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, const float4 *__restrict__ src0,
+                                             const float4 *__restrict__ src1, const u32 *__restrict__ home,
+                                             const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
+                                             const GridInfo &g, u32 i, int tid, F body) {
+    int2 *srun = reinterpret_cast<int2 *>(dsm);            // 9 x TL run descriptors
+    int slots_;
+    load_runs<TL>(home[i], i, g, runs3, cells, srun, tid, &slots_, &c.self_in);
+    for_each_pair<TL>(srun, tid, slots_, [&](int m, bool v0, bool v1) {
+        const Pair p = ldg_pair(src0 + 2 * (size_t)m);
+        if (NSRC == 2) body(p, ldg_pair(src1 + 2 * (size_t)m), v0, v1);
+        else body(p, p, v0, v1);
+    });
+}
+
+// both paths, for a thread that has a particle
+template <int NSRC, class F>
+__device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, const float4 *__restrict__ src0,
+                                     const float4 *__restrict__ src1, const u32 *__restrict__ home,
+                                     const int2 *__restrict__ runs3, const int2 *__restrict__ cells, const GridInfo &g,
+                                     u32 i, int tid, F body) {
+    if (c.mode) tile_walk<NSRC>(c, i, body);
+    else general_walk<NSRC>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+}
+
+#define TILE_ARGS const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,   \
+                  const int *__restrict__ desc, const u32 *__restrict__ runs
+
+// ---- K8 calclambda.glsl:66-103 ------------------------------------------------------------------------------------
+// out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
+template <bool DIAG>
+__global__ void __launch_bounds__(TL)
+k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int tid = threadIdx.x;
+    const u32 i = blockIdx.x * TL + tid;
+    TileCtx tc = tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid);
+    const bool live = i < n;
+    float err = 0.0f;
+    const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    tile_wait(tc, &mbar);
+    if (live) {
+        float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
+        walk<1>(tc, dsm, A, A, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+            const PairGeom q = pair_geom(pi, c, v0, v1);
+            rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
+            const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);       // (h-l)^2 / l
+            S = __ffma2_rn(__fmul2_rn(cc, cc), q.r2, S);                      // sum |grad|^2 (up to a constant)
+            gx = __ffma2_rn(cc, q.dx, gx);
+            gy = __ffma2_rn(cc, q.dy, gy);
+            gz = __ffma2_rn(cc, q.dz, gz);
+        });
+        // FOR_EACH_NEIGHBOUR skips j == i (foreachneighbour.glsl:9): self only ever adds (h^2)^3 = 64 to the poly6 sum
+        float rs = -(rho.x + rho.y);
+        if (tc.self_in) rs -= 64.0f;
+        const float r = POLY6 * rs;
+        const float cg = SPIKY_GRAD * P.one_over_rho_0;
+        const float sx = cg * (gx.x + gx.y), sy = cg * (gy.x + gy.y), sz = cg * (gz.x + gz.y);
+        const float Ssum = cg * cg * (S.x + S.y) + (sx * sx + sy * sy + sz * sz);
+        const float C = r * P.one_over_rho_0 - 1.0f;
+        if (DIAG) err = fabsf(C);
+        else B[i] = make_float4(pi.x, pi.y, pi.z, -C / (Ssum + P.epsilon));
+    }
+    if (DIAG) {
+        __shared__ float red[TL / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+        if ((tid & 31) == 0) red[tid >> 5] = err;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < TL / 32; w++) s += (double)red[w];
+            atomicAdd(diag, s);
+        }
+    }
+}
+
+// ---- K9 updatepos.glsl:43-105, Jacobi: reads B {p, lambda}, writes A -----------------------------------------------
+__global__ void __launch_bounds__(TL)
+k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int tid = threadIdx.x;
+    const u32 i = blockIdx.x * TL + tid;
+    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
+    const bool live = i < n;
+    const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    tile_wait(tc, &mbar);
+    if (!live) return;
+    float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
+    // scorr = -k (scale W)^4 = -(k scale^4 POLY6^4) t^12 with t = max(h^2 - r^2, 0)        (updatepos.glsl:57-60)
+    float sc4 = P.tensile_scale * POLY6;
+    sc4 *= sc4;
+    sc4 *= sc4;
+    const float nk = -P.tensile_k * sc4;
+    const float2 nk2 = make_float2(nk, nk), li2 = make_float2(pi.w, pi.w);
+    walk<1>(tc, dsm, B, B, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+        const PairGeom q = pair_geom(pi, c, v0, v1);
+        float2 t3 = __fmul2_rn(__fmul2_rn(q.t, q.t), q.t);
+        t3 = __fmul2_rn(t3, t3);
+        t3 = __fmul2_rn(t3, t3);                                              // t^12
+        const float2 f = __ffma2_rn(nk2, t3, __fadd2_rn(li2, c.w));           // lambda_i + lambda_j + scorr
+        const float2 cc = __fmul2_rn(f, __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il));
+        ax = __ffma2_rn(cc, q.dx, ax);
+        ay = __ffma2_rn(cc, q.dy, ay);
+        az = __ffma2_rn(cc, q.dz, az);
+    });
+    const float s = SPIKY_GRAD * P.one_over_rho_0;
+    float x = pi.x + s * (ax.x + ax.y), y = pi.y + s * (ay.x + ay.y), z = pi.z + s * (az.x + az.y);
+    x = fminf(fmaxf(x, g.wlo[0]), g.whi[0]);                               // updatepos.glsl:98-100
+    y = fminf(fmaxf(y, g.wlo[1]), g.whi[1]);
+    z = fminf(fmaxf(z, g.wlo[2]), g.whi[2]);
+    A[i] = make_float4(x, y, z, 0.0f);
+}
+
+// ---- K11 vorticity.glsl:34-60 (first sweep): XSPH + vorticity ------------------------------------------------------------
+// out: vprime = v + c*sum v_ij W, omega = sum v_ij x gradW, B = {p, |omega|}
+__global__ void __launch_bounds__(TL)
+k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
+              float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int tid = threadIdx.x;
+    const u32 i = blockIdx.x * TL + tid;
+    TileCtx tc = tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid);
+    const bool live = i < n;
+    const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    tile_wait(tc, &mbar);
+    if (!live) return;
+    float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
+    const float2 neg1 = make_float2(-1.0f, -1.0f);
+    walk<2>(tc, dsm, A, svel, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
+        const PairGeom q = pair_geom(pi, c, v0, v1);
+        const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
+        const float2 uy = make_float2(u.y.x - vi.y, u.y.y - vi.y);
+        const float2 uz = make_float2(u.z.x - vi.z, u.z.y - vi.z);
+        const float2 w = __fmul2_rn(__fmul2_rn(q.t, q.t), q.t);              // -Wpoly6 / POLY6 (q.t is negated)
+        vx = __ffma2_rn(ux, w, vx);
+        vy = __ffma2_rn(uy, w, vy);
+        vz = __ffma2_rn(uz, w, vz);
+        const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);          // grad = SPIKY_GRAD * cc * d
+        const float2 gx = __fmul2_rn(cc, q.dx), gy = __fmul2_rn(cc, q.dy), gz = __fmul2_rn(cc, q.dz);
+        // cross(v_ij, grad)
+        wx = __ffma2_rn(uy, gz, __ffma2_rn(__fmul2_rn(gy, uz), neg1, wx));
+        wy = __ffma2_rn(uz, gx, __ffma2_rn(__fmul2_rn(gz, ux), neg1, wy));
+        wz = __ffma2_rn(ux, gy, __ffma2_rn(__fmul2_rn(gx, uy), neg1, wz));
+    });
+    const float cw = -P.xsph_c * POLY6;
+    vprime[i] = make_float4(vi.x + cw * (vx.x + vx.y), vi.y + cw * (vy.x + vy.y), vi.z + cw * (vz.x + vz.y), 0.0f);
+    const float ox = SPIKY_GRAD * (wx.x + wx.y), oy = SPIKY_GRAD * (wy.x + wy.y), oz = SPIKY_GRAD * (wz.x + wz.y);
+    omega[i] = make_float4(ox, oy, oz, 0.0f);
+    B[i] = make_float4(pi.x, pi.y, pi.z, sqrtf(ox * ox + oy * oy + oz * oz));   // vorticity.glsl:60
+}
+
+// ---- K11 vorticity.glsl:65-85 (second sweep): confinement force, velocity[id] written once -------------------------------
+__global__ void __launch_bounds__(TL)
+k_vorticity_b(u32 n, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
+              const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P) {
+    extern __shared__ __align__(16) unsigned char dsm[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int tid = threadIdx.x;
+    const u32 i = blockIdx.x * TL + tid;
+    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
+    const bool live = i < n;
+    const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    tile_wait(tc, &mbar);
+    if (!live) return;
+    float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
+    walk<1>(tc, dsm, B, B, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+        const PairGeom q = pair_geom(pi, c, v0, v1);
+        const float2 cc = __fmul2_rn(c.w, __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il));   // |omega_j| * grad factor
+        ex = __ffma2_rn(cc, q.dx, ex);
+        ey = __ffma2_rn(cc, q.dy, ey);
+        ez = __ffma2_rn(cc, q.dz, ez);
+    });
+    float nx = SPIKY_GRAD * (ex.x + ex.y), ny = SPIKY_GRAD * (ey.x + ey.y), nz = SPIKY_GRAD * (ez.x + ez.y);
+    const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+    if (l > 0.0f) { nx /= l; ny /= l; nz /= l; }
+    const float4 w = omega[i];
+    const float4 v = vprime[i];
+    const float s = P.timestep * P.vort_eps;
+    vel[perm[i]] = make_float4(v.x + s * (ny * w.z - w.y * nz), v.y + s * (nz * w.x - w.z * nx),
+                               v.z + s * (nx * w.y - w.x * ny), 0.0f);       // cross(N, omega)
+}
+
+inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
+
+}  // namespace
+
+#define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs
+
+size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
+size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * 9 * TL; }
+
+int sweeps_init(void) {
+    cudaError_t e = cudaFuncSetAttribute(k_lambda<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lambda<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vorticity_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vorticity_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM2);
+    return e == cudaSuccess ? 0 : -1;
+}
+
+int launch_plan(pbf_sim *s) {
+    k_plan<<<ntiles(s->n), TL, 0, s->stream>>>(s->n, s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
+                                               s->tiled_sweeps ? 1 : 0);
+    return 1;
+}
+
+int launch_lambda(pbf_sim *s) {
+    k_lambda<false><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
+                                                              nullptr);
+    return 1;
+}
+
+int launch_delta_p(pbf_sim *s) {
+    k_delta_p<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s));
+    return 1;
+}
+
+int launch_vorticity_a(pbf_sim *s) {
+    k_vorticity_a<<<ntiles(s->n), TL, TL_SMEM2, s->stream>>>(s->n, s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
+                                                            s->omega, s->grid, sim_params(s));
+    return 1;
+}
+
+int launch_vorticity_b(pbf_sim *s) {
+    k_vorticity_b<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
+                                                            s->vel, s->grid, sim_params(s));
+    return 1;
+}
+
+int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s) + launch_vorticity_b(s); }
+
+int launch_density_diag(pbf_sim *s) {
+    k_lambda<true><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
+                                                             s->diag);
+    return 1;
+}
