@@ -77,8 +77,8 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
 struct TileCtx {
     int mode;            // 1 tiled, 0 general
     bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
-    const float4 *sm0, *sm1;
-    const u32 *runs;     // this thread's nine packed runs, stride TL
+    unsigned img;        // shared-window address of image 0 (image 1 follows at + TL_IMG)
+    u32 run[9];          // this thread's nine packed runs {image index:16 | count:15 | self:1}
 };
 
 __device__ __forceinline__ Pair make_pair(const float4 &a, const float4 &b) {
@@ -103,8 +103,11 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     const int *dg = desc + (size_t)blockIdx.x * TL_DESC;
     TileCtx c;
     c.mode = __ldg(dg + D_MODE);
-    c.sm0 = sm0; c.sm1 = sm1; c.self_in = false;
-    c.runs = runs + (size_t)blockIdx.x * 9 * TL + tid;
+    c.img = (unsigned)__cvta_generic_to_shared(sm0);
+    c.self_in = false;
+    const u32 *rp = runs + (size_t)blockIdx.x * 9 * TL + tid;
+#pragma unroll
+    for (int o = 0; o < 9; o++) c.run[o] = __ldg(rp + o * TL);   // in flight while the bulk copies land
     if (c.mode) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
         if (tid == 0) {
@@ -149,24 +152,27 @@ __device__ __forceinline__ void tile_wait(const TileCtx &c, unsigned long long *
     }
 }
 
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // Tiled walk of one particle: nine runs in the shared image, two candidates per iteration.
 // body(candidate pair of array 0, same pair of array 1, valid0, valid1)
 template <int NSRC, class F>
-__device__ __forceinline__ void tile_walk(TileCtx &c, u32 i, F body) {
-    u32 cur = __ldg(c.runs);
-#pragma unroll 1
+__device__ __forceinline__ void tile_walk(TileCtx &c, F body) {
+    c.self_in = (c.run[4] >> 31) != 0u;
+#pragma unroll
     for (int o = 0; o < 9; o++) {
-        const u32 nxt = o < 8 ? __ldg(c.runs + (o + 1) * TL) : 0u;
-        const int cnt = (int)((cur >> 16) & 0x7fffu);
-        if (o == 4) c.self_in = (cur >> 31) != 0u;
-        const float4 *p0 = c.sm0 + (cur & 0xffffu), *p1 = c.sm1 + (cur & 0xffffu);
+        unsigned a = c.img + 16u * (c.run[o] & 0xffffu);
+        const unsigned end = a + 16u * ((c.run[o] >> 16) & 0x7fffu);
 #pragma unroll 1
-        for (int k = 0; k < cnt; k += 2) {
-            const Pair p = make_pair(p0[k], p0[k + 1]);
-            if (NSRC == 2) body(p, make_pair(p1[k], p1[k + 1]), true, k + 1 < cnt);
-            else body(p, p, true, k + 1 < cnt);
+        for (; a < end; a += 32u) {
+            const Pair p = make_pair(lds128(a), lds128(a + 16u));
+            if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
+            else body(p, p, true, a + 16u < end);
         }
-        cur = nxt;
     }
 }
 
@@ -192,7 +198,7 @@ __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, const float
                                      const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                      const int2 *__restrict__ runs3, const int2 *__restrict__ cells, const GridInfo &g,
                                      u32 i, int tid, F body) {
-    if (c.mode) tile_walk<NSRC>(c, i, body);
+    if (c.mode) tile_walk<NSRC>(c, body);
     else general_walk<NSRC>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
 }
 
