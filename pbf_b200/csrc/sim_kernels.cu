@@ -28,51 +28,32 @@ __device__ __forceinline__ u32 cell_key(float x, float y, float z, const GridInf
     return k;
 }
 
-// ---- K1 predictpos.glsl:18-38 + cell key + digit histograms of every sort pass + clearhighlight.glsl ----------
+// ---- K1 predictpos.glsl:18-38 + cell key + clearhighlight.glsl: one particle per thread, pure streaming --------------
 __global__ void __launch_bounds__(256)
 k_predict(u32 first, u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
-          float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ hist, u32 *__restrict__ flags,
-          GridInfo g, SimParams P, SortPlan plan) {
-    __shared__ u32 sh[4 * PBF_RADIX];
-    for (int i = threadIdx.x; i < 4 * PBF_RADIX; i += blockDim.x) sh[i] = 0;
-    __syncthreads();
-    const u32 lane = threadIdx.x & 31;
-    const u32 stride = gridDim.x * blockDim.x;
-    const u32 nround = (n + 31u) & ~31u;
+          float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ flags, GridInfo g, SimParams P) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     bool any_hl = false;
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < nround; j += stride) {
-        const bool valid = j < n;
+    if (j < n) {
         const u32 i = first + j;
-        u32 key = 0;
-        if (valid) {
-            float4 p = pos[i];
-            float4 v = vel[i];
-            // exact, uncontracted binary32 in the order of the shader so that keys are bit-identical to the oracle
-            if (P.extforce && p.z > (float)g.gz / 2.0f)
-                v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fmul_rn(2.0f, P.gravity), -1.0f), P.timestep));
-            v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(P.gravity, -1.0f), P.timestep));
-            p.x = __fadd_rn(p.x, __fmul_rn(P.timestep, v.x));
-            p.y = __fadd_rn(p.y, __fmul_rn(P.timestep, v.y));
-            p.z = __fadd_rn(p.z, __fmul_rn(P.timestep, v.z));
-            p.w = __int_as_float((int)i);
-            pred[i] = p;
-            key = cell_key(p.x, p.y, p.z, g);
-            keys[i] = key;
-            // clearhighlight.glsl: flag &= 1 (written back only when it changes anything)
-            u32 h = hl[i];
-            if (h & ~1u) hl[i] = h & 1u;
-            any_hl |= (h & 1u) != 0;
-        }
-        for (int p = 0; p < plan.passes; p++) {    // plan.passes = 0: the caller histograms later (slab mode)
-            u32 d = valid ? ((key >> plan.shift[p]) & plan.mask[p]) : 0xffffffffu;
-            u32 m = __match_any_sync(0xffffffffu, d);
-            if (valid && lane == (u32)(__ffs(m) - 1)) atomicAdd(&sh[p * PBF_RADIX + d], (u32)__popc(m));
-        }
+        float4 p = pos[i];
+        float4 v = vel[i];
+        const u32 h = hl[i];
+        // exact, uncontracted binary32 in the order of the shader so that keys are bit-identical to the oracle
+        if (P.extforce && p.z > (float)g.gz / 2.0f)
+            v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fmul_rn(2.0f, P.gravity), -1.0f), P.timestep));
+        v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(P.gravity, -1.0f), P.timestep));
+        p.x = __fadd_rn(p.x, __fmul_rn(P.timestep, v.x));
+        p.y = __fadd_rn(p.y, __fmul_rn(P.timestep, v.y));
+        p.z = __fadd_rn(p.z, __fmul_rn(P.timestep, v.z));
+        p.w = __int_as_float((int)i);
+        pred[i] = p;
+        keys[i] = cell_key(p.x, p.y, p.z, g);
+        // clearhighlight.glsl: flag &= 1 (written back only when it changes anything)
+        if (h & ~1u) hl[i] = h & 1u;
+        any_hl = (h & 1u) != 0;
     }
-    if (__any_sync(0xffffffffu, any_hl) && lane == 0) flags[0] = 1u;
-    __syncthreads();
-    for (int i = threadIdx.x; i < plan.passes * PBF_RADIX; i += blockDim.x)
-        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+    if (__any_sync(0xffffffffu, any_hl) && (threadIdx.x & 31) == 0) flags[0] = 1u;
 }
 
 // appended halo records already hold p*: cell keys only
@@ -191,16 +172,16 @@ k_highlight(u32 n, const u32 *__restrict__ home, const u32 *__restrict__ perm, c
     __shared__ int2 srun[9 * NB_BLOCK];
     if (flags[0] == 0u) return;                      // nobody carries bit 0: the kernel is a no-op
     const int tid = threadIdx.x;
-    const u32 i = blockIdx.x * NB_BLOCK + tid;
-    if (i >= n) return;
-    if ((hl[perm[i]] & 1u) == 0u) return;
-    int slots;
-    bool self_in;
-    const int cnt = load_runs<NB_BLOCK>(home[i], i, g, runs3, cells, srun, tid, &slots, &self_in);
-    for (int o = 0; o < cnt; o++) {
-        const int2 r = srun[o * NB_BLOCK + tid];
-        for (int j = r.x; j < r.y; j++)
-            if (j != (int)i) atomicOr(&hl[perm[j]], 2u);
+    for (u32 i = blockIdx.x * NB_BLOCK + tid; i < n; i += gridDim.x * NB_BLOCK) {
+        if ((hl[perm[i]] & 1u) == 0u) continue;
+        int slots;
+        bool self_in;
+        const int cnt = load_runs<NB_BLOCK>(home[i], i, g, runs3, cells, srun, tid, &slots, &self_in);
+        for (int o = 0; o < cnt; o++) {
+            const int2 r = srun[o * NB_BLOCK + tid];
+            for (int j = r.x; j < r.y; j++)
+                if (j != (int)i) atomicOr(&hl[perm[j]], 2u);
+        }
     }
 }
 
@@ -285,14 +266,10 @@ int launch_unclear_cells(pbf_sim *s) {
 
 int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist) {
     if (count == 0) return 0;
-    int blocks = nblocks(count, 256);
-    int maxb = s->sm_count * 8;
-    if (blocks > maxb) blocks = maxb;
-    SortPlan plan = s->plan;
-    if (!with_hist) plan.passes = 0;
-    k_predict<<<blocks, 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->hist, s->flags,
-                                             s->grid, sim_params(s), plan);
-    return 1;
+    k_predict<<<nblocks(count, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                          s->grid, sim_params(s));
+    // digit histograms of all sort passes: the keys just written are still in L2
+    return 1 + (with_hist ? launch_sort_hist(s, s->keys + first, count) : 0);
 }
 
 int launch_predict(pbf_sim *s) { return launch_predict_range(s, 0, s->n, true); }
@@ -312,8 +289,10 @@ int launch_reorder_cells(pbf_sim *s) {
 }
 
 int launch_highlight(pbf_sim *s) {
-    k_highlight<<<nblocks(s->n, NB_BLOCK), NB_BLOCK, 0, s->stream>>>(s->n, s->home, s->perm, s->runs3, s->cells, s->hl,
-                                                                     s->flags, s->grid);
+    // a few blocks per SM striding over the particles: the usual case is "nothing selected", a no-op worth ~2 us
+    int blocks = nblocks(s->n, NB_BLOCK);
+    if (blocks > s->sm_count * 4) blocks = s->sm_count * 4;
+    k_highlight<<<blocks, NB_BLOCK, 0, s->stream>>>(s->n, s->home, s->perm, s->runs3, s->cells, s->hl, s->flags, s->grid);
     return 1;
 }
 

@@ -8,7 +8,8 @@
 // STABLE sort on the low plan.bits bits of the key (globalsort.glsl:62-64 proves the reference is stable; bits
 // above plan.bits, e.g. the ceiling wrap of SURVEY.md a3, ride along unsorted exactly as in the reference).
 //
-// Algorithmic traffic: 4 B/particle for the digit histograms (fused into the predict kernel) and 16 B per pass.
+// Algorithmic traffic: 4 B/particle for the digit histograms (read back from L2 right after k_predict wrote the keys)
+// and 16 B per pass.
 #include "pbf_internal.cuh"
 
 namespace {
@@ -46,15 +47,47 @@ __global__ void __launch_bounds__(PBF_RADIX) k_sort_scan(u32 *__restrict__ hist,
     if (d == 0) tile_counter[pass] = 0;
 }
 
-// standalone histogram (pbf_sort_pairs only; the simulation step fuses this into k_predict)
+// digit histograms of every pass.  Cell keys of neighbouring ids share most digits (plain shared atomics would
+// serialise 32 lanes on one bin, match.any costs a pass over the distinct values): every thread takes 16 consecutive
+// keys and run-length encodes each digit stream in registers, one shared atomic per run.
 __global__ void __launch_bounds__(256) k_sort_hist(const u32 *__restrict__ keys, u32 n, SortPlan plan,
                                                     u32 *__restrict__ hist) {
     __shared__ u32 sh[4 * PBF_RADIX];
     for (int i = threadIdx.x; i < 4 * PBF_RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        u32 k = keys[i];
-        for (int p = 0; p < plan.passes; p++) atomicAdd(&sh[p * PBF_RADIX + ((k >> plan.shift[p]) & plan.mask[p])], 1u);
+    const u32 chunks = (n + 15u) >> 4;
+    for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x) {
+        u32 k[16];
+        const u32 base = c << 4;
+        if (base + 16u <= n && (reinterpret_cast<uintptr_t>(keys) & 15u) == 0) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(keys + base);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 v = __ldg(q + j);
+                k[4 * j] = v.x; k[4 * j + 1] = v.y; k[4 * j + 2] = v.z; k[4 * j + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) k[j] = base + j < n ? __ldg(keys + base + j) : 0u;
+        }
+        const int cnt = (int)min(16u, n - base);
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            if (p < plan.passes) {
+                const int sft = plan.shift[p];
+                const u32 msk = plan.mask[p];
+                u32 cur = (k[0] >> sft) & msk, run = 1;
+#pragma unroll
+                for (int j = 1; j < 16; j++) {
+                    const u32 d = (k[j] >> sft) & msk;
+                    if (j < cnt) {
+                        if (d != cur) { atomicAdd(&sh[p * PBF_RADIX + cur], run); cur = d; run = 0; }
+                        run++;
+                    }
+                }
+                atomicAdd(&sh[p * PBF_RADIX + cur], run);
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < plan.passes * PBF_RADIX; i += blockDim.x)
@@ -230,7 +263,7 @@ int launch_sort_passes(pbf_sim *s) {
 
 // digit histograms of every pass of the handle's plan over keys[0..n) (slab mode: keys change after k_predict)
 int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n) {
-    int blocks = (int)((n + 255) / 256);
+    int blocks = (int)(((n + 15) / 16 + 255) / 256);
     int maxb = s->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
@@ -240,7 +273,7 @@ int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n) {
 
 int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, int bits) {
     SortPlan plan = make_sort_plan(bits);
-    int blocks = (int)((n + 255) / 256);
+    int blocks = (int)(((n + 15) / 16 + 255) / 256);
     int maxb = s->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
