@@ -7,7 +7,7 @@
 // o = (dy,dz) of all its particles lie inside ONE contiguous range of the sorted array, about 256 + 3 records long.
 //   * k_plan (once per step, after the cell tables): per particle its nine runs (this is K7, evaluated once per step
 //     as in the reference), per tile the nine ranges [S_o, S_o + n_o) that cover them; the runs are stored relative to
-//     the tile's shared-memory image (16-bit start, 15-bit count: 36 B per particle).
+//     the tile's shared-memory image (12-bit start, 5-bit count: 20 B per particle).
 //   * every sweep: one thread issues nine 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) that
 //     bring the tile's nine ranges into shared memory verbatim -- no per-record instructions, no LSU wavefronts for
 //     staging; meanwhile the other threads fetch their runs.  A thread then walks its nine runs in the image, two
@@ -29,6 +29,7 @@ constexpr int TL = NB_BLOCK;     // particles per tile = threads per block
 constexpr int TL_CAP = 3328;     // most records a tile stages, 16 B each: 12 lattice lines of 256 + slack; 52 KB
 constexpr int TL_DESC = 32;      // ints per tile descriptor: mode, records, nine range starts, nine range lengths
 constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11;
+constexpr int RUN_WORDS = 5;     // packed runs of one particle
 constexpr size_t TL_IMG = (size_t)(TL_CAP + 1) * sizeof(float4);   // one image (+1 finite pad record)
 constexpr size_t TL_SMEM1 = TL_IMG;                                // 4 blocks per SM
 constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays: 2 blocks per SM
@@ -56,17 +57,23 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
     __syncthreads();
     int total = 0;
     bool fits = true;
-    u32 *out = runs + (size_t)blockIdx.x * 9 * TL + tid;
+    // nine 17-bit fields {image index of the run's first record:12 | count:5} and, in bit 153, "run 4 holds the particle
+    // itself", packed into RUN_WORDS words per particle
+    u32 w[RUN_WORDS] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
     for (int o = 0; o < 9; o++) {
         const int no = sE[o] >= 0 ? sE[o] - sS[o] : 0;
-        // image index of the run's first record | count; an empty run is 0
-        u32 v = r[o].y > 0 ? (u32)(r[o].x - sS[o] + total) | ((u32)r[o].y << 16) : 0u;
-        if (o == 4 && (int)i >= r[4].x && (int)i < r[4].x + r[4].y) v |= 0x80000000u;   // the run holds the particle itself
-        out[o * TL] = v;
-        fits = fits && r[o].y < 32768;
+        const u32 v = r[o].y > 0 ? (u32)((r[o].x - sS[o] + total) & 0xfff) | ((u32)(r[o].y & 31) << 12) : 0u;
+        constexpr int RB = 17;
+        w[(RB * o) >> 5] |= v << ((RB * o) & 31);
+        if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= v >> (32 - ((RB * o) & 31));
+        fits = fits && r[o].y < 32;
         total += no;
     }
+    if ((int)i >= r[4].x && (int)i < r[4].x + r[4].y) w[4] |= 1u << 25;
+    u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
+#pragma unroll
+    for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
     fits = __syncthreads_and(fits && total <= TL_CAP && allow);
     int *d = desc + (size_t)blockIdx.x * TL_DESC;
     if (tid == 0) { d[D_MODE] = fits ? 1 : 0; d[D_TOTAL] = total; }
@@ -78,7 +85,7 @@ struct TileCtx {
     int mode;            // 1 tiled, 0 general
     bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
     unsigned img;        // shared-window address of image 0 (image 1 follows at + TL_IMG)
-    u32 run[9];          // this thread's nine packed runs {image index:16 | count:15 | self:1}
+    u32 run[9];          // this thread's nine runs {image index:12 | count:5}
 };
 
 __device__ __forceinline__ Pair make_pair(const float4 &a, const float4 &b) {
@@ -105,9 +112,14 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     c.mode = __ldg(dg + D_MODE);
     c.img = (unsigned)__cvta_generic_to_shared(sm0);
     c.self_in = false;
-    const u32 *rp = runs + (size_t)blockIdx.x * 9 * TL + tid;
+    const u32 *rp = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
+    u32 w[RUN_WORDS + 1];
 #pragma unroll
-    for (int o = 0; o < 9; o++) c.run[o] = __ldg(rp + o * TL);   // in flight while the bulk copies land
+    for (int k = 0; k < RUN_WORDS; k++) w[k] = __ldg(rp + k * TL);   // in flight while the bulk copies land
+    w[RUN_WORDS] = 0u;
+#pragma unroll
+    for (int o = 0; o < 9; o++) c.run[o] = __funnelshift_r(w[(17 * o) >> 5], w[((17 * o) >> 5) + 1], (17 * o) & 31) & 0x1ffffu;
+    c.self_in = ((w[4] >> 25) & 1u) != 0u;
     if (c.mode) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
         if (tid == 0) {
@@ -162,11 +174,10 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 // body(candidate pair of array 0, same pair of array 1, valid0, valid1)
 template <int NSRC, class F>
 __device__ __forceinline__ void tile_walk(TileCtx &c, F body) {
-    c.self_in = (c.run[4] >> 31) != 0u;
 #pragma unroll
     for (int o = 0; o < 9; o++) {
-        unsigned a = c.img + 16u * (c.run[o] & 0xffffu);
-        const unsigned end = a + 16u * ((c.run[o] >> 16) & 0x7fffu);
+        unsigned a = c.img + 16u * (c.run[o] & 0xfffu);
+        const unsigned end = a + 16u * (c.run[o] >> 12);
 #pragma unroll 1
         for (; a < end; a += 32u) {
             const Pair p = make_pair(lds128(a), lds128(a + 16u));
@@ -371,7 +382,7 @@ inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
 #define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs
 
 size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
-size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * 9 * TL; }
+size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 
 int sweeps_init(void) {
     cudaError_t e = cudaFuncSetAttribute(k_lambda<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
