@@ -157,7 +157,8 @@ int pbf_get_diagnostics(pbf_handle h, double *density_error, double *kinetic_ene
 
 /* Tiles (256 consecutive sorted particles) of the last pbf_build_cells / step, and how many of them run the
  * shared-memory tiled sweep path; the rest walk their neighbour runs from global memory ("sweeps").
- * why (may be NULL): [0] tiled, [1] ranges do not fit the shared-memory image; the rest is reserved. */
+ * why (may be NULL): [0] tiled, [1] ranges do not fit the shared-memory image; [2..7] tiles whose nine ranges hold
+ * <= 2304, 2560, 2816, 3072, 3328, more records (what sizes the image). */
 int pbf_get_tile_stats(pbf_handle h, uint32_t *tiles, uint32_t *tiled, uint32_t why[8]);
 
 /* how many kernels the handle has launched (graph replays count their kernel nodes) */

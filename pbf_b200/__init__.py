@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpbf_b200.so")
+# PBF_B200_LIB: another build of the same library (kernel experiments); there is no other implementation to fall back to
+LIB_PATH = os.environ.get("PBF_B200_LIB") or os.path.join(_HERE, "libpbf_b200.so")
 
 PBF_KEY_NOCELL = 0x80000000
 

@@ -559,7 +559,13 @@ int pbf_get_tile_stats(pbf_handle s, uint32_t *tiles, uint32_t *tiled, uint32_t 
     for (size_t t = 0; t < nt; t += stride) {
         a++;
         b += tmp[t] != 0;
-        if (why) why[tmp[t] != 0 ? 0 : 1]++;
+        if (why) {
+            why[tmp[t] != 0 ? 0 : 1]++;
+            // staged records of the tile (desc[1]) in six classes: <= 2304, 2560, 2816, 3072, 3328, more
+            const int total = tmp[t + 1];
+            int c = total <= 2304 ? 0 : (total - 2304 + 255) / 256;
+            why[2 + (c > 5 ? 5 : c)]++;
+        }
     }
     if (tiles) *tiles = a;
     if (tiled) *tiled = b;

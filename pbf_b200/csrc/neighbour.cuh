@@ -12,7 +12,7 @@ constexpr float H = 2.0f;                                // src/SPH.cpp:58
 constexpr float H2 = 4.0f;
 constexpr float POLY6 = 1.56668147106f / 512.0f;         // calclambda.glsl:46, /h^9
 constexpr float SPIKY_GRAD = -3.0f * 4.774648292756860f / 64.0f;   // calclambda.glsl:63, /h^6
-constexpr float FAR = 1.0e8f;       // a masked candidate is moved here: r2 = 1e16 -> both kernels vanish, no inf/nan
+constexpr float FAR2 = 1.0e8f;      // r2 of a masked candidate: clamped to h^2 -> both kernels vanish, no inf/nan
 constexpr float TINY = 1.0e-24f;    // r2 clamp: rsqrt stays finite and c*d = 0 for coincident particles (l == 0 branch)
 
 // neighbourcells.glsl:62-84 for the window x-1..x+1 of one row: first existing start, summed sizes
@@ -90,26 +90,27 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
     return y;
 }
 
-// geometry of one candidate pair against particle p: d = p - c, r2, 1/l, and the two NEGATED clamped factors
-// tn = min(r^2 - h^2, 0) = -(h^2 - r^2)+ and t2n = min(l - h, 0) = -(h - l)+.  Odd powers of them carry a minus sign the
-// callers fold into their final constants (one FADD2 with an immediate each instead of FFMA2 + FADD2 + FMUL2).
+// geometry of one candidate pair against particle p: d = p - c, r2, 1/l, and the two NEGATED factors
+// tn = rc - h^2 = -(h^2 - r^2)+ and t2n = l - h = -(h - l)+ with rc = min(r2 + TINY, h^2), l = rc / sqrt(rc): beyond the
+// support radius both factors vanish without a separate clamp to zero, at r = 0 rsqrt stays finite and c*d = 0 like
+// the l == 0 branch of gradWspiky (r2 + TINY == r2 in binary32 for every r2 > 1e-17).  Odd powers carry a minus sign the
+// callers fold into their final constants.  Members outside the run (v0/v1 false) get rc = h^2, i.e. they leave kernel
+// support; their d is finite (a real record or a zeroed pad record), so 0 * d = 0.
 struct PairGeom {
     float2 dx, dy, dz, r2, il, t, t2;
 };
 
 __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bool v0, bool v1) {
     PairGeom q;
-    const float x0 = v0 ? c.x.x : FAR, x1 = v1 ? c.x.y : FAR;     // out-of-run members leave kernel support
-    q.dx = make_float2(p.x - x0, p.x - x1);
+    q.dx = make_float2(p.x - c.x.x, p.x - c.x.y);
     q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
     q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
     q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));
-    // the clamp keeps rsqrt finite at r = 0 (self, coincident): there c*d = 0 like the l == 0 branch of gradWspiky
-    q.il = make_float2(rsqrt_ftz(fmaxf(q.r2.x, TINY)), rsqrt_ftz(fmaxf(q.r2.y, TINY)));
-    const float2 l = __fmul2_rn(q.r2, q.il);
-    const float2 a = __fadd2_rn(l, make_float2(-H, -H)), b = __fadd2_rn(q.r2, make_float2(-H2, -H2));
-    q.t2 = make_float2(fminf(a.x, 0.0f), fminf(a.y, 0.0f));         // gradWspiky = 0 for l > h
-    q.t = make_float2(fminf(b.x, 0.0f), fminf(b.y, 0.0f));          // Wpoly6 = 0 for r > h
+    const float2 re = __fadd2_rn(q.r2, make_float2(TINY, TINY));
+    const float2 rc = make_float2(fminf(v0 ? re.x : FAR2, H2), fminf(v1 ? re.y : FAR2, H2));
+    q.il = make_float2(rsqrt_ftz(rc.x), rsqrt_ftz(rc.y));
+    q.t2 = __ffma2_rn(rc, q.il, make_float2(-H, -H));                // l - h: 0 at and beyond the support radius
+    q.t = __fadd2_rn(rc, make_float2(-H2, -H2));                     // r^2 - h^2, exactly <= 0
     return q;
 }
 

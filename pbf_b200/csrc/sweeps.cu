@@ -26,11 +26,21 @@
 namespace {
 
 constexpr int TL = NB_BLOCK;     // particles per tile = threads per block
-constexpr int TL_CAP = 3328;     // most records a tile stages, 16 B each: 12 lattice lines of 256 + slack; 52 KB
-constexpr int TL_DESC = 32;      // ints per tile descriptor: mode, records, nine range starts, nine range lengths
-constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11;
+#ifndef PBF_TL_CAP
+#define PBF_TL_CAP 3328
+#endif
+#ifndef PBF_TL_CTAS
+#define PBF_TL_CTAS 4
+#endif
+constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B each (52 KB: four blocks per SM).  Measured on
+                                     // B200: 2560 records / five blocks per SM is no faster (the sweeps are bound by FMA-pipe,
+                                     // issue and shared-memory cycles together, not by residency), and stages 7 % of the tiles twice
+constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
+constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
+constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20;
 constexpr int RUN_WORDS = 5;     // packed runs of one particle
-constexpr size_t TL_IMG = (size_t)(TL_CAP + 1) * sizeof(float4);   // one image (+1 finite pad record)
+constexpr int TL_PAD = 4;        // zeroed records after the last range: a walk reads up to 3 records past its run
+constexpr size_t TL_IMG = (size_t)(TL_CAP + TL_PAD) * sizeof(float4);   // one image
 constexpr size_t TL_SMEM1 = TL_IMG;                                // 4 blocks per SM
 constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays: 2 blocks per SM
 
@@ -55,7 +65,10 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
         if (lane == 0 && b >= 0) { atomicMin(&sS[o], a); atomicMax(&sE[o], b); }
     }
     __syncthreads();
-    int total = 0;
+    // Greedy phases: ranges are staged in order o = 0..8; a phase ends before the range that would overflow the image.
+    // cut = 4-bit first-range index of every phase, closed by 9 (one phase: 0x90).
+    int total = 0, fill = 0, nph = 1;
+    u32 cut = 0;
     bool fits = true;
     // nine 17-bit fields {image index of the run's first record:12 | count:5} and, in bit 153, "run 4 holds the particle
     // itself", packed into RUN_WORDS words per particle
@@ -63,26 +76,30 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
 #pragma unroll
     for (int o = 0; o < 9; o++) {
         const int no = sE[o] >= 0 ? sE[o] - sS[o] : 0;
-        const u32 v = r[o].y > 0 ? (u32)((r[o].x - sS[o] + total) & 0xfff) | ((u32)(r[o].y & 31) << 12) : 0u;
+        if (fill + no > TL_CAP) { if (nph < 7) cut |= (u32)o << (4 * nph); nph++; fill = 0; }
+        const u32 v = r[o].y > 0 ? (u32)((r[o].x - sS[o] + fill) & 0xfff) | ((u32)(r[o].y & 31) << 12) : 0u;
         constexpr int RB = 17;
         w[(RB * o) >> 5] |= v << ((RB * o) & 31);
         if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= v >> (32 - ((RB * o) & 31));
-        fits = fits && r[o].y < 32;
+        fits = fits && r[o].y < 32 && no <= TL_CAP;
+        fill += no;
         total += no;
     }
+    if (nph < 8) cut |= 9u << (4 * nph);
     if ((int)i >= r[4].x && (int)i < r[4].x + r[4].y) w[4] |= 1u << 25;
     u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
-    fits = __syncthreads_and(fits && total <= TL_CAP && allow);
+    fits = __syncthreads_and(fits && nph <= TL_PHASES && allow);
     int *d = desc + (size_t)blockIdx.x * TL_DESC;
-    if (tid == 0) { d[D_MODE] = fits ? 1 : 0; d[D_TOTAL] = total; }
+    if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = total; d[D_CUT] = (int)cut; }
     if (tid < 9) { d[D_S + tid] = sE[tid] >= 0 ? sS[tid] : 0; d[D_N + tid] = sE[tid] >= 0 ? sE[tid] - sS[tid] : 0; }
 }
 
 // ---- tile frame of the sweeps -------------------------------------------------------------------------------------------
 struct TileCtx {
-    int mode;            // 1 tiled, 0 general
+    int mode;            // staging phases of the tiled path (1 for almost every tile), 0 = general path
+    u32 cut;             // first range of every phase, 4 bits each, closed by 9
     bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
     unsigned img;        // shared-window address of image 0 (image 1 follows at + TL_IMG)
     u32 run[9];          // this thread's nine runs {image index:12 | count:5}
@@ -99,19 +116,52 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-// All threads of the block call this.  Thread 0 reads the tile descriptor and issues the bulk copies of the nine
-// ranges of NSRC arrays; everybody then waits on the mbarrier (the caller overlaps its own loads before tile_wait).
+// Thread 0: stage ranges [lo, hi) of NSRC arrays into the image(s): zeroed pad records after the last range (a walk
+// reads up to TL_PAD - 1 records past its run; they are masked but must be finite), then one arrive.expect_tx -- its
+// release makes the pad visible to everybody who passes the wait -- and one bulk copy per non-empty range.
+template <int NSRC>
+__device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, const float4 *__restrict__ src0,
+                                           const float4 *__restrict__ src1, const int *__restrict__ dg, int lo, int hi) {
+    float4 *sm0 = reinterpret_cast<float4 *>(dsm);
+    float4 *sm1 = sm0 + (TL_CAP + TL_PAD);
+    // the whole descriptor in five independent 16-byte loads, before anything waits on it
+    const int4 *d4 = reinterpret_cast<const int4 *>(dg);
+    const int4 q0 = __ldg(d4), q1 = __ldg(d4 + 1), q2 = __ldg(d4 + 2), q3 = __ldg(d4 + 3), q4 = __ldg(d4 + 4);
+    const int dv[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w,
+                        q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
+    int total = 0;
+#pragma unroll
+    for (int o = 0; o < 9; o++) total += (o >= lo && o < hi) ? dv[D_N + o] : 0;
+#pragma unroll
+    for (int k = 0; k < TL_PAD; k++) {
+        sm0[total + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (NSRC == 2) sm1[total + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(total * 16 * NSRC)) : "memory");
+    const unsigned a0 = (unsigned)__cvta_generic_to_shared(sm0), a1 = (unsigned)__cvta_generic_to_shared(sm1);
+    int at = 0;
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+        const int so = dv[D_S + o], no = (o >= lo && o < hi) ? dv[D_N + o] : 0;
+        if (no > 0) {
+            bulk_g2s(a0 + 16u * at, src0 + so, 16u * no, mb);
+            if (NSRC == 2) bulk_g2s(a1 + 16u * at, src1 + so, 16u * no, mb);
+        }
+        at += no;
+    }
+}
+
+// All threads of the block call this.  Thread 0 initialises the mbarrier and stages the first phase; meanwhile the
+// others fetch their runs (the caller overlaps its own loads before tile_sweep).
 template <int NSRC>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
                                               const u32 *__restrict__ runs, int tid) {
-    float4 *sm0 = reinterpret_cast<float4 *>(dsm);
-    float4 *sm1 = sm0 + (TL_CAP + 1);
     const int *dg = desc + (size_t)blockIdx.x * TL_DESC;
     TileCtx c;
     c.mode = __ldg(dg + D_MODE);
-    c.img = (unsigned)__cvta_generic_to_shared(sm0);
-    c.self_in = false;
+    c.cut = (u32)__ldg(dg + D_CUT);
+    c.img = (unsigned)__cvta_generic_to_shared(dsm);
     const u32 *rp = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
     u32 w[RUN_WORDS + 1];
 #pragma unroll
@@ -120,48 +170,23 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
 #pragma unroll
     for (int o = 0; o < 9; o++) c.run[o] = __funnelshift_r(w[(17 * o) >> 5], w[((17 * o) >> 5) + 1], (17 * o) & 31) & 0x1ffffu;
     c.self_in = ((w[4] >> 25) & 1u) != 0u;
-    if (c.mode) {
+    if (c.mode && tid == 0) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
-        if (tid == 0) {
-            // the whole descriptor in five independent 16-byte loads, before anything waits on it
-            const int4 *d4 = reinterpret_cast<const int4 *>(dg);
-            const int4 q0 = __ldg(d4), q1 = __ldg(d4 + 1), q2 = __ldg(d4 + 2), q3 = __ldg(d4 + 3), q4 = __ldg(d4 + 4);
-            const int dv[20] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w,
-                                q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w};
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            const int total = dv[D_TOTAL];
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(total * 16 * NSRC)) : "memory");
-            const unsigned a0 = (unsigned)__cvta_generic_to_shared(sm0), a1 = (unsigned)__cvta_generic_to_shared(sm1);
-            int at = 0;
-#pragma unroll
-            for (int o = 0; o < 9; o++) {
-                const int so = dv[D_S + o], no = dv[D_N + o];
-                if (no > 0) {
-                    bulk_g2s(a0 + 16u * at, src0 + so, 16u * no, mb);
-                    if (NSRC == 2) bulk_g2s(a1 + 16u * at, src1 + so, 16u * no, mb);
-                }
-                at += no;
-            }
-            sm0[total] = make_float4(0.f, 0.f, 0.f, 0.f);      // the record after the last run: read, then masked
-            if (NSRC == 2) sm1[total] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tile_stage<NSRC>(dsm, mb, src0, src1, dg, 0, (int)((c.cut >> 4) & 15u));
     }
     return c;
 }
 
-__device__ __forceinline__ void tile_wait(const TileCtx &c, unsigned long long *mbar) {
-    __syncthreads();                                       // the barrier is initialised, the pad record written
-    if (c.mode) {
-        const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "WAIT_%=:\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
-            "@!p bra WAIT_%=;\n"
-            "}\n" ::"r"(mb) : "memory");
-    }
+__device__ __forceinline__ void mbar_wait(unsigned mb, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "}\n" ::"r"(mb), "r"(parity) : "memory");
 }
 
 __device__ __forceinline__ float4 lds128(unsigned addr) {
@@ -170,20 +195,36 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
     return v;
 }
 
-// Tiled walk of one particle: nine runs in the shared image, two candidates per iteration.
+// Tiled sweep of one particle, all threads of the block (threads without a particle hold nine empty runs): per
+// phase wait for the image, then walk the runs staged in it, two candidates per iteration.
 // body(candidate pair of array 0, same pair of array 1, valid0, valid1)
 template <int NSRC, class F>
-__device__ __forceinline__ void tile_walk(TileCtx &c, F body) {
-#pragma unroll
-    for (int o = 0; o < 9; o++) {
-        unsigned a = c.img + 16u * (c.run[o] & 0xfffu);
-        const unsigned end = a + 16u * (c.run[o] >> 12);
+__device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsigned long long *mbar,
+                                           const float4 *__restrict__ src0, const float4 *__restrict__ src1,
+                                           const int *__restrict__ desc, int tid, F body) {
+    const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+    __syncthreads();                                       // the barrier is initialised
+    int lo = 0;
 #pragma unroll 1
-        for (; a < end; a += 32u) {
-            const Pair p = make_pair(lds128(a), lds128(a + 16u));
-            if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
-            else body(p, p, true, a + 16u < end);
+    for (int ph = 0; ph < c.mode; ph++) {
+        const int hi = (int)((c.cut >> (4 * ph + 4)) & 15u);
+        if (ph > 0) {
+            __syncthreads();                               // everybody is done with the previous phase's image
+            if (tid == 0) tile_stage<NSRC>(dsm, mb, src0, src1, desc + (size_t)blockIdx.x * TL_DESC, lo, hi);
         }
+        mbar_wait(mb, (unsigned)(ph & 1));
+#pragma unroll
+        for (int o = 0; o < 9; o++) {
+            unsigned a = c.img + 16u * (c.run[o] & 0xfffu);
+            const unsigned end = (o >= lo && o < hi) ? a + 16u * (c.run[o] >> 12) : a;
+#pragma unroll 1
+            for (; a < end; a += 32u) {
+                const Pair p = make_pair(lds128(a), lds128(a + 16u));
+                if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
+                else body(p, p, true, a + 16u < end);
+            }
+        }
+        lo = hi;
     }
 }
 
@@ -203,14 +244,14 @@ __device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, con
     });
 }
 
-// both paths, for a thread that has a particle
+// both paths; every thread of the block calls this (the tiled path synchronises the block), `live` = has a particle
 template <int NSRC, class F>
-__device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, const float4 *__restrict__ src0,
+__device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                      const float4 *__restrict__ src1, const u32 *__restrict__ home,
-                                     const int2 *__restrict__ runs3, const int2 *__restrict__ cells, const GridInfo &g,
-                                     u32 i, int tid, F body) {
-    if (c.mode) tile_walk<NSRC>(c, body);
-    else general_walk<NSRC>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+                                     const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
+                                     const int *__restrict__ desc, const GridInfo &g, u32 i, bool live, int tid, F body) {
+    if (c.mode) tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body);
+    else if (live) general_walk<NSRC>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
 }
 
 #define TILE_ARGS const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,   \
@@ -219,7 +260,7 @@ __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, const float
 // ---- K8 calclambda.glsl:66-103 ------------------------------------------------------------------------------------
 // out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
 template <bool DIAG>
-__global__ void __launch_bounds__(TL)
+__global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -229,10 +270,8 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     const bool live = i < n;
     float err = 0.0f;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    tile_wait(tc, &mbar);
-    if (live) {
-        float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
-        walk<1>(tc, dsm, A, A, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
+    walk<1>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);       // (h-l)^2 / l
@@ -240,7 +279,8 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
             gx = __ffma2_rn(cc, q.dx, gx);
             gy = __ffma2_rn(cc, q.dy, gy);
             gz = __ffma2_rn(cc, q.dz, gz);
-        });
+    });
+    if (live) {
         // FOR_EACH_NEIGHBOUR skips j == i (foreachneighbour.glsl:9): self only ever adds (h^2)^3 = 64 to the poly6 sum
         float rs = -(rho.x + rho.y);
         if (tc.self_in) rs -= 64.0f;
@@ -267,7 +307,7 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
 }
 
 // ---- K9 updatepos.glsl:43-105, Jacobi: reads B {p, lambda}, writes A -----------------------------------------------
-__global__ void __launch_bounds__(TL)
+__global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -276,8 +316,6 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
     TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    tile_wait(tc, &mbar);
-    if (!live) return;
     float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
     // scorr = -k (scale W)^4 = -(k scale^4 POLY6^4) t^12 with t = max(h^2 - r^2, 0)        (updatepos.glsl:57-60)
     float sc4 = P.tensile_scale * POLY6;
@@ -285,7 +323,7 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
     sc4 *= sc4;
     const float nk = -P.tensile_k * sc4;
     const float2 nk2 = make_float2(nk, nk), li2 = make_float2(pi.w, pi.w);
-    walk<1>(tc, dsm, B, B, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         float2 t3 = __fmul2_rn(__fmul2_rn(q.t, q.t), q.t);
         t3 = __fmul2_rn(t3, t3);
@@ -296,6 +334,7 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
         ay = __ffma2_rn(cc, q.dy, ay);
         az = __ffma2_rn(cc, q.dz, az);
     });
+    if (!live) return;
     const float s = SPIKY_GRAD * P.one_over_rho_0;
     float x = pi.x + s * (ax.x + ax.y), y = pi.y + s * (ay.x + ay.y), z = pi.z + s * (az.x + az.y);
     x = fminf(fmaxf(x, g.wlo[0]), g.whi[0]);                               // updatepos.glsl:98-100
@@ -317,11 +356,9 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    tile_wait(tc, &mbar);
-    if (!live) return;
     float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
     const float2 neg1 = make_float2(-1.0f, -1.0f);
-    walk<2>(tc, dsm, A, svel, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
+    walk<2>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
         const float2 uy = make_float2(u.y.x - vi.y, u.y.y - vi.y);
@@ -337,6 +374,7 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
         wy = __ffma2_rn(uz, gx, __ffma2_rn(__fmul2_rn(gz, ux), neg1, wy));
         wz = __ffma2_rn(ux, gy, __ffma2_rn(__fmul2_rn(gx, uy), neg1, wz));
     });
+    if (!live) return;
     const float cw = -P.xsph_c * POLY6;
     vprime[i] = make_float4(vi.x + cw * (vx.x + vx.y), vi.y + cw * (vy.x + vy.y), vi.z + cw * (vz.x + vz.y), 0.0f);
     const float ox = SPIKY_GRAD * (wx.x + wx.y), oy = SPIKY_GRAD * (wy.x + wy.y), oz = SPIKY_GRAD * (wz.x + wz.y);
@@ -345,7 +383,7 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
 }
 
 // ---- K11 vorticity.glsl:65-85 (second sweep): confinement force, velocity[id] written once -------------------------------
-__global__ void __launch_bounds__(TL)
+__global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_vorticity_b(u32 n, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
               const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P) {
     extern __shared__ __align__(16) unsigned char dsm[];
@@ -355,16 +393,15 @@ k_vorticity_b(u32 n, const float4 *__restrict__ B, const float4 *__restrict__ vp
     TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    tile_wait(tc, &mbar);
-    if (!live) return;
     float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
-    walk<1>(tc, dsm, B, B, home, runs3, cells, g, i, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 cc = __fmul2_rn(c.w, __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il));   // |omega_j| * grad factor
         ex = __ffma2_rn(cc, q.dx, ex);
         ey = __ffma2_rn(cc, q.dy, ey);
         ez = __ffma2_rn(cc, q.dz, ez);
     });
+    if (!live) return;
     float nx = SPIKY_GRAD * (ex.x + ex.y), ny = SPIKY_GRAD * (ey.x + ey.y), nz = SPIKY_GRAD * (ez.x + ez.y);
     const float l = sqrtf(nx * nx + ny * ny + nz * nz);
     if (l > 0.0f) { nx /= l; ny /= l; nz /= l; }
