@@ -3,8 +3,9 @@
  * NeighbourCellFinder.{h,cpp} and the shaders/sph, shaders/radixsort, shaders/neighbourcellfinder directories.
  *
  * With PBF_WITH_GL the constructor creates the position / velocity / highlight GL buffers exactly as src/SPH.cpp:96-133
- * does and registers them with CUDA; Run() maps them, binds the mapped pointers (pbf_bind_device_buffers) and steps, so
- * the renderer keeps reading the buffers it got from GetPositionBuffer() (src/Simulation.cpp:78-79, 473-479).
+ * does and hands their names to pbf_register_gl_buffers; from then on every pbf_step maps them, steps on the mapped
+ * memory and unmaps, so the renderer keeps reading the buffers it got from GetPositionBuffer() (src/Simulation.cpp:78-79,
+ * 473-479).  The shim itself needs no CUDA header.
  * Headless, the handle owns the buffers and GetPositionDevice() etc. expose the device pointers. */
 #ifndef PBF_SHIM_SPH_H
 #define PBF_SHIM_SPH_H
@@ -40,17 +41,15 @@ public:
             glBindBuffer(GL_SHADER_STORAGE_BUFFER, buffers[i]);
             glBufferData(GL_SHADER_STORAGE_BUFFER, sizes[i], NULL, GL_DYNAMIC_COPY);
             if (i == 2) glClearBufferData(GL_SHADER_STORAGE_BUFFER, GL_R32UI, GL_RED_INTEGER, GL_UNSIGNED_INT, NULL);
-            if (cudaGraphicsGLRegisterBuffer(&resources[i], buffers[i], cudaGraphicsRegisterFlagsNone) != cudaSuccess)
-                throw std::runtime_error("SPH::SPH: cudaGraphicsGLRegisterBuffer failed");
         }
+        pbf_shim::check(pbf_register_gl_buffers(handle, buffers[0], buffers[1], buffers[2]), "SPH::SPH");
 #endif
     }
     ~SPH(void) {
+        pbf_destroy(handle);   /* unregisters the GL buffers first */
 #ifdef PBF_WITH_GL
-        for (int i = 0; i < 3; i++) cudaGraphicsUnregisterResource(resources[i]);
         glDeleteBuffers(3, buffers);
 #endif
-        pbf_destroy(handle);
     }
     SPH(const SPH &) = delete;
     SPH &operator=(const SPH &) = delete;
@@ -94,19 +93,12 @@ public:
     void SetExternalForce(bool state) { params.external_force = state ? 1 : 0; UploadSPHParams(); }
 
     /* SPH::Run (src/SPH.cpp:246-334) */
-    void Run(void) {
-#ifdef PBF_WITH_GL
-        void *ptr[3];
-        size_t bytes;
-        if (cudaGraphicsMapResources(3, resources, (cudaStream_t)pbf_stream(handle)) != cudaSuccess)
-            throw std::runtime_error("SPH::Run: cudaGraphicsMapResources failed");
-        for (int i = 0; i < 3; i++) cudaGraphicsResourceGetMappedPointer(&ptr[i], &bytes, resources[i]);
-        pbf_shim::check(pbf_bind_device_buffers(handle, (float *)ptr[0], (float *)ptr[1], (uint32_t *)ptr[2]), "SPH::Run");
-        pbf_shim::check(pbf_step(handle, 1), "SPH::Run");
-        cudaGraphicsUnmapResources(3, resources, (cudaStream_t)pbf_stream(handle));   /* orders GL after the step */
-#else
-        pbf_shim::check(pbf_step(handle, 1), "SPH::Run");
-#endif
+    void Run(void) { pbf_shim::check(pbf_step(handle, 1), "SPH::Run"); }   /* maps / unmaps registered GL buffers itself */
+    /* dump / resume (no counterpart in the reference): by-id buffers, parameters, step counter */
+    void SaveState(const std::string &path) const { pbf_shim::check(pbf_save_state(handle, path.c_str()), "SPH::SaveState"); }
+    void LoadState(const std::string &path) {
+        pbf_shim::check(pbf_load_state(handle, path.c_str()), "SPH::LoadState");
+        pbf_shim::check(pbf_get_params(handle, &params), "SPH::LoadState");
     }
     /* the same step through the stage entry points, in the order and with the member objects of src/SPH.cpp:246-334 */
     void RunStaged(void) {
@@ -143,7 +135,6 @@ private:
     pbf_params params;
 #ifdef PBF_WITH_GL
     GLuint buffers[3];
-    cudaGraphicsResource_t resources[3];
 #endif
 };
 

@@ -12,8 +12,6 @@
 
 #ifdef PBF_WITH_GL
 #include "common.h" /* the reference's src/common.h: glcorew.h, glm, <vector>, <iostream> ... */
-#include <cuda_gl_interop.h>
-#include <cuda_runtime.h>
 #else
 typedef unsigned int GLuint;
 namespace glm {

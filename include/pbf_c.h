@@ -102,6 +102,15 @@ int pbf_device_buffers(pbf_handle h, float **pos4, float **vel4, uint32_t **high
  * state instead of the handle's own allocations; NULL restores the internal buffer. */
 int pbf_bind_device_buffers(pbf_handle h, float *pos4, float *vel4, uint32_t *highlight);
 uint32_t pbf_num_particles(pbf_handle h);
+/* CUDA-GL interop: run on the renderer's own buffer objects.  Replaces SPH's ownership of positionbuffer /
+ * velocitybuffer / highlightbuffer (src/SPH.cpp:96-133, names handed out by src/SPH.h:49, :181, :205 and bound as
+ * vertex attributes by src/PointSprite.cpp:64-84): the three GL buffer names (N x float4, N x float4, N x uint32) are
+ * registered once, with the GL context current on the calling thread; afterwards every pbf_step maps them on the
+ * handle's stream, steps on the mapped memory and unmaps, so GL draws issued after pbf_step returns see the new
+ * positions.  Fails with PBF_ERR_CUDA when no GL context is current.  pbf_unregister_gl_buffers (also done by
+ * pbf_destroy) returns to the handle's own buffers. */
+int pbf_register_gl_buffers(pbf_handle h, unsigned int pos, unsigned int vel, unsigned int highlight);
+int pbf_unregister_gl_buffers(pbf_handle h);
 
 /* SPH::Run (src/SPH.cpp:246-334), nsteps times. */
 int pbf_step(pbf_handle h, int nsteps);
@@ -170,6 +179,30 @@ void *pbf_stream(pbf_handle h);
  * arrays, nx*ny*nz particles, loop order x,z,y, ids from id0. */
 int pbf_scene_dam_break(int nx, int ny, int nz, const float origin[3], float spacing, int mirror_xz,
                         uint32_t seed, uint32_t id0, float *pos4, float *vel4);
+
+/* ---- state files (dump / resume; no counterpart in the reference, whose state dies with the process).
+ * A file holds what SPH::Run is a function of: the three by-id buffers of src/SPH.cpp:106-133, sphparams_t and the
+ * solver switches (src/SPH.h:189-285), the constructor arguments and a step counter; a resumed run continues bit for
+ * bit.  128-byte header + N x float4 + N x float4 + N x uint32, little endian, FNV-1a-64 checksum of the payload.
+ * The pbf_state_file_* functions work on HOST arrays and need no device. */
+typedef struct {
+    uint32_t num_particles;
+    int32_t grid[3];
+    float wall[3];
+    int32_t ref_quirks;
+    pbf_params params;
+    uint64_t steps;             /* SPH::Run calls completed when the file was written */
+} pbf_state_info;
+int pbf_state_file_write(const char *path, const pbf_state_info *info, const float *pos4, const float *vel4,
+                         const uint32_t *highlight);       /* vel4 / highlight may be NULL (zeros) */
+int pbf_state_file_info(const char *path, pbf_state_info *info);
+int pbf_state_file_read(const char *path, pbf_state_info *info, float *pos4, float *vel4, uint32_t *highlight,
+                        uint32_t capacity);                /* arrays hold `capacity` particles; verifies the checksum */
+/* the handle's current state -> file; file -> handle (N and grid must match the handle; parameters and the step
+ * counter are taken from the file) */
+int pbf_save_state(pbf_handle h, const char *path);
+int pbf_load_state(pbf_handle h, const char *path);
+uint64_t pbf_step_count(pbf_handle h);
 
 /* ---- slab decomposition (multi GPU).  No counterpart in the reference (single GPU): this is
  * the north star's slab runtime.  One handle per rank owns the particles whose cell layer z lies in [z_lo, z_hi); the

@@ -30,6 +30,12 @@ class Params(C.Structure):
                 ("vorticity_confinement", C.c_int32), ("external_force", C.c_int32)]
 
 
+class StateInfo(C.Structure):
+    """pbf_state_info (include/pbf_c.h): what a state file's header holds."""
+    _fields_ = [("num_particles", C.c_uint32), ("grid", C.c_int32 * 3), ("wall", C.c_float * 3),
+                ("ref_quirks", C.c_int32), ("params", Params), ("steps", C.c_uint64)]
+
+
 _lib = None
 
 
@@ -76,6 +82,15 @@ def lib():
         L.pbf_scene_dam_break.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.pbf_sort_bits.argtypes = [C.POINTER(C.c_int32)]
+        L.pbf_register_gl_buffers.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
+        L.pbf_unregister_gl_buffers.argtypes = [C.c_void_p]
+        L.pbf_state_file_write.argtypes = [C.c_char_p, C.POINTER(StateInfo), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pbf_state_file_info.argtypes = [C.c_char_p, C.POINTER(StateInfo)]
+        L.pbf_state_file_read.argtypes = [C.c_char_p, C.POINTER(StateInfo), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.pbf_save_state.argtypes = [C.c_void_p, C.c_char_p]
+        L.pbf_load_state.argtypes = [C.c_void_p, C.c_char_p]
+        L.pbf_step_count.restype = C.c_uint64
+        L.pbf_step_count.argtypes = [C.c_void_p]
         L.pbf_slab_unique_id.argtypes = [C.c_void_p]
         L.pbf_slab_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
         L.pbf_slab_init_group.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_uint32]
@@ -116,6 +131,32 @@ def wpoly6(r, h):
 
 def sort_bits(grid):
     return lib().pbf_sort_bits((C.c_int32 * 3)(*grid))
+
+
+def write_state_file(path, pos, vel=None, highlight=None, grid=(128, 64, 128), wall=(16.0, 0.0, 16.0), ref_quirks=True,
+                     params=None, steps=0):
+    """Writes a state file from HOST arrays (no device needed); see include/pbf_c.h, "state files"."""
+    pos = np.ascontiguousarray(pos, np.float32)
+    vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
+    highlight = None if highlight is None else np.ascontiguousarray(highlight, np.uint32)
+    info = StateInfo(pos.shape[0], (C.c_int32 * 3)(*grid), (C.c_float * 3)(*wall), int(ref_quirks),
+                     params if params is not None else default_params(), steps)
+    _check(lib().pbf_state_file_write(os.fsencode(path), C.byref(info), _ptr(pos), _ptr(vel), _ptr(highlight)))
+
+
+def state_file_info(path):
+    info = StateInfo()
+    _check(lib().pbf_state_file_info(os.fsencode(path), C.byref(info)))
+    return info
+
+
+def read_state_file(path):
+    """-> (info, pos, vel, highlight) as HOST arrays; raises on a bad magic, version, size or checksum."""
+    info = state_file_info(path)
+    n = info.num_particles
+    pos, vel, hl = np.empty((n, 4), np.float32), np.empty((n, 4), np.float32), np.empty(n, np.uint32)
+    _check(lib().pbf_state_file_read(os.fsencode(path), C.byref(info), _ptr(pos), _ptr(vel), _ptr(hl), n))
+    return info, pos, vel, hl
 
 
 def dam_break(nx, ny, nz, origin=(32.5, 0.5, 32.5), spacing=0.94, mirror=False, seed=12345, id0=0):
@@ -224,6 +265,30 @@ class SPH:
     def step_host(self, pos, vel, nsteps=1):
         """End-to-end call: HOST pos/vel in, one step, HOST pos/vel out (in place)."""
         _check(lib().pbf_step_host(self._h, _ptr(pos), _ptr(vel), nsteps))
+
+    def save_state(self, path):
+        """Current by-id state, parameters and step counter -> state file."""
+        _check(lib().pbf_save_state(self._h, os.fsencode(path)))
+
+    def load_state(self, path):
+        _check(lib().pbf_load_state(self._h, os.fsencode(path)))
+
+    @classmethod
+    def from_state_file(cls, path, **kw):
+        """A new SPH sized from the file's header, holding the file's state (resume)."""
+        info = state_file_info(path)
+        sph = cls(info.num_particles, tuple(info.grid), wall=tuple(info.wall), ref_quirks=bool(info.ref_quirks), **kw)
+        sph.load_state(path)
+        return sph
+
+    @property
+    def step_count(self): return lib().pbf_step_count(self._h)
+
+    def register_gl_buffers(self, pos, vel, highlight):
+        """CUDA-GL interop: run on the renderer's GL buffer objects (needs a current GL context)."""
+        _check(lib().pbf_register_gl_buffers(self._h, pos, vel, highlight))
+
+    def unregister_gl_buffers(self): _check(lib().pbf_unregister_gl_buffers(self._h))
 
     def sync(self): _check(lib().pbf_sync(self._h))
     def predict(self): _check(lib().pbf_predict(self._h))

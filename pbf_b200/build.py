@@ -15,7 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
            "--expt-extended-lambda", "-ccbin", "/usr/bin/g++"]
-SOURCES = ["api.cu", "sim_kernels.cu", "sweeps.cu", "sort.cu", "slab.cu", "scene.cpp"]
+SOURCES = ["api.cu", "sim_kernels.cu", "sweeps.cu", "sort.cu", "slab.cu", "checkpoint.cu", "scene.cpp"]
 
 
 def _deps():

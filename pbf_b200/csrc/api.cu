@@ -30,18 +30,6 @@ cudaError_t dalloc(T **p, size_t count) {
     return cudaMalloc((void **)p, count * sizeof(T) + 16);
 }
 
-struct DeviceGuard {   // every entry point runs on the handle's device and restores the caller's
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 void invalidate_graph(pbf_sim *s) {
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->graph) cudaGraphDestroy(s->graph);
@@ -51,7 +39,8 @@ void invalidate_graph(pbf_sim *s) {
 }
 
 // SPH::Run, src/SPH.cpp:246-334.  ev != nullptr records the five phase boundaries of the reference's timer queries.
-int enqueue_step(pbf_sim *s, bool with_events) {
+// pos_ready (optional) is recorded once the by-id positions are final (after K10), i.e. before the vorticity kernels.
+int enqueue_step(pbf_sim *s, bool with_events, cudaEvent_t pos_ready = nullptr) {
     int k = 0;
     cudaStream_t st = s->stream;
     if (with_events) cudaEventRecord(s->ev[0], st);
@@ -76,6 +65,7 @@ int enqueue_step(pbf_sim *s, bool with_events) {
     if (with_events) cudaEventRecord(s->ev[4], st);
     // [vorticity] :315-333
     k += launch_update(s);
+    if (pos_ready) cudaEventRecord(pos_ready, st);
     if (s->params.vorticity_confinement) k += launch_vorticity(s);
     if (with_events) cudaEventRecord(s->ev[5], st);
     return k;
@@ -227,6 +217,8 @@ int pbf_destroy(pbf_handle s) {
     if (shared_stream) { cudaDeviceSynchronize(); s->stream = nullptr; }
     if (s->stream) cudaStreamSynchronize(s->stream);
     slab_free(s);
+    if (s->gl_registered)
+        for (int i = 0; i < 3; i++) cudaGraphicsUnregisterResource(s->gl_res[i]);
     invalidate_graph(s);
     void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
                     s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->runs3, s->bufA, s->bufB,
@@ -235,6 +227,7 @@ int pbf_destroy(pbf_handle s) {
         if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_pos); cudaEventDestroy(s->ev_copied); }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return PBF_OK;
@@ -304,10 +297,79 @@ int pbf_bind_device_buffers(pbf_handle s, float *pos4, float *vel4, uint32_t *hi
     return PBF_OK;
 }
 
+}  // extern "C"
+
+// ---- CUDA-GL interop -------------------------------------------------------------------------------
+// The renderer owns the three GL buffer objects (src/SPH.cpp:96-133 creates them, src/PointSprite.cpp:64-84 reads them as
+// vertex attributes).  They are registered once; every pbf_step maps them on the handle's stream, runs on the mapped
+// pointers and unmaps, which orders GL's later reads after the step.  cudaGraphicsGLRegisterBuffer is declared by hand
+// (cuda_gl_interop.h drags in <GL/gl.h>, which a headless build does not have); it lives in libcudart like the rest.
+extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource **resource, unsigned int buffer,
+                                                     unsigned int flags);
+
+namespace {
+
+int gl_map(pbf_sim *s) {
+    cudaError_t e = cudaGraphicsMapResources(3, s->gl_res, s->stream);
+    if (e != cudaSuccess) return fail(PBF_ERR_CUDA, std::string("cudaGraphicsMapResources: ") + cudaGetErrorString(e));
+    void *ptr[3] = {nullptr, nullptr, nullptr};
+    size_t bytes[3] = {0, 0, 0};
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaGraphicsResourceGetMappedPointer(&ptr[i], &bytes[i], s->gl_res[i]);
+    if (e == cudaSuccess && (bytes[0] < (size_t)s->n * 16 || bytes[1] < (size_t)s->n * 16 || bytes[2] < (size_t)s->n * 4)) {
+        cudaGraphicsUnmapResources(3, s->gl_res, s->stream);
+        return fail(PBF_ERR_INVALID, "GL buffers are smaller than N x float4 / N x uint32");
+    }
+    if (e != cudaSuccess) {
+        cudaGraphicsUnmapResources(3, s->gl_res, s->stream);
+        return fail(PBF_ERR_CUDA, std::string("cudaGraphicsResourceGetMappedPointer: ") + cudaGetErrorString(e));
+    }
+    // mapped addresses are normally the same from one map to the next, so the captured graph survives
+    return pbf_bind_device_buffers(s, (float *)ptr[0], (float *)ptr[1], (uint32_t *)ptr[2]);
+}
+
+}  // namespace
+
+extern "C" int pbf_register_gl_buffers(pbf_handle s, unsigned int pos, unsigned int vel, unsigned int highlight) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (s->gl_registered) return fail(PBF_ERR_STATE, "pbf_register_gl_buffers: buffers already registered");
+    DeviceGuard guard(s->device);
+    const unsigned int names[3] = {pos, vel, highlight};
+    for (int i = 0; i < 3; i++) {
+        cudaError_t e = cudaGraphicsGLRegisterBuffer(&s->gl_res[i], names[i], 0u /* cudaGraphicsRegisterFlagsNone */);
+        if (e != cudaSuccess) {
+            for (int j = 0; j < i; j++) cudaGraphicsUnregisterResource(s->gl_res[j]);
+            (void)cudaGetLastError();
+            return fail(PBF_ERR_CUDA, std::string("cudaGraphicsGLRegisterBuffer (is a GL context current on this thread?): ") +
+                                          cudaGetErrorString(e));
+        }
+    }
+    s->gl_registered = true;
+    return PBF_OK;
+}
+
+extern "C" int pbf_unregister_gl_buffers(pbf_handle s) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!s->gl_registered) return PBF_OK;
+    DeviceGuard guard(s->device);
+    cudaStreamSynchronize(s->stream);
+    for (int i = 0; i < 3; i++) cudaGraphicsUnregisterResource(s->gl_res[i]);
+    s->gl_registered = false;
+    return pbf_bind_device_buffers(s, nullptr, nullptr, nullptr);
+}
+
+extern "C" {
+
 int pbf_step(pbf_handle s, int nsteps) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (nsteps < 0) return fail(PBF_ERR_INVALID, "pbf_step: negative step count");
     DeviceGuard guard(s->device);
+    if (s->gl_registered) {
+        if (int r = gl_map(s)) return r;
+    }
+    struct Unmap {   // GL gets its buffers back on every way out
+        pbf_sim *s;
+        ~Unmap() { if (s->gl_registered) cudaGraphicsUnmapResources(3, s->gl_res, s->stream); }
+    } unmap{s};
     const bool use_graph = s->cfg.use_graph && !s->timing;
     for (int i = 0; i < nsteps; i++) {
         if (use_graph) {
@@ -324,10 +386,12 @@ int pbf_step(pbf_handle s, int nsteps) {
             if (s->graph_valid) {
                 PBF_CUDA(cudaGraphLaunch(s->graph_exec, s->stream));
                 s->launches += s->graph_kernels;
+                s->steps++;
                 continue;
             }
         }
         s->launches += (uint64_t)enqueue_step(s, s->timing);
+        s->steps++;
         s->ev_valid = s->timing;
         PBF_CUDA(cudaGetLastError());
     }
@@ -339,13 +403,38 @@ int pbf_step(pbf_handle s, int nsteps) {
 int pbf_step_host(pbf_handle s, float *pos4, float *vel4, int nsteps) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (!pos4 || !vel4) return fail(PBF_ERR_INVALID, "pbf_step_host: null buffer");
+    if (nsteps < 0) return fail(PBF_ERR_INVALID, "pbf_step_host: negative step count");
+    if (s->gl_registered) return fail(PBF_ERR_STATE, "pbf_step_host: the state lives in the registered GL buffers; use pbf_step");
     DeviceGuard guard(s->device);
-    PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, (size_t)s->n * 16, cudaMemcpyHostToDevice, s->stream));
-    PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, (size_t)s->n * 16, cudaMemcpyHostToDevice, s->stream));
-    int r = pbf_step(s, nsteps);
-    if (r) return r;
-    PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
-    PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
+    const size_t bytes = (size_t)s->n * 16;
+    if (!s->copy_stream) {
+        PBF_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        PBF_CUDA(cudaEventCreateWithFlags(&s->ev_pos, cudaEventDisableTiming));
+        PBF_CUDA(cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+    }
+    PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, bytes, cudaMemcpyHostToDevice, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (nsteps == 0) {
+        PBF_CUDA(cudaStreamSynchronize(s->stream));
+        return PBF_OK;
+    }
+    if (nsteps > 1) {
+        int r = pbf_step(s, nsteps - 1);
+        if (r) return r;
+    }
+    // Last step by direct launches: the positions are final after K10 (update.glsl), so their copy back to the host
+    // runs on a second stream underneath the vorticity kernels (compute bound, the copy engine is idle); the
+    // velocities follow on the main stream.  Without vorticity both arrays are final at the same point.
+    s->launches += (uint64_t)enqueue_step(s, false, s->ev_pos);
+    s->steps++;
+    s->ev_valid = false;
+    s->stage = 0;
+    PBF_CUDA(cudaGetLastError());
+    PBF_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_pos, 0));
+    PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    PBF_CUDA(cudaEventRecord(s->ev_copied, s->copy_stream));
+    PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, bytes, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamWaitEvent(s->stream, s->ev_copied, 0));   // later work on the handle's stream may rewrite pos
     PBF_CUDA(cudaStreamSynchronize(s->stream));
     return PBF_OK;
 }

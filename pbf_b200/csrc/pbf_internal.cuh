@@ -82,8 +82,23 @@ struct pbf_sim {
     cudaGraph_t graph; cudaGraphExec_t graph_exec; bool graph_valid; u32 graph_kernels;
     bool timing; cudaEvent_t ev[6]; bool ev_valid;
     uint64_t launches;
+    bool gl_registered; cudaGraphicsResource_t gl_res[3];   // renderer-owned GL buffers (pbf_register_gl_buffers)
+    uint64_t steps;                       // completed SPH::Run calls since creation / the last state load (checkpoints)
+    cudaStream_t copy_stream; cudaEvent_t ev_pos, ev_copied;   // pbf_step_host: position read-back under the vorticity kernels
     int stage;                            // 0 idle, 1 predicted, 2 sorted, 3 cells built
     struct pbf_slab_state *slab;          // non-null once pbf_slab_init has run (slab.cu)
+};
+
+struct DeviceGuard {   // every entry point runs on the handle's device and restores the caller's
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
 };
 
 // error plumbing (api.cu)

@@ -1,0 +1,205 @@
+"""Edge cases of the CUDA path against the oracle: sparse and over-dense scenes (general sweep path), particles outside
+the grid / on the ceiling plane (keys without a cell), fast splashes, the smallest handle, determinism, and the two
+sweep paths against each other.  Integer results bit-exact, floats within the north star's tolerance (scaled by the
+displacement where a scene is violent by construction)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import pbf_b200
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+GRID = (128, 64, 128)
+POS_TOL = 1e-5 * 128.0
+
+
+def oracle_params(sph):
+    P = oracle.default_params()
+    p = sph._get()
+    for k in ("one_over_rho_0", "epsilon", "gravity", "timestep", "tensile_instability_k",
+              "tensile_instability_scale", "xsph_viscosity_c", "vorticity_epsilon"):
+        setattr(P, k, getattr(p, k))
+    return P
+
+
+def check_tables(sph, g, pos, vel, quirks):
+    """predict + sort + cells on both sides: everything integer must be identical."""
+    P = oracle_params(sph)
+    sph.predict(); sph.sort(); sph.build_cells()
+    rec, keys = sph.get_predicted()
+    orec = oracle.predict(pos, vel, P, g)
+    assert np.array_equal(rec.view(np.uint32), orec.view(np.uint32))
+    assert np.array_equal(keys, oracle.keys(orec, g))
+    skeys, perm, srec = sph.get_sorted()
+    osorted, okeys = oracle.sort(orec, g)
+    assert np.array_equal(skeys, okeys)
+    assert np.array_equal(perm, osorted[:, 3].view(np.int32).astype(np.uint32))
+    start, end = sph.get_cell_ranges()
+    ostart, oend = oracle.findcells(osorted, g)
+    assert np.array_equal(start, ostart)
+    occ = ostart != -1
+    if quirks:
+        occ[0] = False
+    assert np.array_equal(end[occ], oend[occ])
+    rs, rc = sph.get_neighbour_runs()
+    ors, orc = oracle.neighbourcells(osorted, g, ostart, oend)
+    assert np.array_equal(rc, orc)
+    assert np.array_equal(rs[rc > 0], ors[orc > 0])
+    return osorted, ors, orc
+
+
+def check_solver_stages(sph, g, cur, rs, rc, iters=2):
+    """lambda and delta-p per iteration on identical inputs; tolerances relative to the size of the result."""
+    P = oracle_params(sph)
+    for it in range(iters):
+        sph.calc_lambda()
+        lam = sph.get_lambda()
+        olam, _ = oracle.calclambda(cur, rs, rc, P)
+        assert np.max(np.abs(lam - olam)) <= 1e-5 * max(1.0, np.max(np.abs(olam))), it
+        sph.update_positions()
+        _, _, new = sph.get_sorted()
+        onew = oracle.updatepos(cur, rs, rc, olam, P, g)
+        moved = np.max(np.abs(onew[:, :3] - cur[:, :3]))
+        assert np.max(np.abs(new[:, :3] - onew[:, :3])) <= 1e-5 * max(10.0, moved), it
+        cur = new
+
+
+@pytest.mark.parametrize("quirks", [True, False])
+@pytest.mark.parametrize("scene", ["sparse_gas", "clump", "escapees", "splash"])
+def test_edge_scene_tables_and_solver(built_lib, scene, quirks):
+    pos, vel = getattr(scenes, scene)()
+    g = oracle.make_grid(*GRID, ref_quirks=int(quirks))
+    sph = pbf_b200.SPH(pos.shape[0], GRID, ref_quirks=quirks)
+    sph.upload(pos, vel)
+    osorted, ors, orc = check_tables(sph, g, pos, vel, quirks)
+    tiles, tiled = sph.tile_stats()
+    if scene in ("sparse_gas", "clump"):
+        assert tiled < tiles          # these scenes are built to leave the shared-memory path
+    check_solver_stages(sph, g, osorted, ors, orc)
+
+
+@pytest.mark.parametrize("scene", ["sparse_gas", "escapees", "splash"])
+def test_edge_scene_whole_steps(built_lib, scene):
+    pos, vel = getattr(scenes, scene)()
+    g = oracle.make_grid(*GRID)
+    sph = pbf_b200.SPH(pos.shape[0], GRID)
+    sph.SetNumSolverIterations(3)
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    P = oracle_params(sph)
+    sim = oracle.Sim(pos.shape[0], g)
+    opos, ovel = pos.copy(), vel.copy()
+    for step in range(4):
+        before = opos.copy()
+        sph.Run()
+        sim.step(opos, ovel, P, 3, vorticity=True)
+        gpos, gvel = sph.download()
+        scale = max(1.0, np.max(np.abs(opos - before)) / 0.5)     # escapees are hauled back by tens of cells in one step
+        assert np.max(np.abs(gpos - opos)) < POS_TOL * scale, step
+        assert np.max(np.abs(gvel - ovel)) < POS_TOL * scale / 0.016, step
+        sph.upload(opos, ovel)
+
+
+def test_smallest_handle(built_lib):
+    """512 particles (one sort block, src/SPH.cpp:25) in an 8 x 8 x 8 grid with thin walls."""
+    grid, wall = (8, 8, 8), (1.0, 0.0, 1.0)
+    pos, vel = oracle.dam_break(8, 8, 8, origin=(1.2, 0.3, 1.2), spacing=0.7)
+    g = oracle.make_grid(*grid, wall=wall)
+    sph = pbf_b200.SPH(512, grid, wall=wall)
+    sph.SetNumSolverIterations(2)
+    sph.upload(pos, vel)
+    P = oracle_params(sph)
+    sim = oracle.Sim(512, g)
+    opos, ovel = pos.copy(), vel.copy()
+    for step in range(3):
+        sph.Run()
+        sim.step(opos, ovel, P, 2)
+        gpos, gvel = sph.download()
+        assert np.max(np.abs(gpos - opos)) < POS_TOL, step
+        sph.upload(opos, ovel)
+    assert gpos[:, 0].min() >= 1.0 and gpos[:, 0].max() <= 7.0 and gpos[:, 1].min() >= 0.0
+
+
+def test_zero_iterations_and_zero_steps(built_lib):
+    """K = 0: predict, sort, update only (the reference's loop body simply does not run, src/SPH.cpp:302-311)."""
+    pos, vel = oracle.dam_break(16, 16, 16)
+    g = oracle.make_grid(*GRID)
+    sph = pbf_b200.SPH(pos.shape[0], GRID)
+    sph.SetNumSolverIterations(0)
+    sph.upload(pos, vel)
+    sph.Run(0)
+    p0, _ = sph.download()
+    assert np.array_equal(p0, pos)
+    sph.Run()
+    gpos, gvel = sph.download()
+    P = oracle_params(sph)
+    opos, ovel = pos.copy(), vel.copy()
+    oracle.Sim(pos.shape[0], g).step(opos, ovel, P, 0)
+    assert np.array_equal(gpos.view(np.uint32), opos.view(np.uint32))       # no sweep ran: pure IEEE arithmetic, bit exact
+    assert np.array_equal(gvel.view(np.uint32), ovel.view(np.uint32))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_deterministic(built_lib, graph):
+    """Same state in, same bits out -- across handles and across the graph / direct launch paths."""
+    pos, vel = scenes.splash()
+    outs = []
+    for use_graph in (graph, graph, not graph):
+        sph = pbf_b200.SPH(pos.shape[0], GRID, use_graph=use_graph)
+        sph.SetNumSolverIterations(3)
+        sph.SetVorticityConfinementEnabled(True)
+        sph.upload(pos, vel)
+        sph.Run(5)
+        outs.append(sph.download())
+        sph.close()
+    for p, v in outs[1:]:
+        assert np.array_equal(p.view(np.uint32), outs[0][0].view(np.uint32))
+        assert np.array_equal(v.view(np.uint32), outs[0][1].view(np.uint32))
+
+
+def test_tiled_and_general_sweeps_agree(built_lib):
+    """PBF_GENERAL_SWEEPS=1 sends every tile down the global-memory walk; both paths visit the same candidates."""
+    pos, vel = oracle.dam_break(32, 32, 32)
+    res = []
+    for general in ("0", "1"):
+        os.environ["PBF_GENERAL_SWEEPS"] = general
+        try:
+            sph = pbf_b200.SPH(pos.shape[0], GRID)
+        finally:
+            os.environ.pop("PBF_GENERAL_SWEEPS")
+        sph.SetNumSolverIterations(3)
+        sph.SetVorticityConfinementEnabled(True)
+        sph.upload(pos, vel)
+        sph.Run()
+        tiles, tiled = sph.tile_stats()
+        assert (tiled == 0) if general == "1" else (tiled > 0.9 * tiles)
+        res.append(sph.download())
+    assert np.max(np.abs(res[0][0] - res[1][0])) < 2e-5
+    assert np.max(np.abs(res[0][1] - res[1][1])) < 2e-5 / 0.016
+
+
+def test_step_host_matches_step(built_lib):
+    """The end-to-end call (host buffers in and out, position read-back overlapped with the vorticity kernels) returns
+    exactly what upload + Run + download returns."""
+    import torch
+    pos, vel = scenes.splash()
+    for vort in (False, True):
+        a = pbf_b200.SPH(pos.shape[0], GRID)
+        a.SetNumSolverIterations(3)
+        a.SetVorticityConfinementEnabled(vort)
+        a.upload(pos, vel)
+        a.Run(3)
+        apos, avel = a.download()
+        b = pbf_b200.SPH(pos.shape[0], GRID)
+        b.SetNumSolverIterations(3)
+        b.SetVorticityConfinementEnabled(vort)
+        hp = torch.from_numpy(pos.copy()).pin_memory()
+        hv = torch.from_numpy(vel.copy()).pin_memory()
+        b.step_host(hp, hv, 2)
+        b.step_host(hp, hv, 1)
+        assert np.array_equal(hp.numpy().view(np.uint32), apos.view(np.uint32))
+        assert np.array_equal(hv.numpy().view(np.uint32), avel.view(np.uint32))

@@ -1,0 +1,97 @@
+"""BASELINE.json's sizes.  C2 (1M particles): one whole step against the oracle.  C3 (8M particles, the headline): the
+oracle would need minutes, so the step is checked through size-independent properties -- sortedness and stability of
+the permutation, keys recomputed from the predicted records, cell ranges against a NumPy searchsorted, walls, run to
+run determinism, and the solver actually reducing the density error."""
+import numpy as np
+import pytest
+
+import oracle
+import pbf_b200
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-5 * 128.0
+
+
+def test_c2_one_step_against_oracle(built_lib):
+    grid = (256, 128, 256)
+    pos, vel = oracle.dam_break(128, 64, 128)            # 1,048,576 particles
+    g = oracle.make_grid(*grid, ref_quirks=0)
+    sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+    sph.SetNumSolverIterations(3)
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    P = oracle.default_params()
+    sim = oracle.Sim(pos.shape[0], g)
+    opos, ovel = pos.copy(), vel.copy()
+    for step in range(2):
+        sph.Run()
+        sim.step(opos, ovel, P, 3, vorticity=True)
+        keys, perm, _ = sph.get_sorted(records=False)
+        assert np.array_equal(keys, sim.skey)
+        assert np.array_equal(perm, sim.sorted[:, 3].view(np.int32).astype(np.uint32))
+        start, _ = sph.get_cell_ranges()
+        assert np.array_equal(start, sim.start)
+        gpos, gvel = sph.download()
+        assert np.max(np.abs(gpos - opos)) < POS_TOL, step
+        assert np.max(np.abs(gvel - ovel)) < POS_TOL / 0.016, step
+        sph.upload(opos, ovel)
+    tiles, tiled = sph.tile_stats()
+    assert tiled > 0.99 * tiles
+
+
+def test_c3_headline_size_properties(built_lib):
+    grid = (512, 256, 512)
+    gx, gy, gz = grid
+    n3 = (256, 128, 256)                                  # 8,388,608 particles
+    pos, vel = pbf_b200.dam_break(*n3)
+    n = pos.shape[0]
+    sph = pbf_b200.SPH(n, grid, ref_quirks=False)
+    sph.SetNumSolverIterations(4)
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    sph.predict(); sph.sort(); sph.build_cells()
+    rec, keys = sph.get_predicted()
+    # keys recomputed from the predicted records (counting.glsl:53-57 with the integer hash)
+    c = np.clip(rec[:, :3], 0, np.array(grid, np.float32)).astype(np.int64)
+    k = c[:, 0] + c[:, 2] * gx + c[:, 1] * gx * gz
+    assert np.array_equal(keys.astype(np.int64), k)                     # nobody is outside the grid in this scene
+    skeys, perm, _ = sph.get_sorted(records=False)
+    assert np.array_equal(np.bincount(perm, minlength=n), np.ones(n, np.int64))     # a permutation
+    assert np.array_equal(skeys, keys[perm])
+    assert np.all(skeys[1:] >= skeys[:-1])                                # sorted (26 key bits, 4 onesweep passes)
+    same = skeys[1:] == skeys[:-1]
+    assert np.all(perm[1:][same] > perm[:-1][same])                       # stable: ties in id order (globalsort.glsl:62-64)
+    start, end = sph.get_cell_ranges()
+    uk, first = np.unique(skeys, return_index=True)
+    assert np.array_equal(start[uk], first.astype(np.int32))
+    assert np.array_equal(end[uk], np.append(first[1:], n).astype(np.int32))
+    assert (start != -1).sum() == uk.size
+    rs, rc = sph.get_neighbour_runs()
+    assert rc.min() >= 0 and rc[:, 4].min() >= 1                          # every particle finds at least itself
+    assert np.all(rs[:, 4] <= np.arange(n)) and np.all(np.arange(n) < rs[:, 4] + rc[:, 4])
+    del rs, rc, start, end
+    tiles, tiled = sph.tile_stats()
+    assert tiles == n // 256 and tiled > 0.99 * tiles
+
+    # whole steps: walls, finiteness, determinism, and a solver that converges
+    sph.upload(pos, vel)
+    sph.Run(3)
+    p1, v1 = sph.download()
+    assert np.isfinite(p1).all() and np.isfinite(v1).all()
+    assert p1[:, 0].min() >= 16.0 and p1[:, 0].max() <= gx - 16.0 and p1[:, 2].min() >= 16.0 and p1[:, 2].max() <= gz - 16.0
+    assert p1[:, 1].min() >= 0.0 and p1[:, 1].max() <= gy
+    assert not p1[:, 3].any() and not v1[:, 3].any()
+    d4, _ = sph.diagnostics()
+    other = pbf_b200.SPH(n, grid, ref_quirks=False, use_graph=False)
+    other.SetNumSolverIterations(4)
+    other.SetVorticityConfinementEnabled(True)
+    other.upload(pos, vel)
+    other.Run(3)
+    p2, v2 = other.download()
+    assert np.array_equal(p1.view(np.uint32), p2.view(np.uint32)) and np.array_equal(v1.view(np.uint32), v2.view(np.uint32))
+    other.SetNumSolverIterations(1)
+    other.upload(pos, vel)
+    other.Run(3)
+    d1, _ = other.diagnostics()
+    assert d4 < d1                                                        # more solver iterations, smaller mean |rho/rho0 - 1|

@@ -189,3 +189,35 @@ def test_golden_vectors():
     assert np.allclose(sim.lam, G["lam"], rtol=2e-4, atol=2e-6)
     assert np.max(np.abs(pos - G["pos1"])) < 2e-5
     assert np.max(np.abs(vel - G["vel1"])) < 2e-3
+
+
+@pytest.mark.parametrize("scene", ["sparse_gas", "clump", "escapees", "splash"])
+def test_edge_scenes_on_the_oracle(scene):
+    """The edge-case scenes the GPU parity tests use (tests/scenes.py): the oracle keeps every particle, stays finite,
+    pulls escaped particles back inside the walls (updatepos.glsl:98-100) and gives keyless particles no cell."""
+    import scenes
+    pos, vel = getattr(scenes, scene)()
+    n = pos.shape[0]
+    assert n % 512 == 0
+    g = oracle.make_grid(128, 64, 128)
+    P = oracle.default_params()
+    rec = oracle.predict(pos, vel, P, g)
+    k = oracle.keys(rec, g)
+    nocell = (k >> 31) != 0
+    if scene == "escapees":
+        assert nocell.sum() > 100
+        assert nocell[512]                       # the particle that lands on y = gy exactly
+        assert rec[512, 1] == 64.0
+    else:
+        assert not nocell.any()
+    srt, sk = oracle.sort(rec, g)
+    assert sorted(srt[:, 3].view(np.int32).tolist()) == list(range(n))
+    start, end = oracle.findcells(srt, g)
+    inside = ~((sk >> 31) != 0)
+    assert set(np.flatnonzero(start != -1).tolist()) <= set(sk[inside].tolist()) | {0}
+    sim = oracle.Sim(n, g)
+    p, v = pos.copy(), vel.copy()
+    for _ in range(2):
+        sim.step(p, v, P, 3, vorticity=True)
+    assert np.isfinite(p).all() and np.isfinite(v).all()
+    assert p[:, 0].min() >= 16 and p[:, 0].max() <= 112 and p[:, 1].min() >= 0 and p[:, 1].max() <= 64
