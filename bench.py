@@ -41,6 +41,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/traffic.json, written by profiles/summarize.py); only valid for the particle count it was captured at."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    t = json.load(open(p))
+    e = t.get("kernels", {}).get(kernel)
+    if not e or t.get("particles") != n:
+        return None, None
+    return e["dram_bytes_per_launch"], "ncu --set full, %s (bytes per launch)" % t.get("capture", "profiles/")
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -177,7 +190,20 @@ def main():
     sampler.join()
     value = n / (ms_step * 1e-3)
 
-    # ---- per-kernel durations of the four neighbour sweeps (stage entry points, same stream, CUDA events) ---------------
+    # ---- per-kernel durations ------------------------------------------------------------------------------------------
+    # (i) the two density-constraint kernels INSIDE whole steps: timing mode records a CUDA event before every solver
+    # kernel on the library's stream (pbf_get_solver_kernel_timings), averaged over the K iterations of 5 steps;
+    # (ii) the stage entry points alone, for the kernels the library has no in-step events for.
+    sph.enable_timing(True)
+    in_step = {"lambda": [], "delta_p": []}
+    phases = None
+    for _ in range(5):
+        sph.Run(1)
+        a, b = sph.get_solver_kernel_timings()
+        in_step["lambda"].append(a); in_step["delta_p"].append(b)
+        phases = sph.get_timings()
+    sph.enable_timing(False)
+    kernel_ms = {k: float(np.mean(v)) for k, v in in_step.items()}
     sph.predict(); sph.sort(); sph.build_cells()
     tiles, tiled = sph.tile_stats()
     stage_ms = {}
@@ -185,18 +211,15 @@ def main():
     stage_ms["lambda"] = timed(sph.calc_lambda, reps)
     stage_ms["delta_p"] = timed(sph.update_positions, reps)
     sph.calc_lambda(); sph.finalize()
-    # vorticity_a / _b are launched back to back by one entry point; time the pair and split by the ncu launch list share
     stage_ms["vorticity_a+b"] = timed(sph.vorticity, reps)
     sph.upload(pos, vel)
-    sph.enable_timing(True)
     sph.Run(3)
-    phases = sph.get_timings()
-    sph.enable_timing(False)
     peak, peak_src = peaks()
-    dom = max(("lambda", "delta_p"), key=lambda k: stage_ms[k])
+    dom = max(("lambda", "delta_p"), key=lambda k: kernel_ms[k])
     dom_bytes = STAGE_BYTES[dom] * n
-    achieved = dom_bytes / (stage_ms[dom] * 1e-3) / 1e9
+    achieved = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
     step_bytes = algorithmic_bytes(cfg["grid"], cfg["iters"], cfg["vort"])
+    traffic, traffic_src = ncu_traffic("k_" + dom, n)
 
     # ---- end to end through the public call with HOST buffers -------------------------------------------------------------
     hp = torch.from_numpy(pos).pin_memory()
@@ -219,14 +242,15 @@ def main():
                    "step_algorithmic_bytes_per_particle": step_bytes,
                    "step_hbm_frac_of_peak": step_bytes * value / 1e9 / peak,
                    "phase_ms": dict(zip(["predict", "sort", "neighbour_cells", "solver", "vorticity"], phases)),
-                   "stage_ms": stage_ms, "tiles": tiles, "tiles_on_tiled_path": tiled},
+                   "kernel_ms_in_step": kernel_ms, "stage_ms_alone": stage_ms, "tiles": tiles, "tiles_on_tiled_path": tiled},
         "clocks": sampler.summary(),
         "gpu_launches": int(launches),
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * n * 16, "d2h_bytes_per_step": 2 * n * 16,
                 "ms_per_step": e2e_ms, "call": "pbf_step_host (pinned host pos+vel in, pos+vel out)"},
         "roofline": {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": stage_ms[dom],
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": kernel_ms[dom],
+                     "launch_ms_source": "CUDA events around every launch of the kernel inside 5 whole steps (library stream)",
                      "note": "density-constraint kernels are FP32-issue bound, not HBM bound (DESIGN.md); frac is reported against HBM as the north star asks"},
     }
     if not args.no_cpu_baseline:

@@ -159,6 +159,9 @@ int pbf_get_vorticity(pbf_handle h, float *vorticity);
  * solver, vorticity.  Timing needs pbf_enable_timing(h, 1), which runs steps outside the CUDA graph. */
 int pbf_enable_timing(pbf_handle h, int on);
 int pbf_get_timings(pbf_handle h, float ms[5]);
+/* finer than the reference's queries: mean duration of one calclambda and one updatepos launch (src/SPH.cpp:304-310)
+ * over the solver iterations of the last timed step -- what bench.py's roofline is computed from */
+int pbf_get_solver_kernel_timings(pbf_handle h, float *lambda_ms, float *delta_p_ms);
 
 /* Aggregates the north star's long-run criterion needs (not in the reference): mean |rho_i/rho_0 - 1| at
  * the current positions (one extra density sweep) and sum 0.5 |v|^2. */

@@ -78,6 +78,7 @@ def lib():
         L.pbf_get_vorticity.argtypes = [C.c_void_p, C.c_void_p]
         L.pbf_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.pbf_get_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.pbf_get_solver_kernel_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.pbf_get_diagnostics.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pbf_scene_dam_break.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -187,8 +188,8 @@ class SPH:
         self.ncell = gridsize[0] * gridsize[1] * gridsize[2]
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().pbf_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:   # _lib is gone at interpreter exit
+            _lib.pbf_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
@@ -348,6 +349,12 @@ class SPH:
         ms = (C.c_float * 5)()
         _check(lib().pbf_get_timings(self._h, ms))
         return list(ms)
+
+    def get_solver_kernel_timings(self):
+        """(ms per calclambda launch, ms per updatepos launch), averaged over the last timed step's iterations."""
+        a, b = C.c_float(), C.c_float()
+        _check(lib().pbf_get_solver_kernel_timings(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def OutputTiming(self):
         """SPH::OutputTiming (src/SPH.cpp:218-240): same five phase labels."""

@@ -58,10 +58,19 @@ int enqueue_step(pbf_sim *s, bool with_events, cudaEvent_t pos_ready = nullptr) 
     if (with_events) cudaEventRecord(s->ev[3], st);
     // [solver] :277-313
     k += launch_highlight(s);
-    for (int it = 0; it < s->params.num_solver_iterations; it++) {
+    const int K = s->params.num_solver_iterations;
+    if (with_events && (int)s->ev_solver.size() < 2 * K + 1) {
+        const size_t have = s->ev_solver.size();
+        s->ev_solver.resize(2 * K + 1, nullptr);
+        for (size_t i = have; i < s->ev_solver.size(); i++) cudaEventCreate(&s->ev_solver[i]);
+    }
+    for (int it = 0; it < K; it++) {
+        if (with_events) cudaEventRecord(s->ev_solver[2 * it], st);
         k += launch_lambda(s);
+        if (with_events) cudaEventRecord(s->ev_solver[2 * it + 1], st);
         k += launch_delta_p(s);
     }
+    if (with_events) { cudaEventRecord(s->ev_solver[2 * K], st); s->ev_solver_iters = K; }
     if (with_events) cudaEventRecord(s->ev[4], st);
     // [vorticity] :315-333
     k += launch_update(s);
@@ -138,9 +147,8 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     if (prop.major < 10)
         return fail(PBF_ERR_CUDA, std::string("pbf_create: device '") + prop.name + "' is not sm_100 class; this library is built for sm_100a only");
 
-    pbf_sim *s = new (std::nothrow) pbf_sim();
+    pbf_sim *s = new (std::nothrow) pbf_sim();   // value-initialised: every plain member starts at zero
     if (!s) return fail(PBF_ERR_INVALID, "pbf_create: out of host memory");
-    memset((void *)s, 0, sizeof(*s));
     s->cfg = *cfg;
     s->device = dev;
     s->sm_count = prop.multiProcessorCount;
@@ -227,6 +235,8 @@ int pbf_destroy(pbf_handle s) {
         if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (cudaEvent_t e : s->ev_solver)
+        if (e) cudaEventDestroy(e);
     if (s->copy_stream) { cudaStreamDestroy(s->copy_stream); cudaEventDestroy(s->ev_pos); cudaEventDestroy(s->ev_copied); }
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -614,6 +624,24 @@ int pbf_get_timings(pbf_handle s, float ms[5]) {
     DeviceGuard guard(s->device);
     PBF_CUDA(cudaEventSynchronize(s->ev[5]));
     for (int i = 0; i < 5; i++) PBF_CUDA(cudaEventElapsedTime(&ms[i], s->ev[i], s->ev[i + 1]));
+    return PBF_OK;
+}
+
+int pbf_get_solver_kernel_timings(pbf_handle s, float *lambda_ms, float *delta_p_ms) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!s->ev_valid || s->ev_solver_iters <= 0) return fail(PBF_ERR_STATE, "pbf_get_solver_kernel_timings: no timed step with solver iterations");
+    DeviceGuard guard(s->device);
+    const int K = s->ev_solver_iters;
+    PBF_CUDA(cudaEventSynchronize(s->ev_solver[2 * K]));
+    double a = 0.0, b = 0.0;
+    for (int it = 0; it < K; it++) {
+        float x, y;
+        PBF_CUDA(cudaEventElapsedTime(&x, s->ev_solver[2 * it], s->ev_solver[2 * it + 1]));
+        PBF_CUDA(cudaEventElapsedTime(&y, s->ev_solver[2 * it + 1], s->ev_solver[2 * it + 2]));
+        a += x; b += y;
+    }
+    if (lambda_ms) *lambda_ms = (float)(a / K);
+    if (delta_p_ms) *delta_p_ms = (float)(b / K);
     return PBF_OK;
 }
 

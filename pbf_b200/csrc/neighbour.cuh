@@ -50,7 +50,7 @@ __device__ __forceinline__ void fetch_runs(const u32 home, const GridInfo &g, co
 }
 
 // The thread's non-empty runs {start,end} into shared memory.  Returns their number; *slots = number of aligned
-// candidate pairs over all runs; *self_in = whether the particle's own slot lies in run 4 (its own row), i.e. whether
+// candidate pairs over all runs; *self_in = whether the particle's own slot lies in one of its runs, i.e. whether
 // FOR_EACH_NEIGHBOUR would have skipped `self`.
 template <int BLOCK>
 __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const GridInfo &g, const int2 *__restrict__ runs3,
@@ -58,9 +58,10 @@ __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const Grid
     int2 r[9];
     fetch_runs(home, g, runs3, cells, r);
     int cnt = 0, tot = 0;
-    *self_in = (int)i >= r[4].x && (int)i < r[4].x + r[4].y;
+    bool self = false;
 #pragma unroll
     for (int o = 0; o < 9; o++) {
+        self = self || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);   // see k_plan: any run may hold the particle itself
         if (r[o].y > 0) {
             const int s = r[o].x, e = r[o].x + r[o].y;
             srun[cnt * BLOCK + tid] = make_int2(s, e);
@@ -68,6 +69,7 @@ __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const Grid
             tot += ((e + 1) >> 1) - (s >> 1);
         }
     }
+    *self_in = self;
     *slots = tot;
     return cnt;
 }
@@ -106,9 +108,15 @@ __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bo
     q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
     q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
     q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));
+#ifdef PBF_V_ILCLAMP
+    // variant: no TINY add on the FMA pipe; rsqrt(0) = +inf is clamped instead (two FMNMX on the ALU pipe)
+    const float2 rc = make_float2(fminf(v0 ? q.r2.x : FAR2, H2), fminf(v1 ? q.r2.y : FAR2, H2));
+    q.il = make_float2(fminf(rsqrt_ftz(rc.x), 1.0e12f), fminf(rsqrt_ftz(rc.y), 1.0e12f));
+#else
     const float2 re = __fadd2_rn(q.r2, make_float2(TINY, TINY));
     const float2 rc = make_float2(fminf(v0 ? re.x : FAR2, H2), fminf(v1 ? re.y : FAR2, H2));
     q.il = make_float2(rsqrt_ftz(rc.x), rsqrt_ftz(rc.y));
+#endif
     q.t2 = __ffma2_rn(rc, q.il, make_float2(-H, -H));                // l - h: 0 at and beyond the support radius
     q.t = __fadd2_rn(rc, make_float2(-H2, -H2));                     // r^2 - h^2, exactly <= 0
     return q;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/pbf_c.h"
 
@@ -81,6 +82,7 @@ struct pbf_sim {
     // graph replay of the whole step
     cudaGraph_t graph; cudaGraphExec_t graph_exec; bool graph_valid; u32 graph_kernels;
     bool timing; cudaEvent_t ev[6]; bool ev_valid;
+    std::vector<cudaEvent_t> ev_solver; int ev_solver_iters;   // timing mode: one event before every solver kernel
     uint64_t launches;
     bool gl_registered; cudaGraphicsResource_t gl_res[3];   // renderer-owned GL buffers (pbf_register_gl_buffers)
     uint64_t steps;                       // completed SPH::Run calls since creation / the last state load (checkpoints)

@@ -32,6 +32,9 @@ constexpr int TL = NB_BLOCK;     // particles per tile = threads per block
 #ifndef PBF_TL_CTAS
 #define PBF_TL_CTAS 4
 #endif
+#ifndef PBF_PREFETCH_DIST
+#define PBF_PREFETCH_DIST 0
+#endif
 constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B each (52 KB: four blocks per SM).  Measured on
                                      // B200: 2560 records / five blocks per SM is no faster (the sweeps are bound by FMA-pipe,
                                      // issue and shared-memory cycles together, not by residency), and stages 7 % of the tiles twice
@@ -86,7 +89,13 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
         total += no;
     }
     if (nph < 8) cut |= 9u << (4 * nph);
-    if ((int)i >= r[4].x && (int)i < r[4].x + r[4].y) w[4] |= 1u << 25;
+    // Is the particle itself among its candidates (FOR_EACH_NEIGHBOUR skips it by index, foreachneighbour.glsl:9)?  Normally
+    // it sits in run 4, its own row -- but a particle outside the grid is filed under its CLAMPED cell (findcells.glsl)
+    // while its runs are built around the UNCLAMPED one (neighbourcells.glsl:57), so any of the nine runs may hold it.
+    bool self_in = false;
+#pragma unroll
+    for (int o = 0; o < 9; o++) self_in = self_in || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);
+    if (self_in) w[4] |= 1u << 25;
     u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
@@ -114,6 +123,10 @@ __device__ __forceinline__ Pair make_pair(const float4 &a, const float4 &b) {
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {   // bytes: multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // Thread 0: stage ranges [lo, hi) of NSRC arrays into the image(s): zeroed pad records after the last range (a walk
@@ -170,6 +183,27 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
 #pragma unroll
     for (int o = 0; o < 9; o++) c.run[o] = __funnelshift_r(w[(17 * o) >> 5], w[((17 * o) >> 5) + 1], (17 * o) & 31) & 0x1ffffu;
     c.self_in = ((w[4] >> 25) & 1u) != 0u;
+#if PBF_PREFETCH_DIST > 0
+    // One wave ahead: pull what tile blockIdx.x + DIST will need into L2 -- its descriptor (by loading it), its packed
+    // runs and its nine ranges -- so that its own prologue (descriptor -> bulk copies -> data) runs on L2 hits instead of
+    // two DRAM round trips.  Warp 2 does this while the block waits for its own image anyway.
+    if (tid >= 64 && tid < 74) {
+        const u32 ft = blockIdx.x + (u32)PBF_PREFETCH_DIST;
+        if (ft < gridDim.x) {
+            const int *fd = desc + (size_t)ft * TL_DESC;
+            const int o = tid - 64;
+            if (o < 9) {
+                const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
+                if (__ldg(fd + D_MODE) && no > 0) {
+                    bulk_prefetch_l2(src0 + so, 16u * (unsigned)no);
+                    if (NSRC == 2) bulk_prefetch_l2(src1 + so, 16u * (unsigned)no);
+                }
+            } else {
+                bulk_prefetch_l2(runs + (size_t)ft * RUN_WORDS * TL, (unsigned)(RUN_WORDS * TL * sizeof(u32)));
+            }
+        }
+    }
+#endif
     if (c.mode && tid == 0) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
@@ -199,11 +233,37 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 // phase wait for the image, then walk the runs staged in it, two candidates per iteration.
 // body(candidate pair of array 0, same pair of array 1, valid0, valid1)
 template <int NSRC, class F>
+__device__ __forceinline__ void walk_run(unsigned a, const unsigned end, F &body) {
+#pragma unroll 1
+    for (; a < end; a += 32u) {
+#ifdef PBF_V_PROBE_NOLDS     // experiment only (wrong results): no shared-memory reads in the walk
+        Pair p;
+        p.x = p.y = p.z = p.w = make_float2(__uint_as_float(a), __uint_as_float(end));
+#else
+        const Pair p = make_pair(lds128(a), lds128(a + 16u));
+#endif
+        if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
+        else body(p, p, true, a + 16u < end);
+    }
+}
+
+template <int NSRC, class F>
 __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsigned long long *mbar,
                                            const float4 *__restrict__ src0, const float4 *__restrict__ src1,
                                            const int *__restrict__ desc, int tid, F body) {
     const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
     __syncthreads();                                       // the barrier is initialised
+#ifndef PBF_V_NO_ONEPHASE
+    if (c.mode == 1) {                                     // all nine ranges in one image (all but a handful of tiles):
+        mbar_wait(mb, 0u);                                 // no per-run phase test
+#pragma unroll
+        for (int o = 0; o < 9; o++) {
+            const unsigned a = c.img + 16u * (c.run[o] & 0xfffu);
+            walk_run<NSRC>(a, a + 16u * (c.run[o] >> 12), body);
+        }
+        return;
+    }
+#endif
     int lo = 0;
 #pragma unroll 1
     for (int ph = 0; ph < c.mode; ph++) {
@@ -213,16 +273,13 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
             if (tid == 0) tile_stage<NSRC>(dsm, mb, src0, src1, desc + (size_t)blockIdx.x * TL_DESC, lo, hi);
         }
         mbar_wait(mb, (unsigned)(ph & 1));
-#pragma unroll
-        for (int o = 0; o < 9; o++) {
-            unsigned a = c.img + 16u * (c.run[o] & 0xfffu);
-            const unsigned end = (o >= lo && o < hi) ? a + 16u * (c.run[o] >> 12) : a;
 #pragma unroll 1
-            for (; a < end; a += 32u) {
-                const Pair p = make_pair(lds128(a), lds128(a + 16u));
-                if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
-                else body(p, p, true, a + 16u < end);
-            }
+        for (int o = lo; o < hi; o++) {                    // rare path: rolled, the runs come from a switch
+            u32 r = 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) r = (o == k) ? c.run[k] : r;
+            const unsigned a = c.img + 16u * (r & 0xfffu);
+            walk_run<NSRC>(a, a + 16u * (r >> 12), body);
         }
         lo = hi;
     }
@@ -272,6 +329,10 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
     walk<1>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+#ifdef PBF_V_PROBE_NOMATH   // experiment only (wrong results): staging + loads + loop, almost no arithmetic
+            rho = __fadd2_rn(rho, make_float2(c.x.x, v1 ? c.x.y : 0.0f));
+            return;
+#endif
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);       // (h-l)^2 / l
@@ -357,7 +418,11 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
+#ifdef PBF_V_VORT_PQ
+    float2 qx = vx, qy = vx, qz = vx;
+#else
     const float2 neg1 = make_float2(-1.0f, -1.0f);
+#endif
     walk<2>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
@@ -368,12 +433,26 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
         vy = __ffma2_rn(uy, w, vy);
         vz = __ffma2_rn(uz, w, vz);
         const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);          // grad = SPIKY_GRAD * cc * d
+#ifdef PBF_V_VORT_PQ
+        // cross(v_ij, cc d) = P - Q with P = sum (cc u)_a d_b, Q = sum (cc u)_b d_a kept as separate sums: nine packed
+        // operations instead of twelve, the subtraction happens once after the walk
+        const float2 ax = __fmul2_rn(cc, ux), ay = __fmul2_rn(cc, uy), az = __fmul2_rn(cc, uz);
+        wx = __ffma2_rn(ay, q.dz, wx); qx = __ffma2_rn(az, q.dy, qx);
+        wy = __ffma2_rn(az, q.dx, wy); qy = __ffma2_rn(ax, q.dz, qy);
+        wz = __ffma2_rn(ax, q.dy, wz); qz = __ffma2_rn(ay, q.dx, qz);
+#else
         const float2 gx = __fmul2_rn(cc, q.dx), gy = __fmul2_rn(cc, q.dy), gz = __fmul2_rn(cc, q.dz);
         // cross(v_ij, grad)
         wx = __ffma2_rn(uy, gz, __ffma2_rn(__fmul2_rn(gy, uz), neg1, wx));
         wy = __ffma2_rn(uz, gx, __ffma2_rn(__fmul2_rn(gz, ux), neg1, wy));
         wz = __ffma2_rn(ux, gy, __ffma2_rn(__fmul2_rn(gx, uy), neg1, wz));
+#endif
     });
+#ifdef PBF_V_VORT_PQ
+    wx = make_float2(wx.x - qx.x, wx.y - qx.y);
+    wy = make_float2(wy.x - qy.x, wy.y - qy.y);
+    wz = make_float2(wz.x - qz.x, wz.y - qz.y);
+#endif
     if (!live) return;
     const float cw = -P.xsph_c * POLY6;
     vprime[i] = make_float4(vi.x + cw * (vx.x + vx.y), vi.y + cw * (vy.x + vy.y), vi.z + cw * (vz.x + vz.y), 0.0f);

@@ -11,7 +11,7 @@ def _pad4(xyz):
 
 def sparse_gas(n=4096, grid=(128, 64, 128), seed=11, speed=3.0):
     """Uniformly random particles inside the walls: ~0.006 particles per cell, so 256 consecutive sorted particles span
-    hundreds of cell rows -> every tile takes the general (global-memory) sweep path; most cells are empty."""
+    hundreds of cell rows, almost every neighbour run is empty and most cells are."""
     rng = np.random.default_rng(seed)
     lo = np.array([16.0, 0.0, 16.0]); hi = np.array([grid[0] - 16.0, grid[1], grid[2] - 16.0])
     pos = _pad4(rng.uniform(lo, hi, (n, 3)))

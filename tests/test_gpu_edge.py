@@ -77,8 +77,8 @@ def test_edge_scene_tables_and_solver(built_lib, scene, quirks):
     sph.upload(pos, vel)
     osorted, ors, orc = check_tables(sph, g, pos, vel, quirks)
     tiles, tiled = sph.tile_stats()
-    if scene in ("sparse_gas", "clump"):
-        assert tiled < tiles          # these scenes are built to leave the shared-memory path
+    if scene == "clump":
+        assert tiled < tiles          # ~96 candidates per merged run: more than the packed plan describes (31)
     check_solver_stages(sph, g, osorted, ors, orc)
 
 
