@@ -167,10 +167,10 @@ int pbf_get_solver_kernel_timings(pbf_handle h, float *lambda_ms, float *delta_p
  * the current positions (one extra density sweep) and sum 0.5 |v|^2. */
 int pbf_get_diagnostics(pbf_handle h, double *density_error, double *kinetic_energy);
 
-/* Tiles (256 consecutive sorted particles) of the last pbf_build_cells / step, and how many of them run the
+/* Tiles (128 consecutive sorted particles) of the last pbf_build_cells / step, and how many of them run the
  * shared-memory tiled sweep path; the rest walk their neighbour runs from global memory ("sweeps").
- * why (may be NULL): [0] tiled, [1] ranges do not fit the shared-memory image; [2..7] tiles whose nine ranges hold
- * <= 2304, 2560, 2816, 3072, 3328, more records (what sizes the image). */
+ * why (may be NULL): [0] tiled, [1] general path; [2..7] tiles whose nine ranges hold <= 9, 10, 11, 12, 13, more
+ * records per particle of the tile (what sizes the shared-memory image). */
 int pbf_get_tile_stats(pbf_handle h, uint32_t *tiles, uint32_t *tiled, uint32_t why[8]);
 
 /* how many kernels the handle has launched (graph replays count their kernel nodes) */

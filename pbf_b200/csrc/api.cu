@@ -678,10 +678,9 @@ int pbf_get_tile_stats(pbf_handle s, uint32_t *tiles, uint32_t *tiled, uint32_t 
         b += tmp[t] != 0;
         if (why) {
             why[tmp[t] != 0 ? 0 : 1]++;
-            // staged records of the tile (desc[1]) in six classes: <= 2304, 2560, 2816, 3072, 3328, more
-            const int total = tmp[t + 1];
-            int c = total <= 2304 ? 0 : (total - 2304 + 255) / 256;
-            why[2 + (c > 5 ? 5 : c)]++;
+            // staged records of the tile (desc[1]) per particle of a full tile, in six classes: <= 9, 10, 11, 12, 13, more
+            const int per = (tmp[t + 1] + (int)plan_tile_size() - 1) / (int)plan_tile_size();
+            why[2 + (per <= 9 ? 0 : (per > 13 ? 5 : per - 9))]++;
         }
     }
     if (tiles) *tiles = a;

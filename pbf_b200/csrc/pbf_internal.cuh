@@ -137,6 +137,7 @@ int launch_neighbour_runs(pbf_sim *s, int *run_start, int *run_count);
 int sweeps_init(void);                   // opt-in shared-memory sizes of the sweep kernels (once per device)
 size_t plan_desc_ints(u32 cap);
 size_t plan_run_words(u32 cap);
+u32 plan_tile_size(void);                // particles per tile
 int launch_plan(pbf_sim *s);
 SimParams sim_params(const pbf_sim *s);
 // slab.cu

@@ -3,8 +3,9 @@
 //
 // Candidate set = FOR_EACH_NEIGHBOUR (shaders/sph/foreachneighbour.glsl:1-10): for a particle in cell (x,y,z) the nine
 // rows (y+dy, z+dz), each the cells x-1..x+1 merged into one run (neighbourcells.glsl:37-47, :62-84).  Cells are ordered
-// x-fastest (key = x + z*gx + y*gx*gz), so for a TILE of 256 consecutive sorted particles the runs of row offset
-// o = (dy,dz) of all its particles lie inside ONE contiguous range of the sorted array, about 256 + 3 records long.
+// x-fastest (key = x + z*gx + y*gx*gz), so for a TILE of TL = 128 consecutive sorted particles the runs of row offset
+// o = (dy,dz) of all its particles lie inside ONE contiguous range of the sorted array (64 to 400 records at the
+// headline scene, depending on how dense that row is; ~1140 records over the nine ranges, 8.9 per particle).
 //   * k_plan (once per step, after the cell tables): per particle its nine runs (this is K7, evaluated once per step
 //     as in the reference), per tile the nine ranges [S_o, S_o + n_o) that cover them; the runs are stored relative to
 //     the tile's shared-memory image (12-bit start, 5-bit count: 20 B per particle).
@@ -13,39 +14,47 @@
 //     staging; meanwhile the other threads fetch their runs.  A thread then walks its nine runs in the image, two
 //     candidates per iteration (two LDS.128, packed f32x2 arithmetic).  Neighbouring lanes read neighbouring records
 //     of the same row, so the loads are free of bank conflicts.
-// What bounds the sweeps is the L1/shared-memory data pipe (one 128-byte wavefront per clock per SM; a 16-byte load by
-// 32 lanes takes four) together with the FP32 pipe, not HBM: see DESIGN.md and profiles/.
+//   * warp 2 of every block meanwhile pulls what the block one wave later (blockIdx.x + PBF_PREFETCH_DIST) will need --
+//     descriptor, packed runs, nine ranges -- into L2 (cp.async.bulk.prefetch.L2).
+// What bounds the sweeps is instruction issue (FP32 + shared-memory loads + run bookkeeping) at the residency the
+// registers allow (32 warps per SM), not HBM: see DESIGN.md section 4 and profiles/ (with the arithmetic removed a
+// sweep still takes 56 % of its time, with the shared-memory loads removed too 45 %).
 //
-// A tile whose ranges do not fit the image (TL_CAP records: sparse scenes where 256 consecutive particles span many
-// rows) takes the general path: every thread walks its nine runs straight from global memory through L1 (the first
-// version of these kernels).  Both paths visit exactly the same candidate set.
+// A tile whose ranges do not fit the image in up to four staging phases, or with a run of 32+ candidates (very sparse or
+// over-dense scenes), takes the general path: every thread walks its nine runs straight from global memory through L1
+// (the first version of these kernels).  Both paths visit exactly the same candidate set.
 #include <limits.h>
 
 #include "neighbour.cuh"
 
 namespace {
 
-constexpr int TL = NB_BLOCK;     // particles per tile = threads per block
+#ifndef PBF_TL
+#define PBF_TL 128
+#endif
+constexpr int TL = PBF_TL;       // particles per tile = threads per block
+static_assert(TL % 32 == 0 && TL >= 32 && TL <= 1024, "a tile is a whole number of warps");
 #ifndef PBF_TL_CAP
-#define PBF_TL_CAP 3328
+#define PBF_TL_CAP 1664
 #endif
 #ifndef PBF_TL_CTAS
-#define PBF_TL_CTAS 4
+#define PBF_TL_CTAS 8
 #endif
 #ifndef PBF_PREFETCH_DIST
-#define PBF_PREFETCH_DIST 0
+#define PBF_PREFETCH_DIST 1184   // one wave of blocks ahead on a B200 (148 SMs x 8 blocks)
 #endif
-constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B each (52 KB: four blocks per SM).  Measured on
-                                     // B200: 2560 records / five blocks per SM is no faster (the sweeps are bound by FMA-pipe,
-                                     // issue and shared-memory cycles together, not by residency), and stages 7 % of the tiles twice
+constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B each (26 KB: eight blocks of four warps per
+                                     // SM; 2.5 % of the headline scene's tiles need a second phase).  Measured on B200 at 8M
+                                     // particles, whole step: TL 256 / cap 3328 / 4 blocks 4.69 ms, TL 128 / 1664 / 8 4.63 ms,
+                                     // TL 128 / 1920 / 7 4.83 ms, TL 64 / 832 / 16 4.78 ms
 constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
 constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
 constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20;
 constexpr int RUN_WORDS = 5;     // packed runs of one particle
 constexpr int TL_PAD = 4;        // zeroed records after the last range: a walk reads up to 3 records past its run
 constexpr size_t TL_IMG = (size_t)(TL_CAP + TL_PAD) * sizeof(float4);   // one image
-constexpr size_t TL_SMEM1 = TL_IMG;                                // 4 blocks per SM
-constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays: 2 blocks per SM
+constexpr size_t TL_SMEM1 = TL_IMG;                                // PBF_TL_CTAS blocks per SM
+constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays: half as many
 
 // ---- the plan: one block per tile ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TL)
@@ -187,11 +196,12 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     // One wave ahead: pull what tile blockIdx.x + DIST will need into L2 -- its descriptor (by loading it), its packed
     // runs and its nine ranges -- so that its own prologue (descriptor -> bulk copies -> data) runs on L2 hits instead of
     // two DRAM round trips.  Warp 2 does this while the block waits for its own image anyway.
-    if (tid >= 64 && tid < 74) {
+    constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the ten prefetching threads
+    if (tid >= PF0 && tid < PF0 + 10) {
         const u32 ft = blockIdx.x + (u32)PBF_PREFETCH_DIST;
         if (ft < gridDim.x) {
             const int *fd = desc + (size_t)ft * TL_DESC;
-            const int o = tid - 64;
+            const int o = tid - PF0;
             if (o < 9) {
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
                 if (__ldg(fd + D_MODE) && no > 0) {
@@ -497,6 +507,7 @@ inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
 
 #define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs
 
+u32 plan_tile_size(void) { return (u32)TL; }
 size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
 size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 

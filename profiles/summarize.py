@@ -3,6 +3,7 @@
 
   python profiles/summarize.py launches gpurun_out/launches_X.csv  > profiles/X_launches.md
   python profiles/summarize.py full gpurun_out/prof_X.ncu-rep     > profiles/X_full.md
+  python profiles/summarize.py traffic gpurun_out/prof_X.ncu-rep PARTICLES > profiles/traffic.json   (read by bench.py)
 """
 import collections
 import csv
@@ -78,5 +79,26 @@ def full(path):
         print()
 
 
+def traffic(path, particles):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the captured launches of each kernel."""
+    import json
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    acc = collections.OrderedDict()
+    for r in rows[2:]:
+        name = re.sub(r'<.*', '', short(r[idx['Kernel Name']]))
+        b = sum(float(r[idx[k]].replace(',', '')) * scale[units[idx[k]]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        t = float(r[idx['gpu__time_duration.sum']].replace(',', ''))
+        acc.setdefault(name, []).append((b, t, units[idx['gpu__time_duration.sum']]))
+    res = {"capture": path.replace('gpurun_out/', 'profiles/ summary of '), "particles": int(particles), "kernels": {}}
+    for k, v in acc.items():
+        res["kernels"][k] = {"dram_bytes_per_launch": sum(x[0] for x in v) / len(v), "launches": len(v),
+                             "ncu_duration": sum(x[1] for x in v) / len(v), "ncu_duration_unit": v[0][2]}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2])
+    {'launches': launches, 'full': full, 'traffic': traffic}[sys.argv[1]](*sys.argv[2:])

@@ -72,7 +72,7 @@ def test_c3_headline_size_properties(built_lib):
     assert np.all(rs[:, 4] <= np.arange(n)) and np.all(np.arange(n) < rs[:, 4] + rc[:, 4])
     del rs, rc, start, end
     tiles, tiled = sph.tile_stats()
-    assert tiles == n // 256 and tiled > 0.99 * tiles
+    assert tiles == n // 128 and tiled > 0.99 * tiles          # 128-particle tiles (csrc/sweeps.cu)
 
     # whole steps: walls, finiteness, determinism, and a solver that converges
     sph.upload(pos, vel)
