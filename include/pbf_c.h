@@ -215,6 +215,12 @@ uint64_t pbf_step_count(pbf_handle h);
 int pbf_slab_unique_id(void *out128);
 int pbf_slab_init(pbf_handle h, const void *id128, int rank, int nranks, int z_lo, int z_hi, int gz_global,
                   uint32_t halo_capacity);
+/* Peer-memory halo refresh (optional, after pbf_slab_init): the per-iteration lambda / position / |omega| halos go as
+ * plain stores into the neighbour's mailbox over NVLink with a release flag, instead of ncclSend/ncclRecv pairs.
+ * pbf_slab_p2p_handle returns this rank's 64-byte CUDA IPC handle; the host runtime gives every rank its neighbours'
+ * handles (NULL where there is none).  Migration and ghost records keep going through NCCL. */
+int pbf_slab_p2p_handle(pbf_handle h, void *out64);
+int pbf_slab_p2p_connect(pbf_handle h, const void *lo64, const void *hi64);
 /* "virtual ranks": n handles of ONE process on one device, stepped in lock step with device copies instead of
  * NCCL (tests on a single GPU).  Rank r owns layers [z_planes[r], z_planes[r+1]). */
 int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_global, uint32_t halo_capacity);

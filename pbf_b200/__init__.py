@@ -95,6 +95,8 @@ def lib():
         L.pbf_slab_unique_id.argtypes = [C.c_void_p]
         L.pbf_slab_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]
         L.pbf_slab_init_group.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_uint32]
+        L.pbf_slab_p2p_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.pbf_slab_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pbf_slab_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.pbf_slab_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.pbf_slab_step.argtypes = [C.c_void_p, C.c_int]

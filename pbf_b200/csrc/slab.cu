@@ -22,6 +22,7 @@
 // lock step with device-to-device copies in place of NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -65,7 +66,22 @@ struct pbf_slab_state {
     char *send[2], *recv[2];
     u32 *send_idx[2], *ghost_sorted;
     uint64_t migrated, exchanges, bytes_sent;
+    // peer-memory halo refresh (NVLink P2P stores + flags instead of NCCL send/recv): my mailbox, written by my neighbours,
+    // and where I write in theirs
+    bool p2p;
+    char *mbox;                         // [2 sides: from lo, from hi][MB_SLOTS][halo_cap x 16 B], then the flags
+    char *peer_data[2];                 // base of the area I fill in the lo / hi neighbour's mailbox
+    unsigned long long *peer_flag[2];
+    void *ipc_base[2];                  // opened IPC mappings (null for virtual ranks)
+    u32 *push_done;                     // last-block counter of k_halo_push
+    unsigned long long xseq;            // halo refreshes so far: the same number on every rank
 };
+
+constexpr int MB_SLOTS = 4;   // 2 would do: a rank pushes refresh e+2 only after it received e+1, which its neighbour
+                              // pushed after consuming e (push e+1 follows pull e in stream order)
+inline size_t mbox_slot_bytes(const pbf_slab_state *b) { return (size_t)b->halo_cap * 16; }
+inline size_t mbox_flags_offset(const pbf_slab_state *b) { return 2 * (size_t)MB_SLOTS * mbox_slot_bytes(b); }
+inline size_t mbox_bytes(const pbf_slab_state *b) { return mbox_flags_offset(b) + 2 * MB_SLOTS * sizeof(unsigned long long); }
 
 namespace {
 
@@ -273,6 +289,68 @@ k_scatter_p(u32 n, const u32 *__restrict__ idx, const float4 *__restrict__ in, f
     if (k < n) buf[idx[k]] = in[k];
 }
 
+// ---- peer-memory halo refresh ----------------------------------------------------------------------------------------------
+// Push: every boundary particle's value goes straight into the neighbour's mailbox over NVLink (plain stores to peer
+// memory); the block that finishes last publishes the refresh number in the neighbour's flag (release, system scope).
+// Pull: the neighbour's kernel waits for that number (acquire, system scope) and copies mailbox -> ghost slots.
+struct HaloSide {
+    u32 n;
+    const u32 *idx;                 // push: sorted slots of my boundary particles; pull: unused
+    char *data;                     // push: the neighbour's mailbox slot; pull: my mailbox slot
+    unsigned long long *flag;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+k_halo_push(HaloSide lo, HaloSide hi, const float4 *__restrict__ buf, int wide, unsigned long long seq, u32 *done) {
+    u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < lo.n + hi.n) {
+        const HaloSide &h = k < lo.n ? lo : hi;
+        if (k >= lo.n) k -= lo.n;
+        const float4 v = buf[h.idx[k]];
+        if (wide) reinterpret_cast<float4 *>(h.data)[k] = v;
+        else reinterpret_cast<float *>(h.data)[k] = v.w;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+        *done = 0u;
+        __threadfence_system();
+        if (lo.n) st_release_sys(lo.flag, seq);
+        if (hi.n) st_release_sys(hi.flag, seq);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_halo_pull(HaloSide lo, HaloSide hi, const u32 *__restrict__ ghost_sorted, float4 *__restrict__ buf, int wide,
+            unsigned long long seq) {
+    if (threadIdx.x == 0) {
+        if (lo.n) while (ld_acquire_sys(lo.flag) < seq) __nanosleep(64);
+        if (hi.n) while (ld_acquire_sys(hi.flag) < seq) __nanosleep(64);
+    }
+    __syncthreads();
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= lo.n + hi.n) return;
+    const u32 i = ghost_sorted[k];                 // ghosts from lo first, then from hi
+    const char *src = k < lo.n ? lo.data : hi.data;
+    const u32 j = k < lo.n ? k : k - lo.n;
+    // the mailbox is written by another GPU: volatile loads bypass L1, which may still hold the slot's previous contents
+    if (wide) {
+        const volatile float *q = reinterpret_cast<const volatile float *>(src) + 4 * (size_t)j;
+        buf[i] = make_float4(q[0], q[1], q[2], q[3]);
+    } else {
+        buf[i].w = reinterpret_cast<const volatile float *>(src)[j];
+    }
+}
+
 inline int nb(u32 n) { return (int)((n + 255) / 256); }
 
 // ---- transport -------------------------------------------------------------------------------------------------------
@@ -351,7 +429,52 @@ int exchange_counts(pbf_sim **grp, int ng, int which, u32 out[][2], u32 in[][2])
 }
 
 // refresh one 4-byte (.w of bufB) or 16-byte (bufA) quantity of every ghost from its owner
+int halo_refresh_p2p(pbf_sim **grp, int ng, bool wide) {
+    const size_t esz = wide ? 16 : 4;
+    // all pushes first: with virtual ranks every kernel is on one stream, and a pull waits for its neighbours' pushes
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        const unsigned long long seq = ++b->xseq;
+        const size_t slot = (size_t)(seq % MB_SLOTS);
+        HaloSide side[2];
+        for (int k = 0; k < 2; k++) {
+            side[k].n = b->has[k] ? b->n_bnd[k] : 0;
+            side[k].idx = b->send_idx[k];
+            side[k].data = b->peer_data[k] ? b->peer_data[k] + slot * mbox_slot_bytes(b) : nullptr;
+            side[k].flag = b->peer_flag[k] ? b->peer_flag[k] + slot : nullptr;
+        }
+        const u32 n = side[0].n + side[1].n;
+        if (n) {
+            k_halo_push<<<nb(n), 256, 0, s->stream>>>(side[0], side[1], wide ? s->bufA : s->bufB, wide ? 1 : 0, seq, b->push_done);
+            s->launches++;
+        }
+        b->exchanges++;
+        b->bytes_sent += (size_t)n * esz;
+    }
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        const unsigned long long seq = b->xseq;
+        const size_t slot = (size_t)(seq % MB_SLOTS);
+        HaloSide side[2];
+        for (int k = 0; k < 2; k++) {
+            side[k].n = b->has[k] ? b->n_ghost[k] : 0;
+            side[k].idx = nullptr;
+            side[k].data = b->mbox + ((size_t)k * MB_SLOTS + slot) * mbox_slot_bytes(b);
+            side[k].flag = reinterpret_cast<unsigned long long *>(b->mbox + mbox_flags_offset(b)) + k * MB_SLOTS + slot;
+        }
+        const u32 n = side[0].n + side[1].n;
+        if (n) {
+            k_halo_pull<<<nb(n), 256, 0, s->stream>>>(side[0], side[1], b->ghost_sorted, wide ? s->bufA : s->bufB, wide ? 1 : 0, seq);
+            s->launches++;
+        }
+    }
+    return PBF_OK;
+}
+
 int halo_refresh(pbf_sim **grp, int ng, bool wide) {
+    if (grp[0]->slab->p2p) return halo_refresh_p2p(grp, ng, wide);
     const size_t esz = wide ? 16 : 4;
     std::vector<size_t> sb(2 * ng), rb(2 * ng);
     for (int r = 0; r < ng; r++) {
@@ -563,12 +686,23 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
         A((void **)&b->send_idx[i], (size_t)halo_cap * 4);
     }
     A((void **)&b->ghost_sorted, (size_t)2 * halo_cap * 4);
+    A((void **)&b->mbox, mbox_bytes(b)); A((void **)&b->push_done, 16);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_counters, 16 * 4);
     if (e != cudaSuccess) { pbf_set_error(std::string("slab: allocation failed: ") + cudaGetErrorString(e)); return PBF_ERR_CUDA; }
     cudaMemsetAsync(b->gid, 0, (size_t)s->cap * 4, s->stream);
+    cudaMemsetAsync(b->mbox, 0, mbox_bytes(b), s->stream);
+    cudaMemsetAsync(b->push_done, 0, 16, s->stream);
+    cudaStreamSynchronize(s->stream);      // the mailbox flags are zero before any neighbour can see them
     s->slab = b;
     if (s->graph_valid) { cudaGraphExecDestroy(s->graph_exec); cudaGraphDestroy(s->graph); s->graph_valid = false; s->graph = nullptr; s->graph_exec = nullptr; }
     return PBF_OK;
+}
+
+// my lo neighbour's mailbox: I am its hi neighbour, so I fill its "from hi" half (index 1), and vice versa
+void p2p_attach(pbf_slab_state *b, int side, char *peer_mbox) {
+    const int theirs = side == 0 ? 1 : 0;
+    b->peer_data[side] = peer_mbox + (size_t)theirs * MB_SLOTS * mbox_slot_bytes(b);
+    b->peer_flag[side] = reinterpret_cast<unsigned long long *>(peer_mbox + mbox_flags_offset(b)) + theirs * MB_SLOTS;
 }
 
 }  // namespace
@@ -579,6 +713,10 @@ void slab_free(pbf_sim *s) {
     pbf_slab_state *b = s->slab;
     if (!b) return;
     if (b->comm && g_nccl.lib) g_nccl.CommDestroy(b->comm);
+    for (int k = 0; k < 2; k++)
+        if (b->ipc_base[k]) cudaIpcCloseMemHandle(b->ipc_base[k]);
+    if (b->mbox) cudaFree(b->mbox);
+    if (b->push_done) cudaFree(b->push_done);
     void *ptrs[] = {b->gid, b->btag, b->list[0], b->list[1], b->list[2], b->list[3], b->movers, b->holes, b->counters, b->send[0],
                     b->send[1], b->recv[0], b->recv[1], b->send_idx[0], b->send_idx[1], b->ghost_sorted};
     for (void *p : ptrs)
@@ -621,6 +759,39 @@ int pbf_slab_init(pbf_handle s, const void *id128, int rank, int nranks, int z_l
     return rc;
 }
 
+// Peer-memory halo refresh between processes: every rank exports its mailbox as a CUDA IPC handle (64 bytes), the host
+// runtime hands each rank its neighbours' handles (NULL where there is none).  Needs peer access between the devices
+// (NVLink on the B200 box); the mailboxes of all ranks must have been created with the same halo capacity.
+int pbf_slab_p2p_handle(pbf_handle s, void *out64) {
+    if (!s || !s->slab || !out64) { pbf_set_error("pbf_slab_p2p_handle: slab not initialised"); return PBF_ERR_STATE; }
+    DeviceGuard guard(s->device);
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    PBF_CUDA(cudaIpcGetMemHandle(&h, s->slab->mbox));
+    memcpy(out64, &h, 64);
+    return PBF_OK;
+}
+
+int pbf_slab_p2p_connect(pbf_handle s, const void *lo64, const void *hi64) {
+    if (!s || !s->slab) { pbf_set_error("pbf_slab_p2p_connect: slab not initialised"); return PBF_ERR_STATE; }
+    pbf_slab_state *b = s->slab;
+    if (b->group) { pbf_set_error("pbf_slab_p2p_connect: virtual ranks are connected by pbf_slab_init_group"); return PBF_ERR_STATE; }
+    DeviceGuard guard(s->device);
+    const void *handles[2] = {lo64, hi64};
+    for (int side = 0; side < 2; side++) {
+        if (!b->has[side]) continue;
+        if (!handles[side]) { pbf_set_error("pbf_slab_p2p_connect: missing neighbour handle"); return PBF_ERR_INVALID; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles[side], 64);
+        void *base = nullptr;
+        PBF_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        b->ipc_base[side] = base;
+        p2p_attach(b, side, static_cast<char *>(base));
+    }
+    b->p2p = true;
+    return PBF_OK;
+}
+
 // virtual ranks: n handles of this process (same device), rank r owns layers [z_planes[r], z_planes[r+1])
 int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_global, uint32_t halo_capacity) {
     if (!hs || n < 1 || !z_planes) { pbf_set_error("pbf_slab_init_group: bad argument"); return PBF_ERR_INVALID; }
@@ -636,6 +807,15 @@ int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_g
             hs[r]->stream = hs[0]->stream;
         }
     }
+    // the halo refreshes of a virtual group take the same peer-memory path as real ranks, with plain pointers
+    const char *np = getenv("PBF_SLAB_P2P");
+    if (!(np && np[0] == '0'))
+        for (int r = 0; r < n; r++) {
+            pbf_slab_state *b = hs[r]->slab;
+            if (b->has[0]) p2p_attach(b, 0, hs[r - 1]->slab->mbox);
+            if (b->has[1]) p2p_attach(b, 1, hs[r + 1]->slab->mbox);
+            b->p2p = true;
+        }
     return PBF_OK;
 }
 

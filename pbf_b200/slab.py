@@ -5,6 +5,7 @@ One process per GPU (torchrun).  torch.distributed is plumbing only: it broadcas
 reduces timings; the halo/migration traffic itself goes through the library's own communicator on its own stream.
 """
 import ctypes as C
+import os
 import json
 import time
 
@@ -66,6 +67,24 @@ class SlabSPH(SPH):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         _check(lib().pbf_slab_init(self._h, buf, self.rank, self.nranks, self.z_lo, self.z_hi, self.gz_global,
                                    self.halo_capacity))
+
+    def connect_p2p(self, dist, device):
+        """Peer-memory halo refresh: all-gather the ranks' 64-byte CUDA IPC mailbox handles over torch.distributed and
+        open the two neighbours'.  PBF_SLAB_P2P=0 keeps the NCCL send/recv path (the baseline it is measured against)."""
+        import torch
+        if os.environ.get("PBF_SLAB_P2P", "1") == "0" or self.nranks == 1:
+            return False
+        mine = (C.c_char * 64)()
+        _check(lib().pbf_slab_p2p_handle(self._h, mine))
+        t = torch.frombuffer(bytearray(bytes(mine)), dtype=torch.uint8).clone().to(device)
+        parts = [torch.empty_like(t) for _ in range(self.nranks)]
+        dist.all_gather(parts, t)
+        raw = [bytes(x.cpu().numpy().tobytes()) for x in parts]
+        lo = (C.c_char * 64).from_buffer_copy(raw[self.rank - 1]) if self.rank > 0 else None
+        hi = (C.c_char * 64).from_buffer_copy(raw[self.rank + 1]) if self.rank + 1 < self.nranks else None
+        _check(lib().pbf_slab_p2p_connect(self._h, lo, hi))
+        dist.barrier()        # nobody steps before every mailbox is mapped
+        return True
 
     def upload_slab(self, pos, vel, gid):
         pos = np.ascontiguousarray(pos, np.float32)
@@ -177,6 +196,7 @@ def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algo
     halo_cap = 1 << 18
     s = SlabSPH(rank, world, planes, cfg["grid"][:2], gz_global, int(n0 * 1.2) + 2 * halo_cap, halo_cap, device=local)
     s.init_nccl(broadcast_unique_id(dist, rank, dev))
+    p2p = s.connect_p2p(dist, dev)
     s.SetNumSolverIterations(cfg["iters"])
     s.SetVorticityConfinementEnabled(bool(cfg["vort"]))
     s.upload_slab(pos, vel, gid)
@@ -231,7 +251,8 @@ def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algo
             "data": "synthetic",
             "config": {"workload": "dam-break %dx%dx%d particles per GPU (block %d x deeper along z), grid %dx%dx%d per GPU, %d solver iters, vorticity+XSPH %s; z-slabs with 1-layer halos"
                                    % (cfg["n3"] + (world,) + cfg["grid"] + (cfg["iters"], "on" if cfg["vort"] else "off")),
-                       "parallelism": "slab%d" % world, "particles_total": int(n_total),
+                       "parallelism": "slab%d" % world,
+                       "halo_transport": "peer-memory stores + flags over NVLink (lambda, positions, |omega|); NCCL send/recv for migration and ghost records" if p2p else "NCCL send/recv", "particles_total": int(n_total),
                        "migrated_particles_total": int(tsum[2].item()), "ghost_particles_total": int(tsum[3].item()),
                        "exchanges_per_step": st["exchanges"] // max(1, args.steps + args.warmup),
                        "l2": "per-GPU working set (~2 GB) far exceeds the 126 MB L2",

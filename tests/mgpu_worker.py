@@ -24,6 +24,7 @@ def main():
     p, v, g = slab.split_scene(pos, vel, planes, grid[2])[rank]
     s = slab.SlabSPH(rank, world, planes, grid[:2], grid[2], int(p.shape[0] * 1.5) + 2 * 8192, 8192, device=local)
     s.init_nccl(slab.broadcast_unique_id(dist, rank, torch.device("cuda", local)))
+    p2p = s.connect_p2p(dist, torch.device("cuda", local))     # PBF_SLAB_P2P=0: NCCL send/recv for every exchange
     s.SetNumSolverIterations(3)
     s.SetVorticityConfinementEnabled(True)
     s.upload_slab(p, v, g)
@@ -49,7 +50,7 @@ def main():
         mig = sum(p[3]["migrated"] for p in parts)
         gh = sum(p[3]["ghosts_lo"] + p[3]["ghosts_hi"] for p in parts)
         ok = bool(np.all(seen == 1) and dp < 2e-4 and dv < 2e-4 / 0.016 and mig > 0 and gh > 0)
-        print("MGPU_RESULT ok=%s world=%d dp=%.3g dv=%.3g migrated=%d ghosts=%d planes=%s" % (ok, world, dp, dv, mig, gh, planes))
+        print("MGPU_RESULT ok=%s p2p=%s world=%d dp=%.3g dv=%.3g migrated=%d ghosts=%d planes=%s" % (ok, p2p, world, dp, dv, mig, gh, planes))
     dist.barrier()
     s.close()
     dist.destroy_process_group()

@@ -1,5 +1,6 @@
-"""Real multi-GPU parity (NCCL transport): needs >= 2 GPUs, otherwise skipped.  The single-GPU "virtual rank" test in
-test_gpu_parity.py covers the same slab logic with device copies."""
+"""Real multi-GPU parity: needs >= 2 GPUs, otherwise skipped.  Both halo transports -- peer-memory stores with flags over
+NVLink (the default) and NCCL send/recv (PBF_SLAB_P2P=0) -- against a single-domain run.  The single-GPU "virtual rank"
+test in test_gpu_parity.py covers the same slab logic inside one process."""
 import os
 import subprocess
 import sys
@@ -10,13 +11,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_nccl_slabs_match_single_domain(built_lib, world):
+def test_slabs_match_single_domain(built_lib, world, p2p):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29617 + world), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PBF_SLAB_P2P=p2p))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "MGPU_RESULT ok=True" in r.stdout, r.stdout[-3000:]
+    assert "MGPU_RESULT ok=True p2p=%s" % (p2p == "1") in r.stdout, r.stdout[-3000:]
