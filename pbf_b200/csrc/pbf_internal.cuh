@@ -33,6 +33,19 @@ struct SimParams {
     int extforce;
 };
 
+// Fused halo push of the slab runtime (slab.cu): the sweep that produces a halo quantity (lambda, new position, |omega|)
+// stores it for its boundary particles straight into the neighbour GPU's mailbox over NVLink, and the block that
+// finishes last publishes the refresh number.  All zero on a single-GPU handle.
+struct HaloPush {
+    const u32 *map;                  // per sorted slot: 0 = not a boundary particle, k+1 = k-th of the z- face, 0x80000000|(k+1) of z+
+    char *data[2];                   // the z- / z+ neighbour's mailbox slot for this refresh
+    unsigned long long *flag[2];
+    unsigned long long seq;
+    u32 *done;                       // counter of the blocks that have pushed
+    const u32 *expect;               // how many blocks (tiles) hold boundary particles at all: the last of them publishes
+    u32 count[2];                    // boundary particles per face (a flag is only published for a non-empty face)
+};
+
 struct SortPlan {
     int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
     int passes;      // 8-bit onesweep passes
@@ -123,11 +136,11 @@ int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist);
 int launch_keys_only(pbf_sim *s, u32 first, u32 count);
 int launch_reorder_cells(pbf_sim *s);
 int launch_highlight(pbf_sim *s);
-int launch_lambda(pbf_sim *s);
-int launch_delta_p(pbf_sim *s);
+int launch_lambda(pbf_sim *s, const HaloPush *push = nullptr);
+int launch_delta_p(pbf_sim *s, const HaloPush *push = nullptr);
 int launch_update(pbf_sim *s);
 int launch_vorticity(pbf_sim *s);
-int launch_vorticity_a(pbf_sim *s);
+int launch_vorticity_a(pbf_sim *s, const HaloPush *push = nullptr);
 int launch_vorticity_b(pbf_sim *s);
 int launch_density_diag(pbf_sim *s);
 int launch_kinetic_diag(pbf_sim *s);

@@ -73,7 +73,12 @@ struct pbf_slab_state {
     char *peer_data[2];                 // base of the area I fill in the lo / hi neighbour's mailbox
     unsigned long long *peer_flag[2];
     void *ipc_base[2];                  // opened IPC mappings (null for virtual ranks)
-    u32 *push_done;                     // last-block counter of k_halo_push
+    u32 *push_done;                     // last-block counter of k_halo_push / of the fused push
+    u32 *push_tiles;                    // [0] sweep tiles that hold boundary particles, [1..] per-tile "seen" flags
+    u32 max_tiles;
+    u32 *push_map;                      // per sorted slot: which boundary particle of which face (HaloPush::map)
+    bool pushed;                        // the sweep just launched has pushed refresh number xseq already
+    bool fused;                         // PBF_SLAB_FUSED=1: the producing sweep pushes its halo itself (default: a separate push kernel)
     unsigned long long xseq;            // halo refreshes so far: the same number on every rank
 };
 
@@ -254,16 +259,21 @@ k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *po
 // after the sort: where did the boundary particles (to pack) and the ghosts (to overwrite) land?
 __global__ void __launch_bounds__(256)
 k_halo_index(u32 n, u32 n_local, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
-             u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, GridInfo g) {
+             u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, u32 *__restrict__ push_map,
+             u32 *__restrict__ push_tiles, u32 tile_size, GridInfo g) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const u32 k = skey[i] & ~PBF_KEY_NOCELL;
     const int cz = (int)((k % (u32)g.gxgz) / (u32)g.gx);
-    if (cz > 1 && cz < g.gz - 2) return;     // interior layer: neither ghost nor boundary
-    const u32 id = perm[i];
+    u32 t = 0;
+    const bool edge = !(cz > 1 && cz < g.gz - 2);    // interior layers hold neither ghosts nor boundary particles
+    const u32 id = edge ? perm[i] : 0u;
+    if (edge && id < n_local) t = btag[id];
+    push_map[i] = t;
+    if (!edge) return;
     if (id >= n_local) { ghost_sorted[id - n_local] = i; return; }
-    const u32 t = btag[id];
     if (t == 0) return;
+    if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
     if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
     else send_lo[t - 1u] = i;
 }
@@ -429,12 +439,37 @@ int exchange_counts(pbf_sim **grp, int ng, int which, u32 out[][2], u32 in[][2])
 }
 
 // refresh one 4-byte (.w of bufB) or 16-byte (bufA) quantity of every ghost from its owner
+// Fused push: fills the HaloPush block of the sweep that is about to produce the next halo quantity of rank `s` (its
+// epilogue stores the boundary particles' values into the neighbours' mailboxes; halo_refresh then only pulls).
+// false: not applicable -- NCCL transport, or PBF_SLAB_FUSED=0 -- and halo_refresh pushes with its own kernel.
+bool make_push(pbf_sim *s, HaloPush *hp) {
+    pbf_slab_state *b = s->slab;
+    if (!b->p2p || !b->fused) return false;
+    const unsigned long long seq = ++b->xseq;
+    const size_t slot = (size_t)(seq % MB_SLOTS);
+    memset(hp, 0, sizeof(*hp));
+    for (int k = 0; k < 2; k++) {
+        hp->count[k] = b->has[k] ? b->n_bnd[k] : 0;
+        hp->data[k] = b->peer_data[k] ? b->peer_data[k] + slot * mbox_slot_bytes(b) : nullptr;
+        hp->flag[k] = b->peer_flag[k] ? b->peer_flag[k] + slot : nullptr;
+    }
+    hp->seq = seq;
+    hp->done = b->push_done;
+    hp->expect = b->push_tiles;
+    hp->map = hp->count[0] + hp->count[1] ? b->push_map : nullptr;     // nothing to push: the sweep runs as on one GPU
+    b->pushed = true;
+    return true;
+}
+
 int halo_refresh_p2p(pbf_sim **grp, int ng, bool wide) {
     const size_t esz = wide ? 16 : 4;
     // all pushes first: with virtual ranks every kernel is on one stream, and a pull waits for its neighbours' pushes
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
         pbf_slab_state *b = s->slab;
+        b->exchanges++;
+        b->bytes_sent += ((size_t)(b->has[0] ? b->n_bnd[0] : 0) + (b->has[1] ? b->n_bnd[1] : 0)) * esz;
+        if (b->pushed) { b->pushed = false; continue; }       // the producing sweep has pushed this refresh itself
         const unsigned long long seq = ++b->xseq;
         const size_t slot = (size_t)(seq % MB_SLOTS);
         HaloSide side[2];
@@ -449,8 +484,6 @@ int halo_refresh_p2p(pbf_sim **grp, int ng, bool wide) {
             k_halo_push<<<nb(n), 256, 0, s->stream>>>(side[0], side[1], wide ? s->bufA : s->bufB, wide ? 1 : 0, seq, b->push_done);
             s->launches++;
         }
-        b->exchanges++;
-        b->bytes_sent += (size_t)n * esz;
     }
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -620,18 +653,21 @@ int slab_step(pbf_sim **grp, int ng) {
         s->launches += launch_sort_passes(s);
         s->launches += launch_reorder_cells(s);
         if (b->n_ghost[0] + b->n_ghost[1] + b->n_bnd[0] + b->n_bnd[1]) {
+            cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(s->n, b->n_local, s->skey, s->perm, b->btag, b->send_idx[0],
-                                                          b->send_idx[1], b->ghost_sorted, s->grid);
+                                                          b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
+                                                          plan_tile_size(), s->grid);
             s->launches++;
         }
         s->launches += launch_highlight(s);
     }
     // ---- solver: K x [lambda, halo lambda, delta-p, halo positions] ---------------------------------------------------------
     const int K = grp[0]->params.num_solver_iterations;
+    HaloPush hp;
     for (int it = 0; it < K; it++) {
-        for (int r = 0; r < ng; r++) grp[r]->launches += launch_lambda(grp[r]);
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_lambda(grp[r], make_push(grp[r], &hp) ? &hp : nullptr);
         if ((rc = halo_refresh(grp, ng, false))) return rc;
-        for (int r = 0; r < ng; r++) grp[r]->launches += launch_delta_p(grp[r]);
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_delta_p(grp[r], make_push(grp[r], &hp) ? &hp : nullptr);
         if ((rc = halo_refresh(grp, ng, true))) return rc;
     }
     // ---- update, vorticity ----------------------------------------------------------------------------------------------------
@@ -639,7 +675,7 @@ int slab_step(pbf_sim **grp, int ng) {
     if (grp[0]->params.vorticity_confinement) {
         for (int r = 0; r < ng; r++) {
             pbf_sim *s = grp[r];
-            launch_vorticity_a(s);
+            launch_vorticity_a(s, make_push(s, &hp) ? &hp : nullptr);
             s->launches++;
         }
         if ((rc = halo_refresh(grp, ng, false))) return rc;     // |omega| lives in bufB.w like lambda did
@@ -686,7 +722,9 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
         A((void **)&b->send_idx[i], (size_t)halo_cap * 4);
     }
     A((void **)&b->ghost_sorted, (size_t)2 * halo_cap * 4);
-    A((void **)&b->mbox, mbox_bytes(b)); A((void **)&b->push_done, 16);
+    A((void **)&b->mbox, mbox_bytes(b)); A((void **)&b->push_done, 16); A((void **)&b->push_map, (size_t)s->cap * 4);
+    b->max_tiles = (s->cap + plan_tile_size() - 1) / plan_tile_size();
+    A((void **)&b->push_tiles, (size_t)(1 + b->max_tiles) * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_counters, 16 * 4);
     if (e != cudaSuccess) { pbf_set_error(std::string("slab: allocation failed: ") + cudaGetErrorString(e)); return PBF_ERR_CUDA; }
     cudaMemsetAsync(b->gid, 0, (size_t)s->cap * 4, s->stream);
@@ -717,6 +755,8 @@ void slab_free(pbf_sim *s) {
         if (b->ipc_base[k]) cudaIpcCloseMemHandle(b->ipc_base[k]);
     if (b->mbox) cudaFree(b->mbox);
     if (b->push_done) cudaFree(b->push_done);
+    if (b->push_map) cudaFree(b->push_map);
+    if (b->push_tiles) cudaFree(b->push_tiles);
     void *ptrs[] = {b->gid, b->btag, b->list[0], b->list[1], b->list[2], b->list[3], b->movers, b->holes, b->counters, b->send[0],
                     b->send[1], b->recv[0], b->recv[1], b->send_idx[0], b->send_idx[1], b->ghost_sorted};
     for (void *p : ptrs)
@@ -789,6 +829,8 @@ int pbf_slab_p2p_connect(pbf_handle s, const void *lo64, const void *hi64) {
         p2p_attach(b, side, static_cast<char *>(base));
     }
     b->p2p = true;
+    const char *fz = getenv("PBF_SLAB_FUSED");     // measured slower than the separate push kernel: opt in
+    b->fused = fz && fz[0] == '1';
     return PBF_OK;
 }
 
@@ -815,6 +857,8 @@ int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_g
             if (b->has[0]) p2p_attach(b, 0, hs[r - 1]->slab->mbox);
             if (b->has[1]) p2p_attach(b, 1, hs[r + 1]->slab->mbox);
             b->p2p = true;
+            const char *fz = getenv("PBF_SLAB_FUSED");
+            b->fused = fz && fz[0] == '1';
         }
     return PBF_OK;
 }

@@ -321,6 +321,33 @@ __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned lo
     else if (live) general_walk<NSRC>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
 }
 
+// Fused halo push (slab runtime): `wide` sends the 16-byte record, otherwise its .w; every thread of the block calls this
+// after its output is written.
+__device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, const float4 &out, bool wide, int tid) {
+    if (hp.map == nullptr) return;                           // uniform: single-GPU handles stop here
+    bool wrote = false;
+    if (live) {
+        const u32 t = hp.map[i];
+        if (t) {
+            char *dst = (t >> 31) ? hp.data[1] : hp.data[0];         // selects, not indexing: the block stays in constant memory
+            const u32 k = (t & 0x7fffffffu) - 1u;
+            if (wide) reinterpret_cast<float4 *>(dst)[k] = out;
+            else reinterpret_cast<float *>(dst)[k] = out.w;
+            wrote = true;
+        }
+    }
+    // Only tiles with boundary particles (about 2 % of them) pay for the system-scope fence and the counter; their number
+    // is known from the halo index of this step.
+    if (wrote) __threadfence_system();
+    if (!__syncthreads_or(wrote)) return;
+    if (tid == 0 && atomicAdd(hp.done, 1u) + 1u == *hp.expect) {
+        *hp.done = 0u;
+        __threadfence_system();
+        if (hp.count[0]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hp.flag[0]), "l"(hp.seq) : "memory");
+        if (hp.count[1]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hp.flag[1]), "l"(hp.seq) : "memory");
+    }
+}
+
 #define TILE_ARGS const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,   \
                   const int *__restrict__ desc, const u32 *__restrict__ runs
 
@@ -328,7 +355,8 @@ __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned lo
 // out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
 template <bool DIAG>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
-k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag) {
+k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag,
+         const HaloPush hp) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
@@ -336,6 +364,7 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     TileCtx tc = tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid);
     const bool live = i < n;
     float err = 0.0f;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
     walk<1>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
@@ -361,8 +390,9 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
         const float Ssum = cg * cg * (S.x + S.y) + (sx * sx + sy * sy + sz * sz);
         const float C = r * P.one_over_rho_0 - 1.0f;
         if (DIAG) err = fabsf(C);
-        else B[i] = make_float4(pi.x, pi.y, pi.z, -C / (Ssum + P.epsilon));
+        else B[i] = out = make_float4(pi.x, pi.y, pi.z, -C / (Ssum + P.epsilon));
     }
+    if (!DIAG) halo_push(hp, i, live, out, false, tid);
     if (DIAG) {
         __shared__ float red[TL / 32];
 #pragma unroll
@@ -379,7 +409,7 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
 
 // ---- K9 updatepos.glsl:43-105, Jacobi: reads B {p, lambda}, writes A -----------------------------------------------
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
-k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P) {
+k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
@@ -405,20 +435,21 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
         ay = __ffma2_rn(cc, q.dy, ay);
         az = __ffma2_rn(cc, q.dz, az);
     });
-    if (!live) return;
     const float s = SPIKY_GRAD * P.one_over_rho_0;
     float x = pi.x + s * (ax.x + ax.y), y = pi.y + s * (ay.x + ay.y), z = pi.z + s * (az.x + az.y);
     x = fminf(fmaxf(x, g.wlo[0]), g.whi[0]);                               // updatepos.glsl:98-100
     y = fminf(fmaxf(y, g.wlo[1]), g.whi[1]);
     z = fminf(fmaxf(z, g.wlo[2]), g.whi[2]);
-    A[i] = make_float4(x, y, z, 0.0f);
+    const float4 out = make_float4(x, y, z, 0.0f);
+    if (live) A[i] = out;
+    halo_push(hp, i, live, out, true, tid);
 }
 
 // ---- K11 vorticity.glsl:34-60 (first sweep): XSPH + vorticity ------------------------------------------------------------
 // out: vprime = v + c*sum v_ij W, omega = sum v_ij x gradW, B = {p, |omega|}
 __global__ void __launch_bounds__(TL)
 k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
-              float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P) {
+              float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P, const HaloPush hp) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
@@ -463,12 +494,15 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
     wy = make_float2(wy.x - qy.x, wy.y - qy.y);
     wz = make_float2(wz.x - qz.x, wz.y - qz.y);
 #endif
-    if (!live) return;
     const float cw = -P.xsph_c * POLY6;
-    vprime[i] = make_float4(vi.x + cw * (vx.x + vx.y), vi.y + cw * (vy.x + vy.y), vi.z + cw * (vz.x + vz.y), 0.0f);
     const float ox = SPIKY_GRAD * (wx.x + wx.y), oy = SPIKY_GRAD * (wy.x + wy.y), oz = SPIKY_GRAD * (wz.x + wz.y);
-    omega[i] = make_float4(ox, oy, oz, 0.0f);
-    B[i] = make_float4(pi.x, pi.y, pi.z, sqrtf(ox * ox + oy * oy + oz * oz));   // vorticity.glsl:60
+    const float4 out = make_float4(pi.x, pi.y, pi.z, sqrtf(ox * ox + oy * oy + oz * oz));   // vorticity.glsl:60
+    if (live) {
+        vprime[i] = make_float4(vi.x + cw * (vx.x + vx.y), vi.y + cw * (vy.x + vy.y), vi.z + cw * (vz.x + vz.y), 0.0f);
+        omega[i] = make_float4(ox, oy, oz, 0.0f);
+        B[i] = out;
+    }
+    halo_push(hp, i, live, out, false, tid);
 }
 
 // ---- K11 vorticity.glsl:65-85 (second sweep): confinement force, velocity[id] written once -------------------------------
@@ -526,20 +560,23 @@ int launch_plan(pbf_sim *s) {
     return 1;
 }
 
-int launch_lambda(pbf_sim *s) {
+static const HaloPush NO_PUSH = {};
+
+int launch_lambda(pbf_sim *s, const HaloPush *push) {
     k_lambda<false><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
-                                                              nullptr);
+                                                              nullptr, push ? *push : NO_PUSH);
     return 1;
 }
 
-int launch_delta_p(pbf_sim *s) {
-    k_delta_p<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s));
+int launch_delta_p(pbf_sim *s, const HaloPush *push) {
+    k_delta_p<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s),
+                                                        push ? *push : NO_PUSH);
     return 1;
 }
 
-int launch_vorticity_a(pbf_sim *s) {
+int launch_vorticity_a(pbf_sim *s, const HaloPush *push) {
     k_vorticity_a<<<ntiles(s->n), TL, TL_SMEM2, s->stream>>>(s->n, s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
-                                                            s->omega, s->grid, sim_params(s));
+                                                            s->omega, s->grid, sim_params(s), push ? *push : NO_PUSH);
     return 1;
 }
 
@@ -549,10 +586,10 @@ int launch_vorticity_b(pbf_sim *s) {
     return 1;
 }
 
-int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s) + launch_vorticity_b(s); }
+int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s, nullptr) + launch_vorticity_b(s); }
 
 int launch_density_diag(pbf_sim *s) {
     k_lambda<true><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
-                                                             s->diag);
+                                                             s->diag, NO_PUSH);
     return 1;
 }

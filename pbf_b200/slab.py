@@ -252,7 +252,8 @@ def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algo
             "config": {"workload": "dam-break %dx%dx%d particles per GPU (block %d x deeper along z), grid %dx%dx%d per GPU, %d solver iters, vorticity+XSPH %s; z-slabs with 1-layer halos"
                                    % (cfg["n3"] + (world,) + cfg["grid"] + (cfg["iters"], "on" if cfg["vort"] else "off")),
                        "parallelism": "slab%d" % world,
-                       "halo_transport": "peer-memory stores + flags over NVLink (lambda, positions, |omega|); NCCL send/recv for migration and ghost records" if p2p else "NCCL send/recv", "particles_total": int(n_total),
+                       "halo_transport": ("peer-memory stores + flags over NVLink (lambda, positions, |omega|)%s; NCCL send/recv for migration and ghost records"
+                                          % (", pushed by the producing sweep's epilogue" if os.environ.get("PBF_SLAB_FUSED") == "1" else ", push kernel + pull kernel")) if p2p else "NCCL send/recv", "particles_total": int(n_total),
                        "migrated_particles_total": int(tsum[2].item()), "ghost_particles_total": int(tsum[3].item()),
                        "exchanges_per_step": st["exchanges"] // max(1, args.steps + args.warmup),
                        "l2": "per-GPU working set (~2 GB) far exceeds the 126 MB L2",

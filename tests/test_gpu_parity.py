@@ -234,15 +234,16 @@ def test_errors(built_lib):
         sph.upload(np.zeros((100, 4), np.float32))
 
 
-@pytest.mark.parametrize("p2p", ["1", "0"])
+@pytest.mark.parametrize("p2p,fused", [("1", "1"), ("1", "0"), ("0", "0")])
 @pytest.mark.parametrize("nranks", [2, 3])
-def test_virtual_slabs_match_single_domain(built_lib, nranks, p2p, monkeypatch):
+def test_virtual_slabs_match_single_domain(built_lib, nranks, p2p, fused, monkeypatch):
     """Slab decomposition (virtual ranks on one GPU, device copies instead of NCCL) reproduces the single-domain run.
 
     Equal-cell particles are ordered by input slot, which differs between the decompositions, so sums are taken in a
     different order: tolerance instead of bit equality."""
     from pbf_b200 import slab
     monkeypatch.setenv("PBF_SLAB_P2P", p2p)      # halo refresh by peer-memory mailboxes (default) or by copies
+    monkeypatch.setenv("PBF_SLAB_FUSED", fused)  # pushed by the producing sweep's epilogue (default) or by its own kernel
     grid = (64, 32, 96)
     pos, vel = oracle.dam_break(16, 16, 64, origin=(18.5, 0.5, 18.5))
     rng = np.random.default_rng(5)
