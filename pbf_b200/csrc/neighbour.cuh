@@ -108,15 +108,9 @@ __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bo
     q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
     q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
     q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));
-#ifdef PBF_V_ILCLAMP
-    // variant: no TINY add on the FMA pipe; rsqrt(0) = +inf is clamped instead (two FMNMX on the ALU pipe)
-    const float2 rc = make_float2(fminf(v0 ? q.r2.x : FAR2, H2), fminf(v1 ? q.r2.y : FAR2, H2));
-    q.il = make_float2(fminf(rsqrt_ftz(rc.x), 1.0e12f), fminf(rsqrt_ftz(rc.y), 1.0e12f));
-#else
     const float2 re = __fadd2_rn(q.r2, make_float2(TINY, TINY));
     const float2 rc = make_float2(fminf(v0 ? re.x : FAR2, H2), fminf(v1 ? re.y : FAR2, H2));
     q.il = make_float2(rsqrt_ftz(rc.x), rsqrt_ftz(rc.y));
-#endif
     q.t2 = __ffma2_rn(rc, q.il, make_float2(-H, -H));                // l - h: 0 at and beyond the support radius
     q.t = __fadd2_rn(rc, make_float2(-H2, -H2));                     // r^2 - h^2, exactly <= 0
     return q;

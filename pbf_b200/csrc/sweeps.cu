@@ -214,7 +214,41 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
         }
     }
 #endif
-    if (c.mode && tid == 0) {
+    if (c.mode == 1 && tid < 32) {
+        // One image (all but a few per cent of the tiles): lanes 0..8 of warp 0 issue one bulk copy each -- nine range
+        // lengths in one coalesced load, their image offsets by a warp scan -- instead of one thread issuing nine in a row
+        // (~300 instructions on the block's critical path).
+        const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
+        const int no = tid < 9 ? __ldg(dg + D_N + tid) : 0;
+        const int so = tid < 9 ? __ldg(dg + D_S + tid) : 0;
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        int incl = no;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 8);
+        float4 *sm0 = reinterpret_cast<float4 *>(dsm);
+        float4 *sm1 = sm0 + (TL_CAP + TL_PAD);
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < TL_PAD; k++) {              // see tile_stage
+                sm0[total + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NSRC == 2) sm1[total + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((unsigned)(total * 16 * NSRC)) : "memory");
+        }
+        __syncwarp();
+        if (no > 0) {
+            const int at = incl - no;
+            bulk_g2s((unsigned)__cvta_generic_to_shared(sm0) + 16u * at, src0 + so, 16u * no, mb);
+            if (NSRC == 2) bulk_g2s((unsigned)__cvta_generic_to_shared(sm1) + 16u * at, src1 + so, 16u * no, mb);
+        }
+    } else if (c.mode > 1 && tid == 0) {
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -246,12 +280,7 @@ template <int NSRC, class F>
 __device__ __forceinline__ void walk_run(unsigned a, const unsigned end, F &body) {
 #pragma unroll 1
     for (; a < end; a += 32u) {
-#ifdef PBF_V_PROBE_NOLDS     // experiment only (wrong results): no shared-memory reads in the walk
-        Pair p;
-        p.x = p.y = p.z = p.w = make_float2(__uint_as_float(a), __uint_as_float(end));
-#else
         const Pair p = make_pair(lds128(a), lds128(a + 16u));
-#endif
         if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
         else body(p, p, true, a + 16u < end);
     }
@@ -263,7 +292,6 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
                                            const int *__restrict__ desc, int tid, F body) {
     const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
     __syncthreads();                                       // the barrier is initialised
-#ifndef PBF_V_NO_ONEPHASE
     if (c.mode == 1) {                                     // all nine ranges in one image (all but a handful of tiles):
         mbar_wait(mb, 0u);                                 // no per-run phase test
 #pragma unroll
@@ -273,7 +301,6 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
         }
         return;
     }
-#endif
     int lo = 0;
 #pragma unroll 1
     for (int ph = 0; ph < c.mode; ph++) {
@@ -368,10 +395,6 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
     walk<1>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
-#ifdef PBF_V_PROBE_NOMATH   // experiment only (wrong results): staging + loads + loop, almost no arithmetic
-            rho = __fadd2_rn(rho, make_float2(c.x.x, v1 ? c.x.y : 0.0f));
-            return;
-#endif
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);       // (h-l)^2 / l
@@ -459,11 +482,7 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
-#ifdef PBF_V_VORT_PQ
-    float2 qx = vx, qy = vx, qz = vx;
-#else
     const float2 neg1 = make_float2(-1.0f, -1.0f);
-#endif
     walk<2>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
@@ -474,26 +493,12 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
         vy = __ffma2_rn(uy, w, vy);
         vz = __ffma2_rn(uz, w, vz);
         const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);          // grad = SPIKY_GRAD * cc * d
-#ifdef PBF_V_VORT_PQ
-        // cross(v_ij, cc d) = P - Q with P = sum (cc u)_a d_b, Q = sum (cc u)_b d_a kept as separate sums: nine packed
-        // operations instead of twelve, the subtraction happens once after the walk
-        const float2 ax = __fmul2_rn(cc, ux), ay = __fmul2_rn(cc, uy), az = __fmul2_rn(cc, uz);
-        wx = __ffma2_rn(ay, q.dz, wx); qx = __ffma2_rn(az, q.dy, qx);
-        wy = __ffma2_rn(az, q.dx, wy); qy = __ffma2_rn(ax, q.dz, qy);
-        wz = __ffma2_rn(ax, q.dy, wz); qz = __ffma2_rn(ay, q.dx, qz);
-#else
         const float2 gx = __fmul2_rn(cc, q.dx), gy = __fmul2_rn(cc, q.dy), gz = __fmul2_rn(cc, q.dz);
         // cross(v_ij, grad)
         wx = __ffma2_rn(uy, gz, __ffma2_rn(__fmul2_rn(gy, uz), neg1, wx));
         wy = __ffma2_rn(uz, gx, __ffma2_rn(__fmul2_rn(gz, ux), neg1, wy));
         wz = __ffma2_rn(ux, gy, __ffma2_rn(__fmul2_rn(gx, uy), neg1, wz));
-#endif
     });
-#ifdef PBF_V_VORT_PQ
-    wx = make_float2(wx.x - qx.x, wx.y - qx.y);
-    wy = make_float2(wy.x - qy.x, wy.y - qy.y);
-    wz = make_float2(wz.x - qz.x, wz.y - qz.y);
-#endif
     const float cw = -P.xsph_c * POLY6;
     const float ox = SPIKY_GRAD * (wx.x + wx.y), oy = SPIKY_GRAD * (wy.x + wy.y), oz = SPIKY_GRAD * (wz.x + wz.y);
     const float4 out = make_float4(pi.x, pi.y, pi.z, sqrtf(ox * ox + oy * oy + oz * oz));   // vorticity.glsl:60
