@@ -278,11 +278,14 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 // body(candidate pair of array 0, same pair of array 1, valid0, valid1)
 template <int NSRC, class F>
 __device__ __forceinline__ void walk_run(unsigned a, const unsigned end, F &body) {
+    // second candidate of a pair valid <=> a + 16 < end; inside the loop end >= a + 16 >= 16, so the comparison against
+    // end - 16 (hoisted) is the same and saves an add per iteration
+    const unsigned last = end - 16u;
 #pragma unroll 1
     for (; a < end; a += 32u) {
         const Pair p = make_pair(lds128(a), lds128(a + 16u));
-        if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a + 16u < end);
-        else body(p, p, true, a + 16u < end);
+        if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a < last);
+        else body(p, p, true, a < last);
     }
 }
 
