@@ -163,6 +163,15 @@ int pbf_get_timings(pbf_handle h, float ms[5]);
  * over the solver iterations of the last timed step -- what bench.py's roofline is computed from */
 int pbf_get_solver_kernel_timings(pbf_handle h, float *lambda_ms, float *delta_p_ms);
 
+/* Selection.  pbf_pick_particle replaces Selection::GetParticle (src/Selection.cpp:55-85), which
+ * renders every particle as a sphere into an id buffer and reads the pixel under the cursor: here the id of the nearest
+ * sphere (radius in grid units; the reference draws 0.1 render units = 0.5 grid units) hit by the ray origin +
+ * t * direction, t >= 0, or -1.  The caller un-projects the cursor (the reference's camera lives with the renderer).
+ * pbf_toggle_highlight is the highlight-word update of Simulation::OnMouseDown (src/Simulation.cpp:160-195):
+ * flag > 0 -> 0, else 1, on the device, stream ordered. */
+int pbf_pick_particle(pbf_handle h, const float origin[3], const float direction[3], float radius, int32_t *id);
+int pbf_toggle_highlight(pbf_handle h, uint32_t id);
+
 /* Aggregates the north star's long-run criterion needs (not in the reference): mean |rho_i/rho_0 - 1| at
  * the current positions (one extra density sweep) and sum 0.5 |v|^2. */
 int pbf_get_diagnostics(pbf_handle h, double *density_error, double *kinetic_energy);

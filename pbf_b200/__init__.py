@@ -79,6 +79,8 @@ def lib():
         L.pbf_enable_timing.argtypes = [C.c_void_p, C.c_int]
         L.pbf_get_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.pbf_get_solver_kernel_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.pbf_pick_particle.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_int32)]
+        L.pbf_toggle_highlight.argtypes = [C.c_void_p, C.c_uint32]
         L.pbf_get_diagnostics.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pbf_scene_dam_break.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -363,6 +365,16 @@ class SPH:
         names = ("Position prediction", "Sorting", "Neighbour cell search", "Solver", "Vorticity confinement")
         for name, ms in zip(names, self.get_timings()):
             print("%s: %g ms" % (name, ms))
+
+    def pick_particle(self, origin, direction, radius=0.5):
+        """Selection::GetParticle as a ray cast: id of the nearest particle sphere hit by the ray, or -1."""
+        out = C.c_int32()
+        _check(lib().pbf_pick_particle(self._h, (C.c_float * 3)(*origin), (C.c_float * 3)(*direction), radius, C.byref(out)))
+        return out.value
+
+    def toggle_highlight(self, particle_id):
+        """The highlight-word update of Simulation::OnMouseDown (src/Simulation.cpp:182-186)."""
+        _check(lib().pbf_toggle_highlight(self._h, particle_id))
 
     def diagnostics(self, density=True, kinetic=True):
         d, k = C.c_double(), C.c_double()

@@ -645,6 +645,32 @@ int pbf_get_solver_kernel_timings(pbf_handle s, float *lambda_ms, float *delta_p
     return PBF_OK;
 }
 
+int pbf_pick_particle(pbf_handle s, const float origin[3], const float direction[3], float radius, int32_t *id) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!origin || !direction || !id) return fail(PBF_ERR_INVALID, "pbf_pick_particle: null argument");
+    const float len = sqrtf(direction[0] * direction[0] + direction[1] * direction[1] + direction[2] * direction[2]);
+    if (!(len > 0.0f) || !(radius > 0.0f)) return fail(PBF_ERR_INVALID, "pbf_pick_particle: zero direction or radius");
+    const float d[3] = {direction[0] / len, direction[1] / len, direction[2] / len};
+    DeviceGuard guard(s->device);
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(s->diag);   // 16 bytes of scratch, stream ordered
+    PBF_CUDA(cudaMemsetAsync(best, 0xff, sizeof(*best), s->stream));
+    s->launches += launch_pick(s, origin, d, radius, best);
+    unsigned long long host = 0;
+    PBF_CUDA(cudaMemcpyAsync(&host, best, sizeof(host), cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    *id = host == ~0ull ? -1 : (int32_t)(host & 0xffffffffull);
+    return PBF_OK;
+}
+
+int pbf_toggle_highlight(pbf_handle s, uint32_t id) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (id >= s->n) return fail(PBF_ERR_INVALID, "pbf_toggle_highlight: particle id out of range");
+    DeviceGuard guard(s->device);
+    s->launches += launch_toggle_highlight(s, id);
+    PBF_CUDA(cudaGetLastError());
+    return PBF_OK;
+}
+
 int pbf_get_diagnostics(pbf_handle s, double *density_error, double *kinetic_energy) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     DeviceGuard guard(s->device);

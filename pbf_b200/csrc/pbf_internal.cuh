@@ -146,6 +146,8 @@ int launch_density_diag(pbf_sim *s);
 int launch_kinetic_diag(pbf_sim *s);
 int launch_compose_records(pbf_sim *s, float4 *out);
 int launch_neighbour_runs(pbf_sim *s, int *run_start, int *run_count);
+int launch_pick(pbf_sim *s, const float origin[3], const float dir[3], float radius, unsigned long long *best);
+int launch_toggle_highlight(pbf_sim *s, u32 id);
 // sweeps.cu
 int sweeps_init(void);                   // opt-in shared-memory sizes of the sweep kernels (once per device)
 size_t plan_desc_ints(u32 cap);

@@ -234,9 +234,50 @@ __global__ void __launch_bounds__(256) k_kinetic(u32 n, const float4 *__restrict
     }
 }
 
+// ---- picking (Selection::GetParticle, src/Selection.cpp:55-85, done as a ray cast) ---------------------------------------
+// The reference renders every particle as a sphere of radius 0.1 render units = 0.5 grid units (shaders/selection/
+// fragment.glsl, world -> render = 0.2 * pos, shaders/particles/vertex.glsl:44) into an id buffer and reads the pixel under
+// the cursor: the id of the nearest sphere on that pixel's ray, -1 for none.  Here: nearest ray/sphere hit over all
+// particles, (t, id) packed so that one 64-bit atomicMin keeps the nearest (ties: lowest id).
+__global__ void __launch_bounds__(256)
+k_pick(u32 n, const float4 *__restrict__ pos, float ox, float oy, float oz, float dx, float dy, float dz, float radius,
+       unsigned long long *best) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mine = ~0ull;
+    if (i < n) {
+        const float4 p = pos[i];
+        const float cx = p.x - ox, cy = p.y - oy, cz = p.z - oz;
+        const float b = cx * dx + cy * dy + cz * dz;                       // d is a unit vector
+        const float disc = b * b - (cx * cx + cy * cy + cz * cz) + radius * radius;
+        if (disc >= 0.0f) {
+            const float t = b - sqrtf(disc);                               // front hit
+            if (t >= 0.0f) mine = ((unsigned long long)__float_as_uint(t) << 32) | i;
+        }
+    }
+    // one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+        mine = other < mine ? other : mine;
+    }
+    if ((threadIdx.x & 31) == 0 && mine != ~0ull) atomicMin(best, mine);
+}
+
+__global__ void k_toggle_highlight(u32 *hl, u32 id) { hl[id] = hl[id] > 0u ? 0u : 1u; }   // src/Simulation.cpp:182-186
+
 inline int nblocks(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 }  // namespace
+
+int launch_pick(pbf_sim *s, const float o[3], const float d[3], float radius, unsigned long long *best) {
+    k_pick<<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->pos, o[0], o[1], o[2], d[0], d[1], d[2], radius, best);
+    return 1;
+}
+
+int launch_toggle_highlight(pbf_sim *s, u32 id) {
+    k_toggle_highlight<<<1, 1, 0, s->stream>>>(s->hl, id);
+    return 1;
+}
 
 SimParams sim_params(const pbf_sim *s) {
     SimParams P;

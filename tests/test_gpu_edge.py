@@ -203,3 +203,47 @@ def test_step_host_matches_step(built_lib):
         b.step_host(hp, hv, 1)
         assert np.array_equal(hp.numpy().view(np.uint32), apos.view(np.uint32))
         assert np.array_equal(hv.numpy().view(np.uint32), avel.view(np.uint32))
+
+
+def test_pick_and_toggle_highlight(built_lib):
+    """Ray-cast picking against a NumPy ray/sphere search; the highlight toggle of Simulation::OnMouseDown."""
+    pos, vel = oracle.dam_break(16, 16, 16)
+    sph = pbf_b200.SPH(pos.shape[0], GRID)
+    sph.upload(pos, vel)
+    rng = np.random.default_rng(21)
+
+    def reference(o, d, radius):
+        d = d / np.linalg.norm(d)
+        c = pos[:, :3].astype(np.float64) - o
+        b = c @ d
+        disc = b * b - np.einsum("ij,ij->i", c, c) + radius * radius
+        t = np.where(disc >= 0, b - np.sqrt(np.maximum(disc, 0)), np.inf)
+        t[t < 0] = np.inf
+        return int(np.argmin(t)) if np.isfinite(t.min()) else -1, t
+
+    hits = 0
+    for k in range(40):
+        o = np.array([40.0, 8.0, 10.0]) + rng.uniform(-6, 6, 3)
+        target = pos[rng.integers(0, pos.shape[0]), :3] + rng.uniform(-0.3, 0.3, 3)
+        d = target - o
+        want, t = reference(o, d, 0.5)
+        got = sph.pick_particle(o, d, 0.5)
+        if got != want:             # float32 vs float64 may swap two hits at nearly the same depth
+            assert got >= 0 and abs(t[got] - t[want]) < 1e-3
+        hits += got >= 0
+    assert hits == 40
+    assert sph.pick_particle((40.0, 200.0, 40.0), (0.0, 1.0, 0.0)) == -1          # looking away from the fluid
+    with pytest.raises(RuntimeError):
+        sph.pick_particle((0, 0, 0), (0, 0, 0))
+    sph.toggle_highlight(77)
+    _, _, hl = sph.download(highlight=True)
+    assert hl[77] == 1 and hl.sum() == 1
+    sph.Run()                                                                    # neighbours get flag 2 (highlight.glsl)
+    _, _, hl = sph.download(highlight=True)
+    assert hl[77] == 1 and (hl == 2).sum() > 10
+    sph.toggle_highlight(77)
+    sph.Run()
+    _, _, hl = sph.download(highlight=True)
+    assert not hl.any()
+    with pytest.raises(RuntimeError):
+        sph.toggle_highlight(pos.shape[0])
