@@ -91,6 +91,22 @@ int pbf_destroy(pbf_handle h);
 int pbf_set_params(pbf_handle h, const pbf_params *p);
 int pbf_get_params(pbf_handle h, pbf_params *p);
 
+/* Opt-in corrections of known defects of the reference; all off by default, so that the default
+ * behaviour -- and every parity test -- is the reference's.
+ *   density_self_term  calclambda.glsl skips j == i (foreachneighbour.glsl:9), so rho_i lacks W(0) = 0.1958, unlike the PBF
+ *                      paper; 1 adds it back (rest densities tuned for the reference, e.g. rho_0 = 1 on a 0.94 lattice,
+ *                      then need retuning).
+ *   wall_restitution   updatepos.glsl:98-100 clamps positions to the walls and update.glsl derives the velocity from the
+ *                      clamped position, which leaves a particle pressed against a wall with whatever normal velocity
+ *                      the clamp implies.  >= 0: a particle on a wall moving outwards gets v_n <- -e * v_n in update
+ *                      (0 = sticks, 1 = elastic).  < 0: off. */
+typedef struct {
+    int32_t density_self_term;
+    float wall_restitution;
+} pbf_options;
+int pbf_set_options(pbf_handle h, const pbf_options *o);
+int pbf_get_options(pbf_handle h, pbf_options *o);
+
 /* Simulation::ResetParticleBuffer's upload (src/Simulation.cpp:249-272): HOST arrays of N float4 by id.
  * vel may be NULL (zero), highlight is cleared.  pbf_download_state copies back (any pointer may be NULL). */
 int pbf_upload_state(pbf_handle h, const float *pos4, const float *vel4, uint32_t n);
@@ -204,6 +220,7 @@ typedef struct {
     int32_t ref_quirks;
     pbf_params params;
     uint64_t steps;             /* SPH::Run calls completed when the file was written */
+    pbf_options options;
 } pbf_state_info;
 int pbf_state_file_write(const char *path, const pbf_state_info *info, const float *pos4, const float *vel4,
                          const uint32_t *highlight);       /* vel4 / highlight may be NULL (zeros) */

@@ -30,10 +30,15 @@ class Params(C.Structure):
                 ("vorticity_confinement", C.c_int32), ("external_force", C.c_int32)]
 
 
+class Options(C.Structure):
+    """pbf_options (include/pbf_c.h): opt-in corrections of reference defects, all off by default."""
+    _fields_ = [("density_self_term", C.c_int32), ("wall_restitution", C.c_float)]
+
+
 class StateInfo(C.Structure):
     """pbf_state_info (include/pbf_c.h): what a state file's header holds."""
     _fields_ = [("num_particles", C.c_uint32), ("grid", C.c_int32 * 3), ("wall", C.c_float * 3),
-                ("ref_quirks", C.c_int32), ("params", Params), ("steps", C.c_uint64)]
+                ("ref_quirks", C.c_int32), ("params", Params), ("steps", C.c_uint64), ("options", Options)]
 
 
 _lib = None
@@ -63,6 +68,8 @@ def lib():
             getattr(L, name).argtypes = [C.c_void_p]
         L.pbf_step.argtypes = [C.c_void_p, C.c_int]
         L.pbf_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pbf_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.pbf_get_options.argtypes = [C.c_void_p, C.POINTER(Options)]
         L.pbf_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.pbf_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.pbf_upload_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
@@ -139,13 +146,14 @@ def sort_bits(grid):
 
 
 def write_state_file(path, pos, vel=None, highlight=None, grid=(128, 64, 128), wall=(16.0, 0.0, 16.0), ref_quirks=True,
-                     params=None, steps=0):
+                     params=None, steps=0, options=None):
     """Writes a state file from HOST arrays (no device needed); see include/pbf_c.h, "state files"."""
     pos = np.ascontiguousarray(pos, np.float32)
     vel = None if vel is None else np.ascontiguousarray(vel, np.float32)
     highlight = None if highlight is None else np.ascontiguousarray(highlight, np.uint32)
     info = StateInfo(pos.shape[0], (C.c_int32 * 3)(*grid), (C.c_float * 3)(*wall), int(ref_quirks),
-                     params if params is not None else default_params(), steps)
+                     params if params is not None else default_params(), steps,
+                     options if options is not None else Options(0, -1.0))
     _check(lib().pbf_state_file_write(os.fsencode(path), C.byref(info), _ptr(pos), _ptr(vel), _ptr(highlight)))
 
 
@@ -212,6 +220,21 @@ class SPH:
 
     def set_params(self, p):
         _check(lib().pbf_set_params(self._h, C.byref(p)))
+
+    def set_options(self, density_self_term=None, wall_restitution=None):
+        """Opt-in corrections (not in the reference): self term in the density, velocity reflection at the walls."""
+        o = Options()
+        _check(lib().pbf_get_options(self._h, C.byref(o)))
+        if density_self_term is not None:
+            o.density_self_term = int(bool(density_self_term))
+        if wall_restitution is not None:
+            o.wall_restitution = wall_restitution
+        _check(lib().pbf_set_options(self._h, C.byref(o)))
+
+    def get_options(self):
+        o = Options()
+        _check(lib().pbf_get_options(self._h, C.byref(o)))
+        return o
 
     def GetRestDensity(self): return 1.0 / self._get().one_over_rho_0
     def SetRestDensity(self, rho): self._set(one_over_rho_0=np.float32(1.0) / np.float32(rho))

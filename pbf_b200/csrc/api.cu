@@ -168,6 +168,8 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     const char *gs = getenv("PBF_GENERAL_SWEEPS");
     s->tiled_sweeps = !(gs && gs[0] == '1');
     pbf_default_params(&s->params);
+    s->options.density_self_term = 0;
+    s->options.wall_restitution = -1.0f;
 
     DeviceGuard guard(dev);
 #define ALLOC(ptr, count)                                                                                       \
@@ -258,6 +260,24 @@ int pbf_get_params(pbf_handle s, pbf_params *p) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (!p) return fail(PBF_ERR_INVALID, "pbf_get_params: null");
     *p = s->params;
+    return PBF_OK;
+}
+
+int pbf_set_options(pbf_handle s, const pbf_options *o) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!o) return fail(PBF_ERR_INVALID, "pbf_set_options: null");
+    if (o->wall_restitution > 1.0f) return fail(PBF_ERR_INVALID, "pbf_set_options: wall_restitution must be <= 1 (negative = off)");
+    if (memcmp(&s->options, o, sizeof(*o)) != 0) {
+        s->options = *o;
+        invalidate_graph(s);   // kernel arguments are baked into the captured graph
+    }
+    return PBF_OK;
+}
+
+int pbf_get_options(pbf_handle s, pbf_options *o) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!o) return fail(PBF_ERR_INVALID, "pbf_get_options: null");
+    *o = s->options;
     return PBF_OK;
 }
 

@@ -8,7 +8,7 @@
 //
 // Layout (little endian, no padding between sections):
 //   header   128 bytes  magic "PBFB200S", version, header size, N, grid, wall, ref_quirks, pbf_params, step counter,
-//                       FNV-1a-64 of the payload
+//                       FNV-1a-64 of the payload, pbf_options
 //   payload  N x float4 positions, N x float4 velocities, N x uint32 highlight flags
 // The *_file functions work on HOST arrays and need no device; pbf_save_state / pbf_load_state wrap them with the
 // handle's download / upload.
@@ -34,7 +34,10 @@ struct Header {                 // 128 bytes
     pbf_params params;          // 44 bytes, ends at offset 96
     uint64_t steps;
     uint64_t checksum;
-    uint8_t reserved[16];
+    int32_t self_term;          // pbf_options; all-zero (files written before the options existed) = everything off
+    int32_t has_restitution;
+    float restitution;
+    uint8_t reserved[4];
 };
 static_assert(sizeof(Header) == 128, "state file header is 128 bytes");
 
@@ -80,6 +83,8 @@ void to_info(const Header &hd, pbf_state_info *info) {
     info->ref_quirks = hd.ref_quirks;
     info->params = hd.params;
     info->steps = hd.steps;
+    info->options.density_self_term = hd.self_term;
+    info->options.wall_restitution = hd.has_restitution ? hd.restitution : -1.0f;
 }
 
 }  // namespace
@@ -105,6 +110,9 @@ int pbf_state_file_write(const char *path, const pbf_state_info *info, const flo
     hd.ref_quirks = info->ref_quirks;
     hd.params = info->params;
     hd.steps = info->steps;
+    hd.self_term = info->options.density_self_term;
+    hd.has_restitution = info->options.wall_restitution >= 0.0f ? 1 : 0;
+    hd.restitution = hd.has_restitution ? info->options.wall_restitution : 0.0f;
     hd.checksum = payload_sum(pos4, vel4, highlight, n);
     // write next to the target and rename: a crash never leaves a half-written file under the final name
     const std::string tmp = std::string(path) + ".part";
@@ -163,6 +171,7 @@ int pbf_save_state(pbf_handle s, const char *path) {
     for (int a = 0; a < 3; a++) { info.grid[a] = s->cfg.grid[a]; info.wall[a] = s->cfg.wall[a]; }
     info.ref_quirks = s->cfg.ref_quirks;
     info.params = s->params;
+    info.options = s->options;
     info.steps = s->steps;
     return pbf_state_file_write(path, &info, pos.data(), vel.data(), hl.data());
 }
@@ -189,6 +198,8 @@ int pbf_load_state(pbf_handle s, const char *path) {
         PBF_CUDA(cudaMemcpy(s->hl, hl.data(), (size_t)s->n * 4, cudaMemcpyHostToDevice));
     }
     r = pbf_set_params(s, &info.params);
+    if (r) return r;
+    r = pbf_set_options(s, &info.options);
     if (r) return r;
     s->steps = info.steps;
     return PBF_OK;

@@ -31,6 +31,8 @@ struct SimParams {
     float one_over_rho_0, epsilon, gravity, timestep;
     float tensile_k, tensile_scale, xsph_c, vort_eps;
     int extforce;
+    int self_term;          // pbf_options: rho_i includes W(0)
+    float restitution;      // pbf_options: < 0 off
 };
 
 // Fused halo push of the slab runtime (slab.cu): the sweep that produces a halo quantity (lambda, new position, |omega|)
@@ -56,6 +58,7 @@ struct SortPlan {
 struct pbf_sim {
     pbf_config cfg;
     pbf_params params;
+    pbf_options options;
     int device;
     int sm_count;
     cudaStream_t stream;

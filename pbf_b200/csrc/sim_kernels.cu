@@ -149,7 +149,7 @@ k_build_runs(u32 n, const u32 *__restrict__ skey, const int2 *__restrict__ cells
 template <bool VORT>
 __global__ void __launch_bounds__(256)
 k_update(u32 n, const float4 *__restrict__ A, const u32 *__restrict__ perm, float4 *__restrict__ pos,
-         float4 *__restrict__ vel, float4 *__restrict__ svel, SimParams P) {
+         float4 *__restrict__ vel, float4 *__restrict__ svel, SimParams P, GridInfo g) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = A[i];
@@ -160,6 +160,11 @@ k_update(u32 n, const float4 *__restrict__ A, const u32 *__restrict__ perm, floa
     v.y = __fdiv_rn(__fsub_rn(p.y, o.y), P.timestep);
     v.z = __fdiv_rn(__fsub_rn(p.z, o.z), P.timestep);
     v.w = 0.0f;
+    if (P.restitution >= 0.0f) {             // pbf_options::wall_restitution (not in the reference): reflect off the walls
+        if ((p.x <= g.wlo[0] && v.x < 0.0f) || (p.x >= g.whi[0] && v.x > 0.0f)) v.x *= -P.restitution;
+        if ((p.y <= g.wlo[1] && v.y < 0.0f) || (p.y >= g.whi[1] && v.y > 0.0f)) v.y *= -P.restitution;
+        if ((p.z <= g.wlo[2] && v.z < 0.0f) || (p.z >= g.whi[2] && v.z > 0.0f)) v.z *= -P.restitution;
+    }
     pos[id] = make_float4(p.x, p.y, p.z, 0.0f);
     if (VORT) svel[i] = v;
     else vel[id] = v;
@@ -290,6 +295,8 @@ SimParams sim_params(const pbf_sim *s) {
     P.xsph_c = s->params.xsph_viscosity_c;
     P.vort_eps = s->params.vorticity_epsilon;
     P.extforce = s->params.external_force;
+    P.self_term = s->options.density_self_term;
+    P.restitution = s->options.wall_restitution;
     return P;
 }
 
@@ -340,10 +347,10 @@ int launch_highlight(pbf_sim *s) {
 int launch_update(pbf_sim *s) {
     if (s->params.vorticity_confinement)
         k_update<true><<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->bufA, s->perm, s->pos, s->vel, s->svel,
-                                                                  sim_params(s));
+                                                                  sim_params(s), s->grid);
     else
         k_update<false><<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->bufA, s->perm, s->pos, s->vel, s->svel,
-                                                                   sim_params(s));
+                                                                   sim_params(s), s->grid);
     return 1;
 }
 

@@ -409,7 +409,7 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     if (live) {
         // FOR_EACH_NEIGHBOUR skips j == i (foreachneighbour.glsl:9): self only ever adds (h^2)^3 = 64 to the poly6 sum
         float rs = -(rho.x + rho.y);
-        if (tc.self_in) rs -= 64.0f;
+        if (tc.self_in != (P.self_term != 0)) rs += P.self_term ? 64.0f : -64.0f;   // pbf_options::density_self_term keeps it
         const float r = POLY6 * rs;
         const float cg = SPIKY_GRAD * P.one_over_rho_0;
         const float sx = cg * (gx.x + gx.y), sy = cg * (gy.x + gy.y), sz = cg * (gz.x + gz.y);

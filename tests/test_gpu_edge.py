@@ -247,3 +247,59 @@ def test_pick_and_toggle_highlight(built_lib):
     assert not hl.any()
     with pytest.raises(RuntimeError):
         sph.toggle_highlight(pos.shape[0])
+
+
+def test_option_density_self_term(built_lib):
+    """pbf_options::density_self_term adds W(0) back to rho_i (the reference skips j == i): lambda scales by C'/C."""
+    pos, vel = oracle.dam_break(32, 32, 32)
+    g = oracle.make_grid(*GRID)
+    sph = pbf_b200.SPH(pos.shape[0], GRID)
+    sph.upload(pos, vel)
+    P = oracle_params(sph)
+    sph.predict(); sph.sort(); sph.build_cells()
+    _, _, rec = sph.get_sorted()
+    start, end = oracle.findcells(rec, g)
+    rs, rc = oracle.neighbourcells(rec, g, start, end)
+    olam, orho = oracle.calclambda(rec, rs, rc, P)
+    sph.calc_lambda()
+    assert np.max(np.abs(sph.get_lambda() - olam)) < 1e-5 * np.max(np.abs(olam))      # default: the reference's lambda
+    sph.set_options(density_self_term=True)
+    assert sph.get_options().density_self_term == 1
+    sph.calc_lambda()
+    lam = sph.get_lambda()
+    w0 = np.float32(pbf_b200.wpoly6(0.0, 2.0))
+    c_ref = orho.astype(np.float64) * P.one_over_rho_0 - 1.0
+    c_new = (orho.astype(np.float64) + w0) * P.one_over_rho_0 - 1.0
+    ok = np.abs(c_ref) > 1e-3                                                         # lambda = -C / (S + eps): same S
+    want = olam.astype(np.float64)[ok] * c_new[ok] / c_ref[ok]
+    assert np.max(np.abs(lam[ok] - want)) < 2e-4 * np.max(np.abs(want))
+    sph.set_options(density_self_term=False)
+    sph.calc_lambda()
+    assert np.max(np.abs(sph.get_lambda() - olam)) < 1e-5 * np.max(np.abs(olam))
+
+
+def test_option_wall_restitution(built_lib):
+    """Non-interacting particles dropped onto the floor: the reference leaves them the velocity the clamp implies
+    (downwards); with wall_restitution e they leave the floor with -e times that."""
+    n = 512
+    pos = np.zeros((n, 4), np.float32)
+    k = np.arange(n)
+    pos[:, 0] = 20.0 + 3.0 * (k % 16); pos[:, 2] = 20.0 + 2.8 * (k // 16); pos[:, 1] = 0.05      # > h apart: no neighbours
+    vel = np.zeros((n, 4), np.float32)
+    vel[:, 1] = -10.0
+    out = {}
+    for e in (None, 0.0, 0.5):
+        sph = pbf_b200.SPH(n, GRID)
+        sph.SetNumSolverIterations(2)
+        if e is not None:
+            sph.set_options(wall_restitution=e)
+        sph.upload(pos, vel)
+        sph.Run()
+        out[e] = sph.download()
+    p, v = out[None]
+    assert np.all(p[:, 1] == 0.0) and np.allclose(v[:, 1], -0.05 / 0.016, rtol=1e-5)     # update.glsl: (0 - 0.05) / dt
+    assert np.all(out[0.0][0][:, 1] == 0.0) and np.all(out[0.0][1][:, 1] == 0.0)
+    assert np.allclose(out[0.5][1][:, 1], 0.5 * 0.05 / 0.016, rtol=1e-5)
+    assert np.array_equal(out[0.5][1][:, [0, 2]], v[:, [0, 2]])                          # tangential components untouched
+    with pytest.raises(RuntimeError):
+        pbf_b200.SPH(512, (16, 16, 16)).set_options(wall_restitution=1.5)

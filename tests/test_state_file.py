@@ -22,12 +22,14 @@ def test_round_trip_on_host(built_lib, tmp_path):
     p.vorticity_confinement = 1
     p.gravity = 7.5
     path = tmp_path / "a.pbfstate"
-    pbf_b200.write_state_file(path, pos, vel, hl, grid=(100, 50, 90), wall=(8.0, 0.0, 4.0), ref_quirks=False, params=p, steps=41)
+    pbf_b200.write_state_file(path, pos, vel, hl, grid=(100, 50, 90), wall=(8.0, 0.0, 4.0), ref_quirks=False, params=p, steps=41,
+                              options=pbf_b200.Options(1, 0.25))
     assert os.path.getsize(path) == 128 + pos.shape[0] * 36
     assert not os.path.exists(str(path) + ".part")
     info, rpos, rvel, rhl = pbf_b200.read_state_file(path)
     assert info.num_particles == pos.shape[0] and tuple(info.grid) == (100, 50, 90) and tuple(info.wall) == (8.0, 0.0, 4.0)
     assert info.ref_quirks == 0 and info.steps == 41
+    assert info.options.density_self_term == 1 and info.options.wall_restitution == 0.25
     assert info.params.num_solver_iterations == 3 and info.params.vorticity_confinement == 1 and info.params.gravity == 7.5
     assert np.array_equal(rpos.view(np.uint32), pos.view(np.uint32))
     assert np.array_equal(rvel.view(np.uint32), vel.view(np.uint32))
@@ -43,8 +45,9 @@ def test_missing_arrays_are_zero(built_lib, tmp_path):
     pos, _, _ = scene()
     path = tmp_path / "b.pbfstate"
     pbf_b200.write_state_file(path, pos)
-    _, rpos, rvel, rhl = pbf_b200.read_state_file(path)
+    info, rpos, rvel, rhl = pbf_b200.read_state_file(path)
     assert np.array_equal(rpos, pos) and not rvel.any() and not rhl.any()
+    assert info.options.density_self_term == 0 and info.options.wall_restitution < 0      # corrections off by default
 
 
 def test_corruption_is_detected(built_lib, tmp_path):
