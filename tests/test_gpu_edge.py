@@ -303,3 +303,56 @@ def test_option_wall_restitution(built_lib):
     assert np.array_equal(out[0.5][1][:, [0, 2]], v[:, [0, 2]])                          # tangential components untouched
     with pytest.raises(RuntimeError):
         pbf_b200.SPH(512, (16, 16, 16)).set_options(wall_restitution=1.5)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_randomized_scenes(built_lib, seed):
+    """Seeded random grids, walls, parameters and particle mixtures (a lattice blob, a uniform scatter, a few particles
+    outside the grid, a few exact duplicates): integer tables bit exact, two whole steps within tolerance."""
+    rng = np.random.default_rng(1000 + seed)
+    grid = (int(rng.integers(24, 97)), int(rng.integers(12, 49)), int(rng.integers(24, 97)))
+    wall = (float(rng.integers(0, 5)), 0.0, float(rng.integers(0, 5)))
+    quirks = bool(rng.integers(0, 2))
+    n = 512 * int(rng.integers(1, 7))
+    nb = n // 2
+    side = int(np.ceil(nb ** (1 / 3)))
+    ii = np.stack(np.meshgrid(np.arange(side), np.arange(side), np.arange(side), indexing="ij"), -1).reshape(-1, 3)[:nb]
+    lo = np.array([wall[0] + 1, 0.5, wall[2] + 1])
+    hi = np.array([grid[0] - wall[0] - 1, grid[1] - 1, grid[2] - wall[2] - 1], np.float64)
+    spacing = float(rng.uniform(0.7, 1.1))
+    blob = np.minimum(lo + spacing * ii + rng.uniform(-0.01, 0.01, (nb, 3)), hi)
+    scatter = rng.uniform(lo, hi, (n - nb, 3))
+    xyz = np.concatenate([blob, scatter])
+    out = rng.choice(n, 8, replace=False)
+    xyz[out] += rng.choice([-1.0, 1.0], (8, 3)) * np.array(grid) * (rng.random((8, 3)) < 0.4)     # some far outside
+    dup = rng.choice(n, 6, replace=False)
+    xyz[dup[:3]] = xyz[dup[3:]]                                                                    # exact duplicates
+    pos = np.zeros((n, 4), np.float32); pos[:, :3] = xyz
+    vel = np.zeros((n, 4), np.float32); vel[:, :3] = rng.normal(0, float(rng.uniform(0, 6)), (n, 3))
+    iters = int(rng.integers(1, 4))
+    vort = bool(rng.integers(0, 2))
+    g = oracle.make_grid(*grid, wall=wall, ref_quirks=int(quirks))
+    sph = pbf_b200.SPH(n, grid, wall=wall, ref_quirks=quirks)
+    sph.SetNumSolverIterations(iters)
+    sph.SetVorticityConfinementEnabled(vort)
+    sph.SetGravity(float(rng.uniform(5, 15)))
+    sph.SetTimestep(float(rng.uniform(0.008, 0.02)))
+    sph.SetCFMEpsilon(float(rng.uniform(1, 10)))
+    sph.upload(pos, vel)
+    check_tables(sph, g, pos, vel, quirks)
+    sph.SetExternalForce(bool(rng.integers(0, 2)))       # after the table check, which predicts without it
+    P = oracle_params(sph)
+    extforce = bool(sph._get().external_force)
+    dt = sph.GetTimestep()
+    sph.upload(pos, vel)
+    sim = oracle.Sim(n, g)
+    opos, ovel = pos.copy(), vel.copy()
+    for step in range(2):
+        before = opos.copy()
+        sph.Run()
+        sim.step(opos, ovel, P, iters, vorticity=vort, extforce=extforce)
+        gpos, gvel = sph.download()
+        scale = max(1.0, np.max(np.abs(opos - before)) / 0.5)
+        assert np.max(np.abs(gpos - opos)) < POS_TOL * scale, (seed, step)
+        assert np.max(np.abs(gvel - ovel)) < POS_TOL * scale / dt, (seed, step)
+        sph.upload(opos, ovel)
