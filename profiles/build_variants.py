@@ -21,7 +21,7 @@ for spec in sys.argv[1:]:
     objs = []
     for src in B.SOURCES:
         base = src.rsplit(".", 1)[0]
-        if src in ("sweeps.cu", "sim_kernels.cu"):      # the translation units that include neighbour.cuh
+        if src in ("sweeps.cu", "sim_kernels.cu", "sort.cu"):      # the translation units the experiment switches live in
             o = os.path.join(out, "%s_%s.o" % (base, name))
             cmd = [B.NVCC] + B.ARCH + B.CUFLAGS + flags + ["-I", os.path.join(B.HERE, "..", "include"), "-c",
                                                          os.path.join(B.CSRC, src), "-o", o]
