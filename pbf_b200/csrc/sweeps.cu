@@ -61,11 +61,12 @@ constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays
 __global__ void __launch_bounds__(TL)
 k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
        int *__restrict__ desc, u32 *__restrict__ runs, GridInfo g, int allow) {
-    __shared__ int sS[9], sE[9];
-    const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int NW = TL / 32;
+    __shared__ int wS[NW][9], wE[NW][9];          // per warp: first / one-past-last sorted slot its runs of row o touch
+    __shared__ int sS[9], sN[9], sBase[9];         // per tile: range start, length, (image offset of the range) - start
+    __shared__ int sMeta[4];                       // phases, records, cuts, "every range fits one image"
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 i = blockIdx.x * (u32)TL + tid;
-    if (tid < 9) { sS[tid] = INT_MAX; sE[tid] = -1; }
-    __syncthreads();
     int2 r[9];
 #pragma unroll
     for (int o = 0; o < 9; o++) r[o] = make_int2(-1, 0);
@@ -75,36 +76,56 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
         const bool has = r[o].y > 0;
         const int a = __reduce_min_sync(0xffffffffu, has ? r[o].x : INT_MAX);
         const int b = __reduce_max_sync(0xffffffffu, has ? r[o].x + r[o].y : -1);
-        if (lane == 0 && b >= 0) { atomicMin(&sS[o], a); atomicMax(&sE[o], b); }
+        if (lane == 0) { wS[warp][o] = a; wE[warp][o] = b; }
     }
     __syncthreads();
-    // Greedy phases: ranges are staged in order o = 0..8; a phase ends before the range that would overflow the image.
-    // cut = 4-bit first-range index of every phase, closed by 9 (one phase: 0x90).
-    int total = 0, fill = 0, nph = 1;
-    u32 cut = 0;
+    // The per-tile arithmetic once, not in every thread: lane o of warp 0 merges the warps' bounds of range o, lane 0
+    // lays the ranges out.  Greedy phases: ranges are staged in order o = 0..8; a phase ends before the range that would
+    // overflow the image.  cut = 4-bit first-range index of every phase, closed by 9 (one phase: 0x90).
+    if (warp == 0) {
+        if (lane < 9) {
+            int a = INT_MAX, b = -1;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { a = min(a, wS[w][lane]); b = max(b, wE[w][lane]); }
+            sS[lane] = b >= 0 ? a : 0;
+            sN[lane] = b >= 0 ? b - a : 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            int total = 0, fill = 0, nph = 1, ok = 1;
+            u32 cut = 0;
+            for (int o = 0; o < 9; o++) {
+                const int no = sN[o];
+                if (fill + no > TL_CAP) { if (nph < 7) cut |= (u32)o << (4 * nph); nph++; fill = 0; }
+                sBase[o] = fill - sS[o];
+                ok = ok && no <= TL_CAP;
+                fill += no;
+                total += no;
+            }
+            if (nph < 8) cut |= 9u << (4 * nph);
+            sMeta[0] = nph; sMeta[1] = total; sMeta[2] = (int)cut; sMeta[3] = ok;
+        }
+    }
+    __syncthreads();
+    const int nph = sMeta[0];
     bool fits = true;
-    // nine 17-bit fields {image index of the run's first record:12 | count:5} and, in bit 153, "run 4 holds the particle
-    // itself", packed into RUN_WORDS words per particle
+    // nine 17-bit fields {image index of the run's first record:12 | count:5} and, in bit 153, "one of the runs holds the
+    // particle itself", packed into RUN_WORDS words per particle
     u32 v[9];
 #pragma unroll
     for (int o = 0; o < 9; o++) {
-        const int no = sE[o] >= 0 ? sE[o] - sS[o] : 0;
-        if (fill + no > TL_CAP) { if (nph < 7) cut |= (u32)o << (4 * nph); nph++; fill = 0; }
         // run descriptor {image index:12 | count:5}; above it, for the sort below: {8 - row:4 | pair iterations:5}
-        v[o] = r[o].y > 0 ? (u32)((r[o].x - sS[o] + fill) & 0xfff) | ((u32)(r[o].y & 31) << 12) | ((u32)(8 - o) << 17) |
+        v[o] = r[o].y > 0 ? (u32)((r[o].x + sBase[o]) & 0xfff) | ((u32)(r[o].y & 31) << 12) | ((u32)(8 - o) << 17) |
                                 ((u32)(((r[o].y & 31) + 1) >> 1) << 21)
                           : 0u;
-        fits = fits && r[o].y < 32 && no <= TL_CAP;
-        fill += no;
-        total += no;
+        fits = fits && r[o].y < 32;
     }
 #ifndef PBF_PLAN_UNSORTED
-    // A warp walks run slot k of all its lanes in lock step, so it pays max_lanes(count) per slot.  In a one-image tile a
-    // run descriptor is self-contained (image index + count), so every lane may walk its nine runs in ANY order: longest
-    // first puts runs of similar length into the same slot (sum over slots of the per-slot maximum, 1M-particle dam
-    // break: step 0 42.7 -> 42.4 slots per particle, step 25 49.3 -> 44.4, step 40 55.0 -> 45.5, step 120 59.8 -> 49.5).
-    // Only the order of a particle's floating-point sums changes.  Tiles staged in phases keep the row order: there a
-    // run belongs to the phase of its range.
+    // A warp walks run slot k of all its lanes in lock step, so it pays max_lanes(iterations) per slot.  In a one-image
+    // tile a run descriptor is self-contained (image index + count), so every lane may walk its nine runs in ANY order:
+    // longest first puts runs of similar length into the same slot (DESIGN.md section 4 has the numbers: -17 % slots on
+    // a disordered scene, nothing on a regular lattice).  Only the order of a particle's floating-point sums changes.
+    // Tiles staged in phases keep the row order: there a run belongs to the phase of its range.
     if (nph == 1) {
         // sort key {pair iterations = ceil(count / 2):5 | 8 - row:4 | descriptor:17}: what a slot costs is its number of
         // iterations, and runs that cost the same keep the row order -- on a regular lattice hardly anything moves, so
@@ -124,16 +145,14 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
 #undef PBF_CSWAP
     }
 #endif
-#pragma unroll
-    for (int o = 0; o < 9; o++) v[o] &= 0x1ffffu;
     u32 w[RUN_WORDS] = {0u, 0u, 0u, 0u, 0u};
 #pragma unroll
     for (int o = 0; o < 9; o++) {
         constexpr int RB = 17;
-        w[(RB * o) >> 5] |= v[o] << ((RB * o) & 31);
-        if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= v[o] >> (32 - ((RB * o) & 31));
+        const u32 f = v[o] & 0x1ffffu;
+        w[(RB * o) >> 5] |= f << ((RB * o) & 31);
+        if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= f >> (32 - ((RB * o) & 31));
     }
-    if (nph < 8) cut |= 9u << (4 * nph);
     // Is the particle itself among its candidates (FOR_EACH_NEIGHBOUR skips it by index, foreachneighbour.glsl:9)?  Normally
     // it sits in run 4, its own row -- but a particle outside the grid is filed under its CLAMPED cell (findcells.glsl)
     // while its runs are built around the UNCLAMPED one (neighbourcells.glsl:57), so any of the nine runs may hold it.
@@ -146,10 +165,10 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
     u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
-    fits = __syncthreads_and(fits && nph <= TL_PHASES && allow);
+    fits = __syncthreads_and(fits) && sMeta[3] && nph <= TL_PHASES && allow;
     int *d = desc + (size_t)blockIdx.x * TL_DESC;
-    if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = total; d[D_CUT] = (int)cut; }
-    if (tid < 9) { d[D_S + tid] = sE[tid] >= 0 ? sS[tid] : 0; d[D_N + tid] = sE[tid] >= 0 ? sE[tid] - sS[tid] : 0; }
+    if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = sMeta[1]; d[D_CUT] = sMeta[2]; }
+    if (tid < 9) { d[D_S + tid] = sS[tid]; d[D_N + tid] = sN[tid]; }
 }
 
 // ---- tile frame of the sweeps -------------------------------------------------------------------------------------------
