@@ -2,7 +2,7 @@
  * touches the simulation path: the constructor's `sph(GetNumberOfParticles())` (src/Simulation.cpp:25-28),
  * ResetParticleBuffer (:206-273), GetNumberOfParticles (:200-204), Frame()'s `if (running) sph.Run()` (:464-465) and the
  * keys that drive SPH (S step :348-350, Space run, V vorticity :299-301, T timing :308-318, Tab reset :303-305, F external
- * force :280-282/:360-362).  Rendering, camera, GUI text and selection stay with the reference's own Simulation when
+ * force :280-282/:360-362, highlight picking :160-195 as a ray cast).  Rendering, camera and GUI text stay with the reference's own Simulation when
  * the shim SPH is dropped into its tree; this class is for headless use and the tests. */
 #ifndef PBF_SHIM_SIMULATION_H
 #define PBF_SHIM_SIMULATION_H
@@ -44,6 +44,16 @@ public:
         case KEY_SPACE: running = !running; break;
         case KEY_F: sph.SetExternalForce(false); break;
         }
+    }
+    /* Simulation::OnMouseDown with H held (src/Simulation.cpp:160-195): pick the particle under the cursor and toggle its
+     * highlight word.  The reference finds it by rendering an id buffer (Selection::GetParticle); headless, the caller
+     * passes the cursor's ray in grid units and the library casts it (pbf_pick_particle, sphere radius 0.5 grid units =
+     * the 0.1 render units the reference draws).  Returns the particle id or -1. */
+    int OnMouseDown(const float origin[3], const float direction[3]) {
+        int32_t id = -1;
+        pbf_shim::check(pbf_pick_particle(sph.GetHandle(), origin, direction, 0.5f, &id), "Simulation::OnMouseDown");
+        if (id >= 0) pbf_shim::check(pbf_toggle_highlight(sph.GetHandle(), (uint32_t)id), "Simulation::OnMouseDown");
+        return id;
     }
     SPH &GetSPH(void) { return sph; }
 

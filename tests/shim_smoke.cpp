@@ -15,6 +15,10 @@ int main(int argc, char **argv) {
         sim.OnKeyUp(Simulation::KEY_SPACE);   // running
         for (int f = 0; f < frames; f++) sim.Frame();
         sph.RunStaged();                      // one more step through RadixSort / NeighbourCellFinder shims
+        const float eye[3] = {64.0f, 10.0f, -20.0f}, dir[3] = {-0.3f, 0.0f, 1.0f};
+        const int picked = sim.OnMouseDown(eye, dir);   // highlight toggle along a ray into the first block
+        const int again = sim.OnMouseDown(eye, dir);    // the same particle again: toggled back
+        printf("SHIM pick=%d again=%d\n", picked >= 0, picked == again);
         unsigned n = sim.GetNumberOfParticles();
         std::vector<float> pos(4 * (size_t)n), vel(4 * (size_t)n);
         pbf_shim::check(pbf_download_state(sph.GetHandle(), pos.data(), vel.data(), nullptr), "download");

@@ -33,6 +33,7 @@ def test_shim_matches_python_binding(built_lib):
     line = [l for l in r.stdout.splitlines() if l.startswith("SHIM n=")][0]
     vals = dict(kv.split("=") for kv in line.split()[1:])
     assert "expected error" in r.stdout
+    assert "SHIM pick=1 again=1" in r.stdout           # Simulation::OnMouseDown: the ray finds a particle, twice the same
     p1, v1 = pbf_b200.dam_break(32, 32, 32)
     p2, v2 = pbf_b200.dam_break(32, 32, 32, origin=(95.5, 0.5, 95.5), mirror=True, id0=32768)
     sph = pbf_b200.SPH(65536)
