@@ -8,7 +8,7 @@
 // headline scene, depending on how dense that row is; ~1140 records over the nine ranges, 8.9 per particle).
 //   * k_plan (once per step, after the cell tables): per particle its nine runs (this is K7, evaluated once per step
 //     as in the reference), per tile the nine ranges [S_o, S_o + n_o) that cover them; the runs are stored relative to
-//     the tile's shared-memory image (12-bit start, 5-bit count: 20 B per particle), longest first: a warp walks run
+//     the tile's shared-memory image (11-bit start, 5-bit count: 20 B per particle), longest first: a warp walks run
 //     slot k of all its lanes in lock step and pays for the longest, so runs of similar length share a slot.
 //   * every sweep: one thread issues nine 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) that
 //     bring the tile's nine ranges into shared memory verbatim -- no per-record instructions, no LSU wavefronts for
@@ -51,7 +51,9 @@ constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B
 constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
 constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
 constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20;
-constexpr int RUN_WORDS = 5;     // packed runs of one particle
+constexpr int RUN_WORDS = 5;     // packed runs of one particle: nine 16-bit fields {image index:11 | count:5}; then
+                                 // bit 16 of word 4: the particle meets itself in one of its runs
+static_assert(PBF_TL_CAP + 4 <= 2048, "run fields hold an 11-bit image index");
 constexpr int TL_PAD = 4;        // zeroed records after the last range: a walk reads up to 3 records past its run
 constexpr size_t TL_IMG = (size_t)(TL_CAP + TL_PAD) * sizeof(float4);   // one image
 constexpr size_t TL_SMEM1 = TL_IMG;                                // PBF_TL_CTAS blocks per SM
@@ -114,9 +116,9 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
     u32 v[9];
 #pragma unroll
     for (int o = 0; o < 9; o++) {
-        // run descriptor {image index:12 | count:5}; above it, for the sort below: {8 - row:4 | pair iterations:5}
-        v[o] = r[o].y > 0 ? (u32)((r[o].x + sBase[o]) & 0xfff) | ((u32)(r[o].y & 31) << 12) | ((u32)(8 - o) << 17) |
-                                ((u32)(((r[o].y & 31) + 1) >> 1) << 21)
+        // run descriptor {image index:11 | count:5}; above it, for the sort below: {8 - row:4 | pair iterations:5}
+        const u32 iters = (u32)(((r[o].y & 31) + 1) >> 1);
+        v[o] = r[o].y > 0 ? (u32)((r[o].x + sBase[o]) & 0x7ff) | ((u32)(r[o].y & 31) << 11) | ((u32)(8 - o) << 16) | (iters << 20)
                           : 0u;
         fits = fits && r[o].y < 32;
     }
@@ -127,7 +129,7 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
     // a disordered scene, nothing on a regular lattice).  Only the order of a particle's floating-point sums changes.
     // Tiles staged in phases keep the row order: there a run belongs to the phase of its range.
     if (nph == 1) {
-        // sort key {pair iterations = ceil(count / 2):5 | 8 - row:4 | descriptor:17}: what a slot costs is its number of
+        // sort key {pair iterations = ceil(count / 2):5 | 8 - row:4 | descriptor:16}: what a slot costs is its number of
         // iterations, and runs that cost the same keep the row order -- on a regular lattice hardly anything moves, so
         // neighbouring lanes keep reading neighbouring records of the same row (no extra bank conflicts), and the order of
         // the sums does not depend on where the tile's ranges happen to lie
@@ -145,14 +147,10 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
 #undef PBF_CSWAP
     }
 #endif
-    u32 w[RUN_WORDS] = {0u, 0u, 0u, 0u, 0u};
+    u32 w[RUN_WORDS];
 #pragma unroll
-    for (int o = 0; o < 9; o++) {
-        constexpr int RB = 17;
-        const u32 f = v[o] & 0x1ffffu;
-        w[(RB * o) >> 5] |= f << ((RB * o) & 31);
-        if (((RB * o) & 31) + RB > 32) w[((RB * o) >> 5) + 1] |= f >> (32 - ((RB * o) & 31));
-    }
+    for (int k = 0; k < 4; k++) w[k] = (v[2 * k] & 0xffffu) | (v[2 * k + 1] << 16);
+    w[4] = v[8] & 0xffffu;
     // Is the particle itself among its candidates (FOR_EACH_NEIGHBOUR skips it by index, foreachneighbour.glsl:9)?  Normally
     // it sits in run 4, its own row -- but a particle outside the grid is filed under its CLAMPED cell (findcells.glsl)
     // while its runs are built around the UNCLAMPED one (neighbourcells.glsl:57), so any of the nine runs may hold it.
@@ -161,7 +159,7 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
 #pragma unroll
         for (int o = 0; o < 9; o++) self_in = self_in || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);
     }
-    if (self_in) w[4] |= 1u << 25;
+    if (self_in) w[4] |= 1u << 16;
     u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
@@ -177,7 +175,7 @@ struct TileCtx {
     u32 cut;             // first range of every phase, 4 bits each, closed by 9
     bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
     unsigned img;        // shared-window address of image 0 (image 1 follows at + TL_IMG)
-    u32 run[9];          // this thread's nine runs {image index:12 | count:5}
+    u32 run[9];          // this thread's nine runs {image index:11 | count:5}
 };
 
 __device__ __forceinline__ Pair make_pair(const float4 &a, const float4 &b) {
@@ -242,13 +240,13 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     c.cut = (u32)__ldg(dg + D_CUT);
     c.img = (unsigned)__cvta_generic_to_shared(dsm);
     const u32 *rp = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
-    u32 w[RUN_WORDS + 1];
+    u32 w[RUN_WORDS];
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) w[k] = __ldg(rp + k * TL);   // in flight while the bulk copies land
-    w[RUN_WORDS] = 0u;
 #pragma unroll
-    for (int o = 0; o < 9; o++) c.run[o] = __funnelshift_r(w[(17 * o) >> 5], w[((17 * o) >> 5) + 1], (17 * o) & 31) & 0x1ffffu;
-    c.self_in = ((w[4] >> 25) & 1u) != 0u;
+    for (int k = 0; k < 4; k++) { c.run[2 * k] = w[k] & 0xffffu; c.run[2 * k + 1] = w[k] >> 16; }
+    c.run[8] = w[4] & 0xffffu;
+    c.self_in = ((w[4] >> 16) & 1u) != 0u;
 #if PBF_PREFETCH_DIST > 0
     // One wave ahead: pull what tile blockIdx.x + DIST will need into L2 -- its descriptor (by loading it), its packed
     // runs and its nine ranges -- so that its own prologue (descriptor -> bulk copies -> data) runs on L2 hits instead of
@@ -356,8 +354,8 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
         mbar_wait(mb, 0u);                                 // no per-run phase test
 #pragma unroll
         for (int o = 0; o < 9; o++) {
-            const unsigned a = c.img + 16u * (c.run[o] & 0xfffu);
-            walk_run<NSRC>(a, a + 16u * (c.run[o] >> 12), body);
+            const unsigned a = c.img + 16u * (c.run[o] & 0x7ffu);
+            walk_run<NSRC>(a, a + 16u * (c.run[o] >> 11), body);
         }
         return;
     }
@@ -375,8 +373,8 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
             u32 r = 0;
 #pragma unroll
             for (int k = 0; k < 9; k++) r = (o == k) ? c.run[k] : r;
-            const unsigned a = c.img + 16u * (r & 0xfffu);
-            walk_run<NSRC>(a, a + 16u * (r >> 12), body);
+            const unsigned a = c.img + 16u * (r & 0x7ffu);
+            walk_run<NSRC>(a, a + 16u * (r >> 11), body);
         }
         lo = hi;
     }
@@ -447,8 +445,8 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    const u32 i = blockIdx.x * TL + tid;
     TileCtx tc = tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid);
+    const u32 i = blockIdx.x * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -496,8 +494,8 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    const u32 i = blockIdx.x * TL + tid;
     TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
+    const u32 i = blockIdx.x * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
@@ -536,8 +534,8 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    const u32 i = blockIdx.x * TL + tid;
     TileCtx tc = tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid);
+    const u32 i = blockIdx.x * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -577,8 +575,8 @@ k_vorticity_b(u32 n, const float4 *__restrict__ B, const float4 *__restrict__ vp
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    const u32 i = blockIdx.x * TL + tid;
     TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
+    const u32 i = blockIdx.x * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
