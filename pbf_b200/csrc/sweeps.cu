@@ -111,8 +111,8 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
     __syncthreads();
     const int nph = sMeta[0];
     bool fits = true;
-    // nine 17-bit fields {image index of the run's first record:12 | count:5} and, in bit 153, "one of the runs holds the
-    // particle itself", packed into RUN_WORDS words per particle
+    // nine 16-bit fields {image index of the run's first record:11 | count:5}, two per word, and in bit 16 of the last
+    // word "one of the runs holds the particle itself": RUN_WORDS words per particle
     u32 v[9];
 #pragma unroll
     for (int o = 0; o < 9; o++) {
