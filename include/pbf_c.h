@@ -5,7 +5,7 @@
  * The reference has no FFI layer: its boundary is the C++ class API of SPH (src/SPH.h:33-447),
  * RadixSort (src/RadixSort.h:33-131) and NeighbourCellFinder (src/NeighbourCellFinder.h:35-115), called
  * only by Simulation (src/Simulation.cpp).  Each entry point below cites the reference interface it
- * replaces; include/pbf/*.h holds shim classes with the reference's class names and method signatures
+ * replaces; the headers under include/pbf/ hold shim classes with the reference's class names and method signatures
  * that forward to this ABI.
  *
  * Conventions
