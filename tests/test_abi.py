@@ -49,3 +49,11 @@ def test_fails_loudly_without_gpu(built_lib):
     import pbf_b200
     with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
         pbf_b200.SPH(512)
+
+
+def test_header_is_plain_c():
+    """include/pbf_c.h is a C header (no C++ or torch types in the signatures): it must compile as C99 with warnings on."""
+    import subprocess
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "pbf_c.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
