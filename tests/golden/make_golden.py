@@ -61,15 +61,22 @@ def step(pos, vel, iters, ref_quirks=1, vorticity=True):
     start = np.full(gx * gy * gz, -1, np.int32)
     end = np.zeros(gx * gy * gz, np.int32)
     scell = cell[order]
+
+    def in_image(c):                             # imageStore outside the 3-D image is dropped (GL 4.3, 8.26)
+        return 0 <= c[0] < gx and 0 <= c[1] < gy and 0 <= c[2] < gz
+
     if ref_quirks:
         start[0] = 0
-    else:
+    elif in_image(scell[0]):
         start[skey[0]] = 0
     for i in range(1, n):
         if tuple(scell[i]) != tuple(scell[i - 1]):
-            start[skey[i]] = i
-            end[skey[i - 1]] = i
-    end[skey[n - 1]] = n                         # restatement policy: the reference leaves this one stale
+            if in_image(scell[i]):
+                start[skey[i]] = i
+            if in_image(scell[i - 1]):
+                end[skey[i - 1]] = i
+    if in_image(scell[n - 1]):
+        end[skey[n - 1]] = n                     # restatement policy: the reference leaves this one stale
     # neighbourcells.glsl:52-91
     g3 = sp.astype(np.int64)                     # ivec3(pos): truncation, not clamped
     run_start = np.full((n, 9), -1, np.int32)
@@ -132,17 +139,51 @@ def step(pos, vel, iters, ref_quirks=1, vorticity=True):
             if l > 0:
                 gv = gv / l
             vel1[sid[i], :3] = vx[i] + P["dt"] * P["eps_v"] * np.cross(gv, om[i])
-    return dict(skey=skey.astype(np.uint32), start=start, run_count=run_count, lam=lam, pos1=pos1, vel1=vel1)
+    return dict(skey=skey.astype(np.uint32), perm=sid.astype(np.uint32), start=start, run_count=run_count, lam=lam,
+                pos1=pos1, vel1=vel1)
+
+
+def edge_scene(seed=777, n=512):
+    """A small lattice block, a sparse scatter, particles outside the grid on all six sides, one that lands on y = gy
+    exactly, one on x = gx exactly, and a pair of exact duplicates (all in the reference's default grid)."""
+    rng = np.random.default_rng(seed)
+    side = 6
+    ii = np.stack(np.meshgrid(np.arange(side), np.arange(side), np.arange(side), indexing="ij"), -1).reshape(-1, 3)
+    block = 50.0 + 0.94 * ii + rng.uniform(-0.005, 0.005, (side ** 3, 3))
+    m = n - side ** 3
+    g = np.array(GRID, np.float64)
+    rest = rng.uniform([17, 1, 17], [g[0] - 17, g[1] - 1, g[2] - 17], (m, 3))
+    for k in range(48):                          # eight per face
+        a = k % 3
+        rest[k, a] = -rng.uniform(0.1, 3.0) if (k // 3) % 2 == 0 else g[a] + rng.uniform(0.1, 3.0)
+    xyz = np.concatenate([block, rest])
+    pos = np.zeros((n, 4), np.float32); pos[:, :3] = xyz
+    vel = np.zeros((n, 4), np.float32); vel[:, :3] = rng.normal(0, 2.0, (n, 3))
+    vel[side ** 3: side ** 3 + 48, :3] = rng.normal(0, 20.0, (48, 3))
+    a = side ** 3 + 48
+    pos[a] = (60.0, GRID[1], 60.0, 0.0); vel[a] = (0.0, P["gravity"] * P["dt"], 0.0, 0.0)       # p*.y = gy exactly
+    pos[a + 1] = (GRID[0], 20.0, 60.0, 0.0); vel[a + 1] = (0.0, 0.0, 0.0, 0.0)                   # p*.x = gx exactly
+    pos[a + 2] = pos[3]; vel[a + 2] = vel[3]                                                       # exact duplicate
+    return pos, vel
 
 
 def main():
     import pbf_b200
     n3, seed, iters = (8, 8, 8), 4242, 3
-    pos, vel = pbf_b200.dam_break(*n3, seed=seed)
-    out = step(pos, vel, iters)
-    np.savez_compressed(os.path.join(HERE, "c1_small.npz"), n3=np.array(n3), grid=np.array(GRID), seed=seed, iters=iters,
-                        ref_quirks=1, pos0=pos, **out)
-    print("wrote c1_small.npz:", {k: v.shape for k, v in out.items()})
+    if "--edge" not in sys.argv:
+        pos, vel = pbf_b200.dam_break(*n3, seed=seed)
+        out = step(pos, vel, iters)
+        out.pop("perm")                          # c1_small.npz predates the permutation entry; keep the file as committed
+        np.savez_compressed(os.path.join(HERE, "c1_small.npz"), n3=np.array(n3), grid=np.array(GRID), seed=seed, iters=iters,
+                            ref_quirks=1, pos0=pos, **out)
+        print("wrote c1_small.npz:", {k: v.shape for k, v in out.items()})
+    # edge cases: out-of-grid particles, the ceiling and x = gx planes, duplicates -- in both quirk modes
+    pos, vel = edge_scene()
+    for quirks in (1, 0):
+        out = step(pos, vel, 2, ref_quirks=quirks)
+        name = "edge_small_q%d.npz" % quirks
+        np.savez_compressed(os.path.join(HERE, name), grid=np.array(GRID), iters=2, ref_quirks=quirks, pos0=pos, vel0=vel, **out)
+        print("wrote %s:" % name, {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -328,3 +328,26 @@ def test_virtual_slabs_ballistic_splash(built_lib):
     owners = [s.stats()["n_local"] for s in grp.ranks]
     assert sum(owners) == pos.shape[0]
     grp.close()
+
+
+@pytest.mark.parametrize("quirks", [1, 0])
+def test_golden_edge_vectors_cuda(built_lib, quirks):
+    """CUDA path against the edge-case golden files of the independent NumPy restatement: particles outside the grid on
+    every side, on the y = gy and x = gx planes, exact duplicates (tests/golden/make_golden.py --edge)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "edge_small_q%d.npz" % quirks))
+    pos, vel = G["pos0"].copy(), G["vel0"].copy()
+    sph = pbf_b200.SPH(pos.shape[0], tuple(G["grid"].tolist()), ref_quirks=bool(quirks))
+    sph.SetNumSolverIterations(int(G["iters"]))
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    sph.Run()
+    _, perm, _ = sph.get_sorted(records=False)
+    assert np.array_equal(perm, G["perm"])
+    start, _ = sph.get_cell_ranges()
+    assert np.array_equal(start, G["start"])
+    _, rc = sph.get_neighbour_runs()
+    assert np.array_equal(rc, G["run_count"])
+    gpos, gvel = sph.download()
+    assert np.max(np.abs(gpos - G["pos1"])) < 1e-4
+    assert np.max(np.abs(gvel - G["vel1"])) < 1e-4 / 0.016

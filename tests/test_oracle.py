@@ -221,3 +221,22 @@ def test_edge_scenes_on_the_oracle(scene):
         sim.step(p, v, P, 3, vorticity=True)
     assert np.isfinite(p).all() and np.isfinite(v).all()
     assert p[:, 0].min() >= 16 and p[:, 0].max() <= 112 and p[:, 1].min() >= 0 and p[:, 1].max() <= 64
+
+
+@pytest.mark.parametrize("quirks", [1, 0])
+def test_golden_edge_vectors(quirks):
+    """C oracle against the independent NumPy restatement (tests/golden/make_golden.py --edge) on the edge cases: particles
+    outside the grid on every side, on the y = gy and x = gx planes (no cell), exact duplicates -- in both quirk modes."""
+    G = np.load(os.path.join(HERE, "golden", "edge_small_q%d.npz" % quirks))
+    g = oracle.make_grid(*G["grid"].tolist(), ref_quirks=quirks)
+    P = oracle.default_params()
+    pos, vel = G["pos0"].copy(), G["vel0"].copy()
+    sim = oracle.Sim(pos.shape[0], g)
+    sim.step(pos, vel, P, int(G["iters"]), vorticity=True)
+    assert np.array_equal(sim.sorted[:, 3].view(np.int32).astype(np.uint32), G["perm"])
+    assert np.array_equal(sim.start, G["start"])
+    assert np.array_equal(sim.run_count, G["run_count"])
+    assert np.allclose(sim.lam, G["lam"], rtol=2e-4, atol=2e-6)
+    # escaped particles are hauled back by up to ~3 cells in this step: scale the one-step tolerance with the motion
+    assert np.max(np.abs(pos - G["pos1"])) < 1e-4
+    assert np.max(np.abs(vel - G["vel1"])) < 1e-4 / 0.016
