@@ -43,11 +43,14 @@ def grad_wspiky(d):                             # calclambda.glsl:57-64, d: (m,3
     return g.astype(np.float32)
 
 
-def step(pos, vel, iters, ref_quirks=1, vorticity=True):
+def step(pos, vel, iters, ref_quirks=1, vorticity=True, extforce=False, highlight=None):
     n = pos.shape[0]
     gx, gy, gz = GRID
     # predictpos.glsl:18-38
     v = vel[:, :3].copy()
+    if extforce:                                 # :27-28, applied before gravity, to particles with z > GRID_SIZE.z / 2
+        far = pos[:, 2] > F(gz) / F(2)           # GRID_SIZE is injected as a vec3 (src/SPH.cpp:29): float division
+        v[far, 2] += F(2) * P["gravity"] * F(-1) * P["dt"]
     v[:, 1] += P["gravity"] * F(-1) * P["dt"]
     p = (pos[:, :3] + P["dt"] * v).astype(np.float32)
     # counting.glsl:53-57
@@ -99,6 +102,12 @@ def step(pos, vel, iters, ref_quirks=1, vorticity=True):
         return idx[idx != i].astype(np.int64)
 
     nb = [neighbours(i) for i in range(n)]
+    hl = None
+    if highlight is not None:                    # clearhighlight.glsl (flag &= 1), then highlight.glsl:17-30 (src/SPH.cpp:288-296)
+        hl = highlight & np.uint32(1)
+        for i in range(n):
+            if hl[sid[i]] & 1:
+                hl[sid[nb[i]]] |= np.uint32(2)
     lam = np.zeros(n, np.float32)
     for _ in range(iters):
         for i in range(n):                       # calclambda.glsl:66-103
@@ -139,8 +148,11 @@ def step(pos, vel, iters, ref_quirks=1, vorticity=True):
             if l > 0:
                 gv = gv / l
             vel1[sid[i], :3] = vx[i] + P["dt"] * P["eps_v"] * np.cross(gv, om[i])
-    return dict(skey=skey.astype(np.uint32), perm=sid.astype(np.uint32), start=start, run_count=run_count, lam=lam,
-                pos1=pos1, vel1=vel1)
+    out = dict(skey=skey.astype(np.uint32), perm=sid.astype(np.uint32), start=start, run_count=run_count, lam=lam,
+               pos1=pos1, vel1=vel1)
+    if hl is not None:
+        out["highlight1"] = hl
+    return out
 
 
 def edge_scene(seed=777, n=512):
@@ -184,6 +196,16 @@ def main():
         name = "edge_small_q%d.npz" % quirks
         np.savez_compressed(os.path.join(HERE, name), grid=np.array(GRID), iters=2, ref_quirks=quirks, pos0=pos, vel0=vel, **out)
         print("wrote %s:" % name, {k: v.shape for k, v in out.items()})
+    # external force (F key, src/Simulation.cpp:280-282) and highlight marks (H + click, :160-195) on a lattice block
+    pos, vel = pbf_b200.dam_break(8, 8, 8, origin=(60.5, 0.5, 60.5), seed=99)      # straddles z = 64
+    hl = np.zeros(pos.shape[0], np.uint32)
+    hl[[3, 100, 400]] = 1
+    hl[[7, 8]] = 2                               # stale neighbour marks from the step before
+    hl[200] = 3
+    out = step(pos, vel, 2, extforce=True, highlight=hl)
+    np.savez_compressed(os.path.join(HERE, "force_highlight_small.npz"), grid=np.array(GRID), iters=2, ref_quirks=1, pos0=pos,
+                        vel0=vel, highlight0=hl, **out)
+    print("wrote force_highlight_small.npz:", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -351,3 +351,27 @@ def test_golden_edge_vectors_cuda(built_lib, quirks):
     gpos, gvel = sph.download()
     assert np.max(np.abs(gpos - G["pos1"])) < 1e-4
     assert np.max(np.abs(gvel - G["vel1"])) < 1e-4 / 0.016
+
+
+def test_golden_force_and_highlight_cuda(built_lib):
+    """CUDA path against the NumPy restatement's golden with the external force on and highlight marks set."""
+    import os
+    import torch
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "force_highlight_small.npz"))
+    pos, vel = G["pos0"].copy(), G["vel0"].copy()
+    sph = pbf_b200.SPH(pos.shape[0], tuple(G["grid"].tolist()), ref_quirks=bool(G["ref_quirks"]))
+    sph.SetNumSolverIterations(int(G["iters"]))
+    sph.SetVorticityConfinementEnabled(True)
+    sph.SetExternalForce(True)
+    sph.upload(pos, vel)                                   # clears the highlight buffer (src/Simulation.cpp:271-272)
+    t = torch.from_numpy(G["highlight0"].view(np.int32).copy()).cuda()
+    torch.cuda.synchronize()
+    sph.bind_device_buffers(highlight=t)
+    sph.Run()
+    sph.sync()
+    _, perm, _ = sph.get_sorted(records=False)
+    assert np.array_equal(perm, G["perm"])
+    assert np.array_equal(t.cpu().numpy().view(np.uint32), G["highlight1"])
+    gpos, gvel = sph.download()
+    assert np.max(np.abs(gpos - G["pos1"])) < 2e-5
+    assert np.max(np.abs(gvel - G["vel1"])) < 2e-3

@@ -240,3 +240,22 @@ def test_golden_edge_vectors(quirks):
     # escaped particles are hauled back by up to ~3 cells in this step: scale the one-step tolerance with the motion
     assert np.max(np.abs(pos - G["pos1"])) < 1e-4
     assert np.max(np.abs(vel - G["vel1"])) < 1e-4 / 0.016
+
+
+def test_golden_force_and_highlight():
+    """C oracle against the NumPy restatement with the external force on (predictpos.glsl:27-28) and highlight marks
+    (clearhighlight.glsl, highlight.glsl)."""
+    G = np.load(os.path.join(HERE, "golden", "force_highlight_small.npz"))
+    g = oracle.make_grid(*G["grid"].tolist(), ref_quirks=int(G["ref_quirks"]))
+    P = oracle.default_params()
+    pos, vel, hl = G["pos0"].copy(), G["vel0"].copy(), G["highlight0"].copy()
+    assert (pos[:, 2] > 64).any() and (pos[:, 2] < 64).any()          # the block straddles the force's plane
+    sim = oracle.Sim(pos.shape[0], g)
+    sim.step(pos, vel, P, int(G["iters"]), vorticity=True, extforce=True, highlight=hl)
+    assert np.array_equal(sim.sorted[:, 3].view(np.int32).astype(np.uint32), G["perm"])
+    assert np.array_equal(sim.start, G["start"])
+    assert np.array_equal(sim.run_count, G["run_count"])
+    assert np.array_equal(hl, G["highlight1"])
+    assert (hl == 2).sum() > 20 and hl[200] == 1 and hl[3] in (1, 3)
+    assert np.max(np.abs(pos - G["pos1"])) < 2e-5
+    assert np.max(np.abs(vel - G["vel1"])) < 2e-3
