@@ -31,3 +31,15 @@ def test_reference_arm_json_line(built_lib):
 
 def test_reference_arm_other_ranks_are_silent(built_lib):
     assert run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_own_arm_refuses_to_run_without_a_gpu(built_lib):
+    """No CPU fallback: without a CUDA device bench.py's own arm stops with a message instead of measuring something else."""
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
