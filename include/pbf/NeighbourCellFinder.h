@@ -10,7 +10,7 @@
 
 #include <vector>
 
-#include "common.h"
+#include "shim_common.h"
 
 class NeighbourCellFinder {
 public:

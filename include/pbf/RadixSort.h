@@ -8,7 +8,7 @@
 
 #include <vector>
 
-#include "common.h"
+#include "shim_common.h"
 
 class RadixSort {
 public:

@@ -14,7 +14,7 @@
 
 #include "NeighbourCellFinder.h"
 #include "RadixSort.h"
-#include "common.h"
+#include "shim_common.h"
 
 class SPH {
 public:

@@ -1,4 +1,4 @@
-/* common.h -- what the shim classes need from the reference's src/common.h (GL types, glm::ivec3).
+/* shim_common.h -- what the shim classes need from the reference's src/common.h (GL types, glm::ivec3).
  * Inside the reference tree define PBF_WITH_GL: the reference's own common.h (glcorew + glm) is used and the SPH shim
  * shares its particle buffers with the renderer through CUDA-GL interop.  Standalone (headless, as in this repo's
  * tests) minimal stand-ins are defined instead. */
@@ -11,7 +11,14 @@
 #include "../pbf_c.h"
 
 #ifdef PBF_WITH_GL
-#include "common.h" /* the reference's src/common.h: glcorew.h, glm, <vector>, <iostream> ... */
+/* The reference's src/common.h (glcorew.h, glm, <vector>, <iostream> ...).  This file must not be called common.h itself:
+ * a quote include searches the including file's directory first and would find the shim again.  Inside the reference
+ * tree every translation unit that uses SPH has already included src/common.h through src/Simulation.h, whose include
+ * guard makes this a no-op; otherwise put the reference's src/ on the include path or point PBF_REF_COMMON_H at it. */
+#ifndef PBF_REF_COMMON_H
+#define PBF_REF_COMMON_H "common.h"
+#endif
+#include PBF_REF_COMMON_H
 #else
 typedef unsigned int GLuint;
 namespace glm {

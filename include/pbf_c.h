@@ -82,6 +82,8 @@ float pbf_wpoly6(float r, float h);
 void pbf_default_params(pbf_params *p);
 /* RadixSort's numbits/pass count (src/RadixSort.cpp:24-30, :44, :127): number of low key bits sorted */
 int pbf_sort_bits(const int32_t grid[3]);
+/* onesweep passes libpbf_b200 runs for that many key bits (the reference runs pbf_sort_bits / 2 two-bit passes) */
+int pbf_sort_passes(const int32_t grid[3]);
 
 /* SPH::SPH / SPH::~SPH (src/SPH.cpp:24-156) */
 int pbf_create(const pbf_config *cfg, pbf_handle *out);
@@ -127,6 +129,17 @@ uint32_t pbf_num_particles(pbf_handle h);
  * pbf_destroy) returns to the handle's own buffers. */
 int pbf_register_gl_buffers(pbf_handle h, unsigned int pos, unsigned int vel, unsigned int highlight);
 int pbf_unregister_gl_buffers(pbf_handle h);
+/* The same ownership protocol for any other owner of the three by-id buffers (a Vulkan / EGL renderer importing external
+ * memory, a host application with its own allocator): instead of GL names the caller registers two callbacks.  Every entry
+ * point that reads or writes particle state calls map(user, stream, &pos4, &vel4, &highlight) first -- `stream` is the
+ * handle's cudaStream_t; the callback returns 0 and three DEVICE pointers (N x float4, N x float4, N x uint32, 16-byte
+ * aligned) that stay valid until unmap -- enqueues its work on that stream, and calls unmap(user, stream) on every way
+ * out.  Nothing is touched outside a map/unmap bracket; pbf_device_buffers and pbf_step_host are refused while
+ * registered.  pbf_register_gl_buffers is this protocol with cudaGraphicsMapResources / cudaGraphicsUnmapResources. */
+typedef int (*pbf_map_fn)(void *user, void *stream, float **pos4, float **vel4, uint32_t **highlight);
+typedef int (*pbf_unmap_fn)(void *user, void *stream);
+int pbf_register_external_buffers(pbf_handle h, pbf_map_fn map, pbf_unmap_fn unmap, void *user);
+int pbf_unregister_external_buffers(pbf_handle h);
 
 /* SPH::Run (src/SPH.cpp:246-334), nsteps times. */
 int pbf_step(pbf_handle h, int nsteps);
@@ -253,8 +266,15 @@ int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_g
 /* local particles of the slab (HOST arrays by slot) with their global ids; download returns the current owners */
 int pbf_slab_upload(pbf_handle h, const float *pos4, const float *vel4, const uint32_t *gid, uint32_t n);
 int pbf_slab_download(pbf_handle h, float *pos4, float *vel4, uint32_t *gid, uint32_t *n);
+/* highlight words of the local particles in the same slot order (selection bits travel with migrating particles and with
+ * the ghosts, so highlight.glsl's marks cross slab planes); pbf_toggle_highlight on a slab handle takes a SLOT */
+int pbf_slab_download_highlight(pbf_handle h, uint32_t *highlight);
 /* with a virtual group, stepping any member steps the whole group */
 int pbf_slab_step(pbf_handle h, int nsteps);
+/* One rank's end-to-end call: n_in local particles from HOST arrays (pinned for speed) in, nsteps, the particles the rank
+ * owns afterwards back out into the same arrays (*n_out of them; the arrays hold `capacity`) */
+int pbf_slab_step_host(pbf_handle h, float *pos4, float *vel4, uint32_t *gid, uint32_t n_in, uint32_t capacity,
+                       uint32_t *n_out, int nsteps);
 /* out: local particles, ghosts from z-, ghosts from z+, boundary sent to z-, to z+, migrated away (total),
  * exchanges (total), bytes sent (total) */
 int pbf_slab_stats(pbf_handle h, uint64_t out[8]);

@@ -41,6 +41,10 @@ class StateInfo(C.Structure):
                 ("ref_quirks", C.c_int32), ("params", Params), ("steps", C.c_uint64), ("options", Options)]
 
 
+# pbf_map_fn / pbf_unmap_fn (include/pbf_c.h): the owner of the by-id buffers hands them out between map and unmap
+MAP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))
+UNMAP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p)
+
 _lib = None
 
 
@@ -92,8 +96,11 @@ def lib():
         L.pbf_scene_dam_break.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.pbf_sort_bits.argtypes = [C.POINTER(C.c_int32)]
+        L.pbf_sort_passes.argtypes = [C.POINTER(C.c_int32)]
         L.pbf_register_gl_buffers.argtypes = [C.c_void_p, C.c_uint, C.c_uint, C.c_uint]
         L.pbf_unregister_gl_buffers.argtypes = [C.c_void_p]
+        L.pbf_register_external_buffers.argtypes = [C.c_void_p, MAP_FN, UNMAP_FN, C.c_void_p]
+        L.pbf_unregister_external_buffers.argtypes = [C.c_void_p]
         L.pbf_state_file_write.argtypes = [C.c_char_p, C.POINTER(StateInfo), C.c_void_p, C.c_void_p, C.c_void_p]
         L.pbf_state_file_info.argtypes = [C.c_char_p, C.POINTER(StateInfo)]
         L.pbf_state_file_read.argtypes = [C.c_char_p, C.POINTER(StateInfo), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
@@ -108,7 +115,10 @@ def lib():
         L.pbf_slab_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pbf_slab_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.pbf_slab_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.pbf_slab_download_highlight.argtypes = [C.c_void_p, C.c_void_p]
         L.pbf_slab_step.argtypes = [C.c_void_p, C.c_int]
+        L.pbf_slab_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                                         C.POINTER(C.c_uint32), C.c_int]
         L.pbf_slab_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
@@ -143,6 +153,11 @@ def wpoly6(r, h):
 
 def sort_bits(grid):
     return lib().pbf_sort_bits((C.c_int32 * 3)(*grid))
+
+
+def sort_passes(grid):
+    """Onesweep passes the library needs for this grid's key bits (the reference needs sort_bits / 2 two-bit passes)."""
+    return lib().pbf_sort_passes((C.c_int32 * 3)(*grid))
 
 
 def write_state_file(path, pos, vel=None, highlight=None, grid=(128, 64, 128), wall=(16.0, 0.0, 16.0), ref_quirks=True,
@@ -317,6 +332,30 @@ class SPH:
         _check(lib().pbf_register_gl_buffers(self._h, pos, vel, highlight))
 
     def unregister_gl_buffers(self): _check(lib().pbf_unregister_gl_buffers(self._h))
+
+    def register_external_buffers(self, map_fn, unmap_fn):
+        """The map/unmap protocol of the GL interop for any other owner of the by-id buffers: map_fn(stream) returns the
+        three device addresses (pos, vel, highlight), valid until unmap_fn(stream)."""
+        def _map(user, stream, p, v, h):
+            try:
+                a, b, c = map_fn(stream)
+                p[0], v[0], h[0] = a, b, c
+                return 0
+            except Exception:
+                return 1
+
+        def _unmap(user, stream):
+            try:
+                unmap_fn(stream)
+                return 0
+            except Exception:
+                return 1
+        self._ext_cb = (MAP_FN(_map), UNMAP_FN(_unmap))      # keep the thunks alive
+        _check(lib().pbf_register_external_buffers(self._h, self._ext_cb[0], self._ext_cb[1], None))
+
+    def unregister_external_buffers(self):
+        _check(lib().pbf_unregister_external_buffers(self._h))
+        self._ext_cb = None
 
     def sync(self): _check(lib().pbf_sync(self._h))
     def predict(self): _check(lib().pbf_predict(self._h))

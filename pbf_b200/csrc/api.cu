@@ -117,6 +117,8 @@ int pbf_sort_bits(const int32_t grid[3]) {   // src/RadixSort.cpp:44, :127
     return 2 * ((numbits + 1) >> 1);
 }
 
+int pbf_sort_passes(const int32_t grid[3]) { return make_sort_plan(pbf_sort_bits(grid)).passes; }
+
 int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     if (!cfg || !out) return fail(PBF_ERR_INVALID, "pbf_create: null argument");
     *out = nullptr;
@@ -188,7 +190,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     ALLOC(s->ktmp[0], cap); ALLOC(s->ktmp[1], cap); ALLOC(s->vtmp[0], cap); ALLOC(s->vtmp[1], cap);
     ALLOC(s->skey, cap); ALLOC(s->perm, cap); ALLOC(s->home, cap);
     s->max_tiles = sort_max_tiles(cap);
-    ALLOC(s->hist, 4 * PBF_RADIX); ALLOC(s->gbase, 4 * PBF_RADIX); ALLOC(s->tile_counter, 4);
+    ALLOC(s->hist, 8 * PBF_RADIX); ALLOC(s->gbase, 8 * PBF_RADIX);   // second halves: pbf_sort_pairs ALLOC(s->tile_counter, 4);
     ALLOC(s->status, (size_t)4 * s->max_tiles * PBF_RADIX);
     ALLOC(s->cells, s->ncell); ALLOC(s->runs3, s->ncell);
     ALLOC(s->bufA, cap); ALLOC(s->bufB, cap); ALLOC(s->svel, cap); ALLOC(s->vprime, cap); ALLOC(s->omega, cap);
@@ -203,7 +205,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     cudaMemsetAsync(s->pos_own, 0, (size_t)cap * 16, s->stream);
     cudaMemsetAsync(s->vel_own, 0, (size_t)cap * 16, s->stream);
     cudaMemsetAsync(s->hl_own, 0, (size_t)cap * 4, s->stream);
-    cudaMemsetAsync(s->hist, 0, 4 * PBF_RADIX * 4, s->stream);
+    cudaMemsetAsync(s->hist, 0, 8 * PBF_RADIX * 4, s->stream);
     cudaMemsetAsync(s->tile_counter, 0, 16, s->stream);
     cudaMemsetAsync(s->flags, 0, 16, s->stream);
     for (float4 *b : {s->pred, s->bufA, s->bufB, s->svel, s->vprime, s->omega})   // pair loads may touch one slot of padding
@@ -227,7 +229,7 @@ int pbf_destroy(pbf_handle s) {
     if (shared_stream) { cudaDeviceSynchronize(); s->stream = nullptr; }
     if (s->stream) cudaStreamSynchronize(s->stream);
     slab_free(s);
-    if (s->gl_registered)
+    if (s->gl_registered && !s->ext_map)
         for (int i = 0; i < 3; i++) cudaGraphicsUnregisterResource(s->gl_res[i]);
     invalidate_graph(s);
     void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
@@ -288,6 +290,8 @@ int pbf_upload_state(pbf_handle s, const float *pos4, const float *vel4, uint32_
     if (!pos4) return fail(PBF_ERR_INVALID, "pbf_upload_state: null positions");
     if (n != s->n) return fail(PBF_ERR_INVALID, "pbf_upload_state: n differs from the handle's particle count");
     DeviceGuard guard(s->device);
+    GlScope gl(s);
+    if (gl.rc) return gl.rc;
     PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
     if (vel4) PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, (size_t)n * 16, cudaMemcpyHostToDevice, s->stream));
     else PBF_CUDA(cudaMemsetAsync(s->vel, 0, (size_t)n * 16, s->stream));
@@ -300,6 +304,8 @@ int pbf_upload_state(pbf_handle s, const float *pos4, const float *vel4, uint32_
 int pbf_download_state(pbf_handle s, float *pos4, float *vel4, uint32_t *highlight) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     DeviceGuard guard(s->device);
+    GlScope gl(s);
+    if (gl.rc) return gl.rc;
     if (pos4) PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
     if (vel4) PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, (size_t)s->n * 16, cudaMemcpyDeviceToHost, s->stream));
     if (highlight) PBF_CUDA(cudaMemcpyAsync(highlight, s->hl, (size_t)s->n * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -309,6 +315,8 @@ int pbf_download_state(pbf_handle s, float *pos4, float *vel4, uint32_t *highlig
 
 int pbf_device_buffers(pbf_handle s, float **pos4, float **vel4, uint32_t **highlight) {
     if (check_handle(s)) return PBF_ERR_INVALID;
+    if (s->gl_registered)   // a mapped address is only valid between map and unmap: the renderer reaches the data through GL
+        return fail(PBF_ERR_STATE, "pbf_device_buffers: the state lives in registered (GL / external) buffers, whose addresses are only valid while mapped");
     if (pos4) *pos4 = (float *)s->pos;
     if (vel4) *vel4 = (float *)s->vel;
     if (highlight) *highlight = s->hl;
@@ -340,6 +348,18 @@ extern "C" cudaError_t cudaGraphicsGLRegisterBuffer(struct cudaGraphicsResource 
 namespace {
 
 int gl_map(pbf_sim *s) {
+    if (s->ext_map) {   // caller-owned buffers behind callbacks (pbf_register_external_buffers)
+        float *p = nullptr, *v = nullptr;
+        uint32_t *h = nullptr;
+        const int rc = s->ext_map(s->ext_user, (void *)s->stream, &p, &v, &h);
+        if (rc != 0 || !p || !v || !h) {
+            if (rc == 0) s->ext_unmap(s->ext_user, (void *)s->stream);
+            return fail(PBF_ERR_STATE, "external buffer map callback failed (code " + std::to_string(rc) + ")");
+        }
+        const int br = pbf_bind_device_buffers(s, p, v, h);
+        if (br) s->ext_unmap(s->ext_user, (void *)s->stream);
+        return br;
+    }
     cudaError_t e = cudaGraphicsMapResources(3, s->gl_res, s->stream);
     if (e != cudaSuccess) return fail(PBF_ERR_CUDA, std::string("cudaGraphicsMapResources: ") + cudaGetErrorString(e));
     void *ptr[3] = {nullptr, nullptr, nullptr};
@@ -359,9 +379,23 @@ int gl_map(pbf_sim *s) {
 
 }  // namespace
 
+GlScope::GlScope(pbf_sim *sim) : s(sim), rc(PBF_OK), owner(false) {
+    if (!s || !s->gl_registered || s->gl_mapped) return;
+    rc = gl_map(s);
+    if (rc == PBF_OK) { s->gl_mapped = true; owner = true; }
+}
+
+GlScope::~GlScope() {
+    if (!owner) return;
+    if (s->ext_map) s->ext_unmap(s->ext_user, (void *)s->stream);
+    else cudaGraphicsUnmapResources(3, s->gl_res, s->stream);
+    s->gl_mapped = false;
+}
+
 extern "C" int pbf_register_gl_buffers(pbf_handle s, unsigned int pos, unsigned int vel, unsigned int highlight) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (s->gl_registered) return fail(PBF_ERR_STATE, "pbf_register_gl_buffers: buffers already registered");
+    if (s->slab) return fail(PBF_ERR_STATE, "pbf_register_gl_buffers: not available on slab handles");
     DeviceGuard guard(s->device);
     const unsigned int names[3] = {pos, vel, highlight};
     for (int i = 0; i < 3; i++) {
@@ -382,10 +416,24 @@ extern "C" int pbf_unregister_gl_buffers(pbf_handle s) {
     if (!s->gl_registered) return PBF_OK;
     DeviceGuard guard(s->device);
     cudaStreamSynchronize(s->stream);
-    for (int i = 0; i < 3; i++) cudaGraphicsUnregisterResource(s->gl_res[i]);
+    if (!s->ext_map)
+        for (int i = 0; i < 3; i++) cudaGraphicsUnregisterResource(s->gl_res[i]);
+    s->ext_map = nullptr; s->ext_unmap = nullptr; s->ext_user = nullptr;
     s->gl_registered = false;
     return pbf_bind_device_buffers(s, nullptr, nullptr, nullptr);
 }
+
+extern "C" int pbf_register_external_buffers(pbf_handle s, pbf_map_fn map, pbf_unmap_fn unmap, void *user) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (!map || !unmap) return fail(PBF_ERR_INVALID, "pbf_register_external_buffers: null callback");
+    if (s->gl_registered) return fail(PBF_ERR_STATE, "pbf_register_external_buffers: buffers already registered");
+    if (s->slab) return fail(PBF_ERR_STATE, "pbf_register_external_buffers: not available on slab handles");
+    s->ext_map = map; s->ext_unmap = unmap; s->ext_user = user;
+    s->gl_registered = true;
+    return PBF_OK;
+}
+
+extern "C" int pbf_unregister_external_buffers(pbf_handle s) { return pbf_unregister_gl_buffers(s); }
 
 extern "C" {
 
@@ -393,13 +441,9 @@ int pbf_step(pbf_handle s, int nsteps) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (nsteps < 0) return fail(PBF_ERR_INVALID, "pbf_step: negative step count");
     DeviceGuard guard(s->device);
-    if (s->gl_registered) {
-        if (int r = gl_map(s)) return r;
-    }
-    struct Unmap {   // GL gets its buffers back on every way out
-        pbf_sim *s;
-        ~Unmap() { if (s->gl_registered) cudaGraphicsUnmapResources(3, s->gl_res, s->stream); }
-    } unmap{s};
+    if (s->slab) return fail(PBF_ERR_STATE, "pbf_step: this handle is one slab of a decomposed domain; use pbf_slab_step");
+    GlScope gl(s);   // GL gets its buffers back on every way out
+    if (gl.rc) return gl.rc;
     const bool use_graph = s->cfg.use_graph && !s->timing;
     for (int i = 0; i < nsteps; i++) {
         if (use_graph) {
@@ -434,7 +478,7 @@ int pbf_step_host(pbf_handle s, float *pos4, float *vel4, int nsteps) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (!pos4 || !vel4) return fail(PBF_ERR_INVALID, "pbf_step_host: null buffer");
     if (nsteps < 0) return fail(PBF_ERR_INVALID, "pbf_step_host: negative step count");
-    if (s->gl_registered) return fail(PBF_ERR_STATE, "pbf_step_host: the state lives in the registered GL buffers; use pbf_step");
+    if (s->gl_registered) return fail(PBF_ERR_STATE, "pbf_step_host: the state lives in registered (GL / external) buffers; use pbf_step");
     DeviceGuard guard(s->device);
     const size_t bytes = (size_t)s->n * 16;
     if (!s->copy_stream) {
@@ -480,7 +524,9 @@ int pbf_sync(pbf_handle s) {
 #define STAGE_PROLOGUE(need, name)                                                                       \
     if (check_handle(s)) return PBF_ERR_INVALID;                                                         \
     if (s->stage < (need)) return fail(PBF_ERR_STATE, name ": called before the stages it depends on"); \
-    DeviceGuard guard(s->device);
+    DeviceGuard guard(s->device);                                                                        \
+    GlScope gl(s);                                                                                       \
+    if (gl.rc) return gl.rc;
 
 int pbf_predict(pbf_handle s) {
     STAGE_PROLOGUE(0, "pbf_predict");
@@ -495,6 +541,9 @@ int pbf_predict(pbf_handle s) {
 
 int pbf_sort(pbf_handle s) {
     STAGE_PROLOGUE(1, "pbf_sort");
+    // RadixSort::Run sorts the records predictpos.glsl has just written; the digit histograms of those keys are consumed
+    // by the scan, so a second Run without a new pbf_predict has nothing to sort from
+    if (s->stage != 1) return fail(PBF_ERR_STATE, "pbf_sort: already sorted; call pbf_predict first");
     s->launches += launch_sort_scan(s);
     s->launches += launch_sort_passes(s);
     PBF_CUDA(cudaGetLastError());
@@ -672,6 +721,8 @@ int pbf_pick_particle(pbf_handle s, const float origin[3], const float direction
     if (!(len > 0.0f) || !(radius > 0.0f)) return fail(PBF_ERR_INVALID, "pbf_pick_particle: zero direction or radius");
     const float d[3] = {direction[0] / len, direction[1] / len, direction[2] / len};
     DeviceGuard guard(s->device);
+    GlScope gl(s);
+    if (gl.rc) return gl.rc;
     unsigned long long *best = reinterpret_cast<unsigned long long *>(s->diag);   // 16 bytes of scratch, stream ordered
     PBF_CUDA(cudaMemsetAsync(best, 0xff, sizeof(*best), s->stream));
     s->launches += launch_pick(s, origin, d, radius, best);
@@ -686,6 +737,8 @@ int pbf_toggle_highlight(pbf_handle s, uint32_t id) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (id >= s->n) return fail(PBF_ERR_INVALID, "pbf_toggle_highlight: particle id out of range");
     DeviceGuard guard(s->device);
+    GlScope gl(s);
+    if (gl.rc) return gl.rc;
     s->launches += launch_toggle_highlight(s, id);
     PBF_CUDA(cudaGetLastError());
     return PBF_OK;
@@ -694,6 +747,8 @@ int pbf_toggle_highlight(pbf_handle s, uint32_t id) {
 int pbf_get_diagnostics(pbf_handle s, double *density_error, double *kinetic_energy) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     DeviceGuard guard(s->device);
+    GlScope gl(s);
+    if (gl.rc) return gl.rc;
     PBF_CUDA(cudaMemsetAsync(s->diag, 0, 2 * sizeof(double), s->stream));
     if (density_error) {
         if (s->n_prev_sorted != s->n) return fail(PBF_ERR_STATE, "pbf_get_diagnostics: density needs a completed step");

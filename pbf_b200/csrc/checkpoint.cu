@@ -187,6 +187,12 @@ int pbf_load_state(pbf_handle s, const char *path) {
         info.grid[2] != s->cfg.grid[2])
         return fail(PBF_ERR_INVALID, std::string(path) + ": particle count or grid differs from the handle's (create the handle "
                                                          "from pbf_state_file_info)");
+    // walls and the findcells quirk mode are constructor arguments like the grid: a run resumed under different ones would
+    // not continue bit for bit
+    if (info.wall[0] != s->cfg.wall[0] || info.wall[1] != s->cfg.wall[1] || info.wall[2] != s->cfg.wall[2] ||
+        (info.ref_quirks != 0) != (s->cfg.ref_quirks != 0))
+        return fail(PBF_ERR_INVALID, std::string(path) + ": wall offsets or ref_quirks differ from the handle's (create the "
+                                                         "handle from pbf_state_file_info)");
     std::vector<float> pos((size_t)s->n * 4), vel((size_t)s->n * 4);
     std::vector<uint32_t> hl(s->n);
     r = pbf_state_file_read(path, &info, pos.data(), vel.data(), hl.data(), s->n);
@@ -195,7 +201,10 @@ int pbf_load_state(pbf_handle s, const char *path) {
     if (r) return r;
     {
         DeviceGuard guard(s->device);
-        PBF_CUDA(cudaMemcpy(s->hl, hl.data(), (size_t)s->n * 4, cudaMemcpyHostToDevice));
+        GlScope gl(s);
+        if (gl.rc) return gl.rc;
+        PBF_CUDA(cudaMemcpyAsync(s->hl, hl.data(), (size_t)s->n * 4, cudaMemcpyHostToDevice, s->stream));
+        PBF_CUDA(cudaStreamSynchronize(s->stream));
     }
     r = pbf_set_params(s, &info.params);
     if (r) return r;

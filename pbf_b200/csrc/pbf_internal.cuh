@@ -101,6 +101,10 @@ struct pbf_sim {
     std::vector<cudaEvent_t> ev_solver; int ev_solver_iters;   // timing mode: one event before every solver kernel
     uint64_t launches;
     bool gl_registered; cudaGraphicsResource_t gl_res[3];   // renderer-owned GL buffers (pbf_register_gl_buffers)
+    bool gl_mapped;                       // inside a GlScope: pos/vel/hl point at the mapped GL buffers
+    // the same protocol for any other owner of the by-id buffers (pbf_register_external_buffers): gl_registered is set,
+    // gl_res stay null and map / unmap go through the caller's callbacks
+    pbf_map_fn ext_map; pbf_unmap_fn ext_unmap; void *ext_user;
     uint64_t steps;                       // completed SPH::Run calls since creation / the last state load (checkpoints)
     cudaStream_t copy_stream; cudaEvent_t ev_pos, ev_copied;   // pbf_step_host: position read-back under the vorticity kernels
     int stage;                            // 0 idle, 1 predicted, 2 sorted, 3 cells built
@@ -117,6 +121,20 @@ struct DeviceGuard {   // every entry point runs on the handle's device and rest
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
     }
+};
+
+// With GL buffers registered (pbf_register_gl_buffers) the by-id state lives in the renderer's buffer objects, which CUDA may
+// only touch between map and unmap.  Every entry point that reads or writes pos / vel / hl opens one of these: it maps
+// the three resources on the handle's stream and binds the mapped pointers; the destructor unmaps, which orders GL's
+// later reads after the work enqueued in between.  Without registered buffers it does nothing.  Nestable.
+struct GlScope {
+    pbf_sim *s;
+    int rc;          // PBF_OK or the error of the map; check before touching the buffers
+    bool owner;
+    explicit GlScope(pbf_sim *sim);
+    ~GlScope();
+    GlScope(const GlScope &) = delete;
+    GlScope &operator=(const GlScope &) = delete;
 };
 
 // error plumbing (api.cu)

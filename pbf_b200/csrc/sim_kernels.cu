@@ -40,7 +40,8 @@ k_predict(u32 first, u32 n, const float4 *__restrict__ pos, const float4 *__rest
         float4 v = vel[i];
         const u32 h = hl[i];
         // exact, uncontracted binary32 in the order of the shader so that keys are bit-identical to the oracle
-        if (P.extforce && p.z > (float)g.gz / 2.0f)
+        // GRID_SIZE.z/2 of the whole domain (predictpos.glsl:27): on a slab handle g.gz is only the window's depth
+        if (P.extforce && p.z > (float)g.gz_global / 2.0f)
             v.z = __fadd_rn(v.z, __fmul_rn(__fmul_rn(__fmul_rn(2.0f, P.gravity), -1.0f), P.timestep));
         v.y = __fadd_rn(v.y, __fmul_rn(__fmul_rn(P.gravity, -1.0f), P.timestep));
         p.x = __fadd_rn(p.x, __fmul_rn(P.timestep, v.x));

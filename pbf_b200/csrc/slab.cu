@@ -231,26 +231,33 @@ k_mark_boundary(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, in
 
 __global__ void __launch_bounds__(256)
 k_pack_ghosts(u32 count, const u32 *__restrict__ list, const float4 *__restrict__ pred, const float4 *__restrict__ pos,
-              GhostRec *__restrict__ out) {
+              const u32 *__restrict__ hl, GhostRec *__restrict__ out) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     u32 s = list[k];
     GhostRec r;
     r.pred = pred[s];
     r.old = pos[s];
+    // the selection bit travels with the ghost (position.w is 0 by contract): highlight.glsl:17-30 marks every neighbour of
+    // a selected particle, and a neighbour may live on the other side of the plane.  The stencil is symmetric, so it is
+    // enough that the OWNER of each particle sees the selected ghosts; marks put on ghost slots are dropped.
+    r.old.w = __uint_as_float(hl[s] & 1u);
     out[k] = r;
 }
 
 __global__ void __launch_bounds__(256)
 k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *pos, float4 *vel, float4 *pred, u32 *hl,
-                u32 *keys, GridInfo g) {
+                u32 *keys, u32 *flags, GridInfo g) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= count) return;
     GhostRec r = in[k];
     u32 s = base + k;
+    const u32 selected = __float_as_uint(r.old.w) & 1u;
+    r.old.w = 0.0f;
     pos[s] = r.old;                          // so that k_update derives the ghost's velocity like any other particle's
     vel[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    hl[s] = 0u;
+    hl[s] = selected;
+    if (selected) flags[0] = 1u;             // k_highlight has work even if no local particle is selected
     r.pred.w = __int_as_float((int)s);
     pred[s] = r.pred;
     keys[s] = window_key(r.pred.x, r.pred.y, r.pred.z, g);
@@ -263,10 +270,13 @@ k_halo_index(u32 n, u32 n_local, const u32 *__restrict__ skey, const u32 *__rest
              u32 *__restrict__ push_tiles, u32 tile_size, GridInfo g) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u32 k = skey[i] & ~PBF_KEY_NOCELL;
+    const u32 kraw = skey[i];
+    const u32 k = kraw & ~PBF_KEY_NOCELL;
     const int cz = (int)((k % (u32)g.gxgz) / (u32)g.gx);
     u32 t = 0;
-    const bool edge = !(cz > 1 && cz < g.gz - 2);    // interior layers hold neither ghosts nor boundary particles
+    // interior layers hold neither ghosts nor boundary particles.  The layer decoded from the hash is only exact for keys
+    // with a cell: a particle clamped to x = gx hashes like (0, z + 1), so keys without a cell always take the slow path
+    const bool edge = (kraw & PBF_KEY_NOCELL) != 0u || !(cz > 1 && cz < g.gz - 2);
     const u32 id = edge ? perm[i] : 0u;
     if (edge && id < n_local) t = btag[id];
     push_map[i] = t;
@@ -623,7 +633,7 @@ int slab_step(pbf_sim **grp, int ng) {
             sb[2 * r + side] = (size_t)O[r][side] * sizeof(GhostRec);
             rb[2 * r + side] = (size_t)I[r][side] * sizeof(GhostRec);
             if (O[r][side]) {
-                k_pack_ghosts<<<nb(O[r][side]), 256, 0, s->stream>>>(O[r][side], b->list[2 + side], s->pred, s->pos,
+                k_pack_ghosts<<<nb(O[r][side]), 256, 0, s->stream>>>(O[r][side], b->list[2 + side], s->pred, s->pos, s->hl,
                                                                       (GhostRec *)b->send[side]);
                 s->launches++;
             }
@@ -641,7 +651,7 @@ int slab_step(pbf_sim **grp, int ng) {
         for (int side = 0; side < 2; side++) {
             if (b->n_ghost[side]) {
                 k_unpack_ghosts<<<nb(b->n_ghost[side]), 256, 0, s->stream>>>(b->n_ghost[side], base, (const GhostRec *)b->recv[side],
-                                                                              s->pos, s->vel, s->pred, s->hl, s->keys, s->grid);
+                                                                              s->pos, s->vel, s->pred, s->hl, s->keys, s->flags, s->grid);
                 s->launches++;
             }
             base += b->n_ghost[side];
@@ -898,6 +908,15 @@ int pbf_slab_download(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, uin
     return PBF_OK;
 }
 
+// highlight words of the local particles, by slot (same order as pbf_slab_download's arrays)
+int pbf_slab_download_highlight(pbf_handle s, uint32_t *highlight) {
+    if (!s || !s->slab || !highlight) { pbf_set_error("pbf_slab_download_highlight: slab not initialised or null buffer"); return PBF_ERR_STATE; }
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaMemcpyAsync(highlight, s->hl, (size_t)s->slab->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    return PBF_OK;
+}
+
 // SPH::Run on this rank's slab (NCCL transport), or on every virtual rank of the handle's group
 int pbf_slab_step(pbf_handle s, int nsteps) {
     if (!s || !s->slab) { pbf_set_error("pbf_slab_step: slab not initialised"); return PBF_ERR_STATE; }
@@ -911,6 +930,33 @@ int pbf_slab_step(pbf_handle s, int nsteps) {
     }
     cudaSetDevice(prev);
     return rc;
+}
+
+// End-to-end call of a slab rank: HOST arrays in (n_in local particles by slot + global ids), nsteps, HOST arrays out (the
+// particles this rank owns afterwards; *n_out of them, at most `capacity`).  The arrays should be pinned: every copy is
+// asynchronous on the handle's stream and the call synchronises once, at the end.
+int pbf_slab_step_host(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, uint32_t n_in, uint32_t capacity,
+                       uint32_t *n_out, int nsteps) {
+    if (!s || !s->slab) { pbf_set_error("pbf_slab_step_host: slab not initialised"); return PBF_ERR_STATE; }
+    if (!pos4 || !vel4 || !gid || !n_out) { pbf_set_error("pbf_slab_step_host: null buffer"); return PBF_ERR_INVALID; }
+    if (n_in > s->cap || n_in > capacity) { pbf_set_error("pbf_slab_step_host: n exceeds capacity"); return PBF_ERR_CAPACITY; }
+    if (s->slab->group) { pbf_set_error("pbf_slab_step_host: one rank per process only (virtual groups step together)"); return PBF_ERR_STATE; }
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaMemcpyAsync(s->pos, pos4, (size_t)n_in * 16, cudaMemcpyHostToDevice, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(s->vel, vel4, (size_t)n_in * 16, cudaMemcpyHostToDevice, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(s->slab->gid, gid, (size_t)n_in * 4, cudaMemcpyHostToDevice, s->stream));
+    s->n = n_in;
+    s->slab->n_local = n_in;
+    const int rc = pbf_slab_step(s, nsteps);
+    if (rc) return rc;
+    const u32 m = s->slab->n_local;
+    if (m > capacity) { pbf_set_error("pbf_slab_step_host: more particles than the caller's arrays hold"); return PBF_ERR_CAPACITY; }
+    PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)m * 16, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(vel4, s->vel, (size_t)m * 16, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaMemcpyAsync(gid, s->slab->gid, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    *n_out = m;
+    return PBF_OK;
 }
 
 // out[0] local particles, [1] ghosts from z-, [2] ghosts from z+, [3] boundary sent to z-, [4] sent to z+,

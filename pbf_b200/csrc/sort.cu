@@ -219,7 +219,7 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
     }
 }
 
-int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n) {
+int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, const u32 *gbase) {
     const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
     if (tiles == 0) return 0;
     cudaMemsetAsync(s->status, 0, (size_t)plan.passes * tiles * PBF_RADIX * sizeof(u32), s->stream);
@@ -232,10 +232,10 @@ int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin,
         u32 *st = s->status + (size_t)p * tiles * PBF_RADIX;
         if (p == 0 && vin == nullptr)
             k_onesweep<true><<<tiles, SORT_BLOCK, 0, s->stream>>>(ki, nullptr, ko, vo, n, plan.shift[p], plan.mask[p],
-                                                                  s->gbase + p * PBF_RADIX, st, s->tile_counter + p);
+                                                                  gbase + p * PBF_RADIX, st, s->tile_counter + p);
         else
             k_onesweep<false><<<tiles, SORT_BLOCK, 0, s->stream>>>(ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
-                                                                   s->gbase + p * PBF_RADIX, st, s->tile_counter + p);
+                                                                   gbase + p * PBF_RADIX, st, s->tile_counter + p);
         launched++;
     }
     return launched;
@@ -264,7 +264,7 @@ int launch_sort_scan(pbf_sim *s) {
 
 // the simulation's sort: keys by id (histograms already accumulated by k_predict), values = iota
 int launch_sort_passes(pbf_sim *s) {
-    return run_passes(s, s->plan, s->keys, nullptr, s->skey, s->perm, s->n);
+    return run_passes(s, s->plan, s->keys, nullptr, s->skey, s->perm, s->n, s->gbase);
 }
 
 // digit histograms of every pass of the handle's plan over keys[0..n) (slab mode: keys change after k_predict)
@@ -273,6 +273,9 @@ int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n) {
     int maxb = s->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
+    // the histograms are accumulated with atomics: start from zero whatever ran before (pbf_predict twice, pbf_predict
+    // followed by pbf_step, ... -- k_sort_scan also clears them, but only when a sort follows)
+    cudaMemsetAsync(s->hist, 0, 4 * PBF_RADIX * sizeof(u32), s->stream);
     k_sort_hist<<<blocks, 256, 0, s->stream>>>(keys, n, s->plan, s->hist);
     return 1;
 }
@@ -283,8 +286,11 @@ int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32
     int maxb = s->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    cudaMemsetAsync(s->hist, 0, 4 * PBF_RADIX * sizeof(u32), s->stream);
-    k_sort_hist<<<blocks, 256, 0, s->stream>>>(kin, n, plan, s->hist);
-    k_sort_scan<<<plan.passes, PBF_RADIX, 0, s->stream>>>(s->hist, s->gbase, s->tile_counter);
-    return 2 + run_passes(s, plan, kin, vin, kout, vout, n);
+    // own histogram / digit-base scratch (second half of the allocations): a standalone sort between pbf_predict and
+    // pbf_sort must not disturb the histograms the simulation's sort is about to scan
+    u32 *hist = s->hist + 4 * PBF_RADIX, *gbase = s->gbase + 4 * PBF_RADIX;
+    cudaMemsetAsync(hist, 0, 4 * PBF_RADIX * sizeof(u32), s->stream);
+    k_sort_hist<<<blocks, 256, 0, s->stream>>>(kin, n, plan, hist);
+    k_sort_scan<<<plan.passes, PBF_RADIX, 0, s->stream>>>(hist, gbase, s->tile_counter);
+    return 2 + run_passes(s, plan, kin, vin, kout, vout, n, gbase);
 }

@@ -101,8 +101,22 @@ class SlabSPH(SPH):
         _check(lib().pbf_slab_download(self._h, _ptr(pos), _ptr(vel), _ptr(gid), C.byref(n)))
         return pos, vel, gid
 
+    def download_highlight(self):
+        n = C.c_uint32()
+        _check(lib().pbf_slab_download(self._h, None, None, None, C.byref(n)))
+        hl = np.empty(n.value, np.uint32)
+        _check(lib().pbf_slab_download_highlight(self._h, _ptr(hl)))
+        return hl
+
     def Run(self, nsteps=1):
         _check(lib().pbf_slab_step(self._h, nsteps))
+
+    def step_host(self, pos, vel, gid, n, capacity, nsteps=1):
+        """End-to-end call: n local particles from (pinned) host arrays in, nsteps, the particles this rank owns afterwards
+        back out into the same arrays; returns their number."""
+        m = C.c_uint32()
+        _check(lib().pbf_slab_step_host(self._h, _ptr(pos), _ptr(vel), _ptr(gid), n, capacity, C.byref(m), nsteps))
+        return m.value
 
     def stats(self):
         out = (C.c_uint64 * 8)()
@@ -164,6 +178,21 @@ class VirtualGroup:
         assert np.all(seen == 1), "every particle must be owned by exactly one rank"
         return pos, vel
 
+    def toggle_highlight(self, gids):
+        """Simulation::OnMouseDown's highlight toggle for particles given by GLOBAL id (the owner's slot is looked up)."""
+        want = set(int(g) for g in np.atleast_1d(gids))
+        for s in self.ranks:
+            _, _, gid = s.download_slab()
+            for slot in np.nonzero(np.isin(gid, list(want)))[0]:
+                s.toggle_highlight(int(slot))
+
+    def gather_highlight(self):
+        out = np.zeros(self.n, np.uint32)
+        for s in self.ranks:
+            _, _, gid = s.download_slab()
+            out[gid] = s.download_highlight()
+        return out
+
     def close(self):
         for s in reversed(self.ranks):
             s.close()
@@ -186,15 +215,17 @@ def weak_scene(rank, nranks, n3, grid_local_z=512, origin=(32.5, 0.5, 32.5), spa
     return pos, vel, gid, planes, gz_global
 
 
-def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algorithmic_bytes):
-    """Weak scaling: every rank holds one C3-sized slab of a dam-break block that is `world` times deeper."""
+def bench(args, name, cfg, scene, rank, world, local, B):
+    """Multi-GPU lines of bench.py (B = the bench module): weak scaling (one block per GPU, default: ballistic splash) or
+    strong scaling (one tank cut into `world` slabs).  Device time = CUDA events on the library's stream bracketed by
+    barriers, max over ranks; end to end = pbf_slab_step_host with persistent pinned host buffers."""
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", local)
-    pos, vel, gid, planes, gz_global = weak_scene(rank, world, cfg["n3"], cfg["grid"][2])
+    pos, vel, gid, planes, ggrid = B.rank_block(name, cfg, rank, world, scene)
     n0 = pos.shape[0]
-    halo_cap = 1 << 18
-    s = SlabSPH(rank, world, planes, cfg["grid"][:2], gz_global, int(n0 * 1.2) + 2 * halo_cap, halo_cap, device=local)
+    halo_cap = 1 << 19 if n0 > (12 << 20) else 1 << 18
+    s = SlabSPH(rank, world, planes, ggrid[:2], ggrid[2], int(n0 * 1.25) + 2 * halo_cap, halo_cap, device=local)
     s.init_nccl(broadcast_unique_id(dist, rank, dev))
     p2p = s.connect_p2p(dist, dev)
     s.SetNumSolverIterations(cfg["iters"])
@@ -203,10 +234,11 @@ def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algo
     stream = torch.cuda.ExternalStream(s.stream, device=local)
     s.Run(args.warmup)
     s.sync()
-    sampler = ClockSampler(local)
+    sampler = B.ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = s.kernel_launches
+    m0 = s.stats()["migrated"]
     with torch.cuda.stream(stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
@@ -219,52 +251,67 @@ def bench(args, cfg, rank, world, local, metric, unit, peaks, ClockSampler, algo
         ms = e0.elapsed_time(e1) / args.steps
     launches = s.kernel_launches - l0
     st = s.stats()
-    t = torch.tensor([ms, float(st["n_local"]), float(st["migrated"]), float(st["ghosts_lo"] + st["ghosts_hi"])],
+    t = torch.tensor([ms, float(st["n_local"]), float(st["migrated"] - m0), float(st["ghosts_lo"] + st["ghosts_hi"])],
                      dtype=torch.float64, device=dev)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tmin = t.clone()
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     tsum = t.clone()
     dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-    # end to end: host buffers in and out every step (download/upload of the local slab around one step)
-    hp, hv, hg = s.download_slab()
+    # end to end: the rank's particles in from pinned host arrays, one step, the particles it then owns back out
+    cap = s.capacity
+    hp = torch.zeros((cap, 4), dtype=torch.float32).pin_memory()
+    hv = torch.zeros((cap, 4), dtype=torch.float32).pin_memory()
+    hg = torch.zeros((cap,), dtype=torch.int32).pin_memory()
+    lp, lv, lg = s.download_slab()
+    n_loc = lp.shape[0]
+    hp[:n_loc] = torch.from_numpy(lp); hv[:n_loc] = torch.from_numpy(lv); hg[:n_loc] = torch.from_numpy(lg.view(np.int32))
+    del lp, lv, lg
+    n_loc = s.step_host(hp, hv, hg, n_loc, cap)                   # warm
+    e2e_steps = max(3, min(args.steps, 10))
+    moved = 0
     dist.barrier()
     t0 = time.perf_counter()
-    e2e_steps = 3
     for _ in range(e2e_steps):
-        s.upload_slab(hp, hv, hg)
-        s.Run(1)
-        hp, hv, hg = s.download_slab()
+        moved += 2 * n_loc * 36
+        n_loc = s.step_host(hp, hv, hg, n_loc, cap)
     dist.barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3], dtype=torch.float64, device=dev)
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3, moved / (2.0 * e2e_steps)], dtype=torch.float64, device=dev)
+    e2e_max = e2e.clone()
+    dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(e2e, op=dist.ReduceOp.SUM)
     if rank == 0:
         sampler.stop_flag = True
         sampler.join()
         n_total = tsum[1].item()
         ms_step = tmax[0].item()
         value = n_total / (ms_step * 1e-3)
-        peak, peak_src = peaks()
-        step_bytes = algorithmic_bytes((cfg["grid"][0], cfg["grid"][1], cfg["grid"][2]), cfg["iters"], cfg["vort"])
+        peak, peak_src = B.peaks()
+        local_grid = (ggrid[0], ggrid[1], max(b - a for a, b in zip(planes[:-1], planes[1:])) + 2)
+        step_bytes = B.algorithmic_bytes(local_grid, cfg["iters"], cfg["vort"])
+        per_gpu_gbs = step_bytes * value / world / 1e9
         print(json.dumps({
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "dam-break %dx%dx%d particles per GPU (block %d x deeper along z), grid %dx%dx%d per GPU, %d solver iters, vorticity+XSPH %s; z-slabs with 1-layer halos"
-                                   % (cfg["n3"] + (world,) + cfg["grid"] + (cfg["iters"], "on" if cfg["vort"] else "off")),
-                       "parallelism": "slab%d" % world,
-                       "halo_transport": ("peer-memory stores + flags over NVLink (lambda, positions, |omega|)%s; NCCL send/recv for migration and ghost records"
-                                          % (", pushed by the producing sweep's epilogue" if os.environ.get("PBF_SLAB_FUSED") == "1" else ", push kernel + pull kernel")) if p2p else "NCCL send/recv", "particles_total": int(n_total),
-                       "migrated_particles_total": int(tsum[2].item()), "ghost_particles_total": int(tsum[3].item()),
+            "config": B.static_config(name, cfg, world, scene),
+            "detail": {"halo_transport": ("peer-memory stores + flags over NVLink (lambda, positions, |omega|)%s; NCCL send/recv for migration and ghost records"
+                                          % (", pushed by the producing sweep's epilogue" if os.environ.get("PBF_SLAB_FUSED") == "1" else ", push kernel + pull kernel")) if p2p else "NCCL send/recv",
+                       "particles_total": int(n_total), "particles_per_rank_min_max": [int(tmin[1].item()), int(tmax[1].item())],
+                       "migrated_particles_in_timed_steps": int(tsum[2].item()),
+                       "migrated_fraction_per_step": tsum[2].item() / max(1.0, n_total * args.steps),
+                       "ghost_particles_total": int(tsum[3].item()),
+                       "ms_per_step_min_over_ranks": tmin[0].item(),
                        "exchanges_per_step": st["exchanges"] // max(1, args.steps + args.warmup),
-                       "l2": "per-GPU working set (~2 GB) far exceeds the 126 MB L2",
                        "step_algorithmic_bytes_per_particle": step_bytes,
-                       "step_hbm_frac_of_peak": step_bytes * value / world / 1e9 / peak},
+                       "step_hbm_frac_of_peak": per_gpu_gbs / peak},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
-            "e2e": {"value": n_total / (e2e_ms.item() * 1e-3), "unit": unit, "h2d_bytes_per_step": int(n_total * 36),
-                    "d2h_bytes_per_step": int(n_total * 36), "ms_per_step": e2e_ms.item(),
-                    "call": "pbf_slab_upload + pbf_slab_step + pbf_slab_download per step (host pos+vel+gid)"},
-            "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": step_bytes * value / world / 1e9,
-                         "peak": peak, "unit": "GB/s", "frac": step_bytes * value / world / 1e9 / peak, "traffic": None,
+            "e2e": {"value": n_total / (e2e_max[0].item() * 1e-3), "unit": B.UNIT, "h2d_bytes_per_step": int(e2e[1].item()),
+                    "d2h_bytes_per_step": int(e2e[1].item()), "ms_per_step": e2e_max[0].item(),
+                    "call": "pbf_slab_step_host per rank (persistent pinned host pos+vel+gid in, pos+vel+gid out)"},
+            "roofline": {"bound": "hbm", "kernel": "whole step (per GPU)", "achieved": per_gpu_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None,
                          "peak_source": peak_src, "note": "per-GPU algorithmic bytes / step time; see the N=1 line for the dominant kernel"},
         }))
     dist.barrier()

@@ -27,30 +27,46 @@ def main():
     p2p = s.connect_p2p(dist, torch.device("cuda", local))     # PBF_SLAB_P2P=0: NCCL send/recv for every exchange
     s.SetNumSolverIterations(3)
     s.SetVorticityConfinementEnabled(True)
+    s.SetExternalForce(True)            # predictpos.glsl:27 compares against GRID_SIZE.z/2 of the WHOLE domain (80 here)
     s.upload_slab(p, v, g)
+    # select the particles of one column either side of the first plane: highlight.glsl's marks must cross it
+    sel = np.nonzero((np.abs(pos[:, 2] - planes[1]) < 1.0) & (np.abs(pos[:, 0] - 25.0) < 1.0) & (pos[:, 1] < 3.0))[0]
+    for slot in np.nonzero(np.isin(g, sel))[0]:
+        s.toggle_highlight(int(slot))
     steps = 6
     s.Run(steps)
     lp, lv, lg = s.download_slab()
+    lh = s.download_highlight()
     st = s.stats()
     parts = [None] * world
-    dist.all_gather_object(parts, (lp, lv, lg, st))
+    dist.all_gather_object(parts, (lp, lv, lg, st, lh))
     ok = True
     if rank == 0:
         gpos = np.zeros_like(pos); gvel = np.zeros_like(vel); seen = np.zeros(pos.shape[0], np.int32)
-        for lp, lv, lg, _ in parts:
-            gpos[lg], gvel[lg] = lp, lv
+        ghl = np.zeros(pos.shape[0], np.uint32)
+        for lp, lv, lg, _, lh in parts:
+            gpos[lg], gvel[lg], ghl[lg] = lp, lv, lh
             seen[lg] += 1
         single = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False, device=local)
         single.SetNumSolverIterations(3)
         single.SetVorticityConfinementEnabled(True)
+        single.SetExternalForce(True)
         single.upload(pos, vel)
+        for i in sel:
+            single.toggle_highlight(int(i))
         single.Run(steps)
-        spos, svel = single.download()
+        spos, svel, shl = single.download(highlight=True)
         dp, dv = np.max(np.abs(spos - gpos)), np.max(np.abs(svel - gvel))
         mig = sum(p[3]["migrated"] for p in parts)
         gh = sum(p[3]["ghosts_lo"] + p[3]["ghosts_hi"] for p in parts)
-        ok = bool(np.all(seen == 1) and dp < 2e-4 and dv < 2e-4 / 0.016 and mig > 0 and gh > 0)
-        print("MGPU_RESULT ok=%s p2p=%s world=%d dp=%.3g dv=%.3g migrated=%d ghosts=%d planes=%s" % (ok, p2p, world, dp, dv, mig, gh, planes))
+        # selection bits are bit exact; the marks of the last step depend on which particles are neighbours, and a particle
+        # within rounding distance of a cell face may sit on either side of it in the two runs: allow a handful
+        hl_bad = int(np.count_nonzero(shl != ghl))
+        marked = int(np.count_nonzero(ghl & 2))
+        ok = bool(np.all(seen == 1) and dp < 2e-4 and dv < 2e-4 / 0.016 and mig > 0 and gh > 0
+                  and np.array_equal(shl & 1, ghl & 1) and sel.size >= 4 and marked > sel.size and hl_bad <= 2)
+        print("MGPU_RESULT ok=%s p2p=%s world=%d dp=%.3g dv=%.3g migrated=%d ghosts=%d selected=%d marked=%d hl_mismatch=%d planes=%s"
+              % (ok, p2p, world, dp, dv, mig, gh, sel.size, marked, hl_bad, planes))
     dist.barrier()
     s.close()
     dist.destroy_process_group()

@@ -1,0 +1,253 @@
+"""Round-2 parity cases: the headline size (C3, 8M particles) against the oracle, the stage API called out of order, the
+external force across slab planes, highlight marks across slab planes, and the map/unmap protocol of renderer-owned
+buffers (pbf_register_external_buffers = the GL interop path with the GL calls replaced by callbacks)."""
+import numpy as np
+import pytest
+
+import oracle
+import pbf_b200
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-5 * 128.0
+VEL_TOL = POS_TOL / 0.016
+
+
+def test_c3_one_step_against_oracle(built_lib):
+    """BASELINE configs[2], the headline: 8,388,608 particles, grid 512x256x512, K = 4, vorticity + XSPH, one whole step.
+    Keys, permutation and cell starts bit exact; positions within 1e-5 x 128, velocities within that / dt."""
+    grid = (512, 256, 512)
+    pos, vel = oracle.dam_break(256, 128, 256)
+    n = pos.shape[0]
+    assert n == 8388608
+    sph = pbf_b200.SPH(n, grid, ref_quirks=False)
+    sph.SetNumSolverIterations(4)
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    sph.Run()
+    oracle.set_num_threads(__import__("os").cpu_count())
+    sim = oracle.Sim(n, oracle.make_grid(*grid, ref_quirks=0))
+    opos, ovel = pos.copy(), vel.copy()
+    sim.step(opos, ovel, oracle.default_params(), 4, vorticity=True)
+    keys, perm, _ = sph.get_sorted(records=False)
+    assert np.array_equal(keys, sim.skey)
+    assert np.array_equal(perm, sim.sorted[:, 3].view(np.int32).astype(np.uint32))
+    start, end = sph.get_cell_ranges()
+    assert np.array_equal(start, sim.start)
+    occupied = start != -1
+    assert np.array_equal(end[occupied], sim.end[occupied])
+    del start, end, occupied
+    gpos, gvel = sph.download()
+    dp, dv = float(np.max(np.abs(gpos - opos))), float(np.max(np.abs(gvel - ovel)))
+    assert dp < POS_TOL and dv < VEL_TOL, (dp, dv)
+    # the observed differences are rounding level (FMA contraction, rsqrt.approx): keep them from creeping up unnoticed
+    assert dp < 1e-4 and dv < 1e-2, (dp, dv)
+
+
+def _one_step_state(sph):
+    keys, perm, _ = sph.get_sorted(records=False)
+    start, end = sph.get_cell_ranges()
+    return keys, perm, start, end
+
+
+def test_stage_api_out_of_order(built_lib):
+    """pbf_predict twice, pbf_predict followed by pbf_step, a second pbf_sort, and a standalone pbf_sort_pairs
+    between pbf_predict and pbf_sort must neither corrupt the digit histograms nor go unnoticed."""
+    import torch
+    pos, vel = oracle.dam_break(32, 32, 32)
+    n = pos.shape[0]
+    ref = pbf_b200.SPH(n)
+    ref.upload(pos, vel)
+    ref.predict(); ref.sort(); ref.build_cells()
+    want = _one_step_state(ref)
+
+    a = pbf_b200.SPH(n)
+    a.upload(pos, vel)
+    a.predict(); a.predict()                               # histograms must not double
+    a.sort(); a.build_cells()
+    for x, y in zip(_one_step_state(a), want):
+        assert np.array_equal(x, y)
+    with pytest.raises(RuntimeError, match="already sorted"):
+        a.sort()                                           # RadixSort::Run twice: refused, not a silent wrong permutation
+
+    b = pbf_b200.SPH(n)
+    b.upload(pos, vel)
+    b.predict()
+    kin = torch.randint(0, 1 << 20, (5000,), dtype=torch.int32, device="cuda")
+    vin = torch.arange(5000, dtype=torch.int32, device="cuda")
+    kout, vout = torch.empty_like(kin), torch.empty_like(vin)
+    b.sort_pairs(kin, vin, kout, vout, 5000, 20)           # own scratch: the simulation's histograms survive
+    b.sort(); b.build_cells()
+    for x, y in zip(_one_step_state(b), want):
+        assert np.array_equal(x, y)
+    b.sync()
+    order = np.argsort(kin.cpu().numpy(), kind="stable")
+    assert np.array_equal(vout.cpu().numpy(), order.astype(np.int32))
+
+    c = pbf_b200.SPH(n)
+    c.SetNumSolverIterations(3)
+    c.upload(pos, vel)
+    c.predict()                                            # abandoned stage sequence, then whole steps
+    c.Run(2)
+    d = pbf_b200.SPH(n)
+    d.SetNumSolverIterations(3)
+    d.upload(pos, vel)
+    d.Run(2)
+    (pc, vc), (pd, vd) = c.download(), d.download()
+    assert np.array_equal(pc.view(np.uint32), pd.view(np.uint32)) and np.array_equal(vc.view(np.uint32), vd.view(np.uint32))
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_virtual_slabs_external_force(built_lib, nranks):
+    """predictpos.glsl:27 compares against GRID_SIZE.z/2 of the WHOLE domain; a slab's window depth must not leak in.
+    The block straddles z = gz/2, so the force acts on part of every slab."""
+    from pbf_b200 import slab
+    grid = (64, 32, 96)
+    pos, vel = oracle.dam_break(16, 16, 64, origin=(18.5, 0.5, 18.5))      # z in [18.5, 77.7], gz/2 = 48
+    assert (pos[:, 2] > 48).any() and (pos[:, 2] < 48).any()
+    single = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+    single.SetNumSolverIterations(3)
+    single.SetExternalForce(True)
+    single.upload(pos, vel)
+    grp = slab.VirtualGroup(pos, vel, nranks, grid, halo_capacity=8192)
+    grp.set_params(num_solver_iterations=3, external_force=1)
+    for step in range(5):
+        single.Run()
+        grp.Run()
+    spos, svel = single.download()
+    gpos, gvel = grp.gather()
+    assert np.max(np.abs(spos - gpos)) < 2e-4
+    assert np.max(np.abs(svel - gvel)) < 2e-4 / 0.016
+    # and the force did something: particles beyond gz/2 were pushed towards -z against the oracle's prediction too
+    P = oracle.default_params()
+    rec = oracle.predict(pos, vel, P, oracle.make_grid(*grid, ref_quirks=0), True)
+    assert (rec[pos[:, 2] > 48, 2] < pos[pos[:, 2] > 48, 2]).all()
+    grp.close()
+
+
+def test_virtual_slabs_highlight_crosses_planes(built_lib):
+    """highlight.glsl:17-30 marks every neighbour of a selected particle; with slabs a neighbour may live on the other
+    side of a plane (a ghost here, a local particle there).  Flags by global id must equal the single-domain run's."""
+    from pbf_b200 import slab
+    grid = (64, 32, 96)
+    pos, vel = oracle.dam_break(16, 16, 64, origin=(18.5, 0.5, 18.5))
+    n = pos.shape[0]
+    single = pbf_b200.SPH(n, grid, ref_quirks=False)
+    single.SetNumSolverIterations(2)
+    single.upload(pos, vel)
+    grp = slab.VirtualGroup(pos, vel, 2, grid, halo_capacity=8192)
+    grp.set_params(num_solver_iterations=2)
+    plane = grp.z_planes[1]
+    # select the particles of the two cell layers either side of the plane, in one column
+    sel = np.nonzero((np.abs(pos[:, 2] - plane) < 1.0) & (np.abs(pos[:, 0] - 25.0) < 1.0) & (pos[:, 1] < 3.0))[0]
+    assert sel.size >= 4
+    for i in sel:
+        single.toggle_highlight(int(i))
+    grp.toggle_highlight(sel)
+    single.Run()
+    grp.Run()
+    _, _, shl = single.download(highlight=True)
+    ghl = grp.gather_highlight()
+    assert (shl & 2).sum() > sel.size                       # neighbours were marked
+    assert np.array_equal(shl, ghl)
+    # marks on both sides of the plane
+    marked = np.nonzero(ghl & 2)[0]
+    assert (pos[marked, 2] < plane).any() and (pos[marked, 2] >= plane).any()
+    grp.close()
+
+
+def test_external_buffers_protocol(built_lib):
+    """The GL-interop code path with the GL calls replaced by callbacks (pbf_register_external_buffers): every entry point
+    that touches particle state brackets its work with map/unmap, nothing touches the handle's private buffers, and the
+    results are bit identical to a handle that owns its buffers (upload landed in the wrong buffers)."""
+    import torch
+    pos, vel = oracle.dam_break(16, 16, 16)
+    n = pos.shape[0]
+    own = pbf_b200.SPH(n)
+    own.SetNumSolverIterations(3)
+    own.SetVorticityConfinementEnabled(True)
+    own.upload(pos, vel)
+
+    ext = pbf_b200.SPH(n)
+    ext.SetNumSolverIterations(3)
+    ext.SetVorticityConfinementEnabled(True)
+    bufs = [torch.full((n, 4), float("nan"), device="cuda"), torch.full((n, 4), float("nan"), device="cuda"),
+            torch.full((n,), 7, dtype=torch.int32, device="cuda")]
+    log = {"map": 0, "unmap": 0, "mapped": False, "bad": 0}
+
+    def do_map(stream):
+        log["bad"] += log["mapped"]
+        log["mapped"] = True
+        log["map"] += 1
+        return bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr()
+
+    def do_unmap(stream):
+        log["bad"] += not log["mapped"]
+        log["mapped"] = False
+        log["unmap"] += 1
+
+    ext.register_external_buffers(do_map, do_unmap)
+    with pytest.raises(RuntimeError, match="only valid while mapped"):
+        ext.GetPositionBuffer()
+    ext.upload(pos, vel)                                       # Simulation::ResetParticleBuffer through the library
+    ext.sync()
+    torch.cuda.synchronize()
+    assert np.array_equal(bufs[0].cpu().numpy().view(np.uint32), pos.view(np.uint32))   # landed in the OWNER's buffers
+    assert int(bufs[2].abs().sum()) == 0                       # highlight cleared (src/Simulation.cpp:271-272)
+    calls = log["map"]
+    assert calls >= 1 and log["map"] == log["unmap"]
+    for _ in range(3):
+        own.Run()
+        ext.Run()
+    assert log["map"] == calls + 3 and log["map"] == log["unmap"]
+    ext.toggle_highlight(5); own.toggle_highlight(5)
+    ext.Run(); own.Run()
+    assert ext.pick_particle((64.0, 5.0, -20.0), (-0.3, 0.0, 1.0)) == own.pick_particle((64.0, 5.0, -20.0), (-0.3, 0.0, 1.0))
+    d_ext, d_own = ext.diagnostics(), own.diagnostics()
+    assert d_ext == d_own
+    ep, ev, eh = ext.download(highlight=True)
+    op, ov, oh = own.download(highlight=True)
+    assert np.array_equal(ep.view(np.uint32), op.view(np.uint32)) and np.array_equal(ev.view(np.uint32), ov.view(np.uint32))
+    assert np.array_equal(eh, oh) and (eh & 2).any()
+    # the stage entry points bracket too
+    ext.predict(); ext.sort(); ext.build_cells(); ext.highlight(); ext.calc_lambda(); ext.update_positions(); ext.finalize()
+    ext.vorticity()
+    own.predict(); own.sort(); own.build_cells(); own.highlight(); own.calc_lambda(); own.update_positions(); own.finalize()
+    own.vorticity()
+    ep, ev = ext.download()
+    op, ov = own.download()
+    assert np.array_equal(ep.view(np.uint32), op.view(np.uint32)) and np.array_equal(ev.view(np.uint32), ov.view(np.uint32))
+    assert log["bad"] == 0 and log["map"] == log["unmap"] and not log["mapped"]
+    torch.cuda.synchronize()
+    assert np.array_equal(bufs[0].cpu().numpy().view(np.uint32), ep.view(np.uint32))     # the owner sees the new state
+    ext.unregister_external_buffers()
+    before = log["map"]
+    ext.upload(pos, vel)
+    ext.Run()
+    assert log["map"] == before                                 # back on the handle's own buffers
+    ext.close(); own.close()
+
+
+def test_load_state_checks_walls_and_quirks(built_lib, tmp_path):
+    pos, vel = oracle.dam_break(8, 8, 8)
+    path = str(tmp_path / "s.pbf")
+    a = pbf_b200.SPH(512, ref_quirks=True)
+    a.upload(pos, vel)
+    a.save_state(path)
+    b = pbf_b200.SPH(512, ref_quirks=False)
+    with pytest.raises(RuntimeError, match="ref_quirks"):
+        b.load_state(path)
+    c = pbf_b200.SPH(512, wall=(8.0, 0.0, 8.0), ref_quirks=True)
+    with pytest.raises(RuntimeError, match="wall"):
+        c.load_state(path)
+    d = pbf_b200.SPH(512, ref_quirks=True)
+    d.load_state(path)
+
+
+def test_step_on_slab_handle_is_refused(built_lib):
+    from pbf_b200 import slab
+    pos, vel = oracle.dam_break(16, 16, 32, origin=(18.5, 0.5, 18.5))
+    grp = slab.VirtualGroup(pos, vel, 2, (64, 32, 64), halo_capacity=4096)
+    with pytest.raises(RuntimeError, match="pbf_slab_step"):
+        pbf_b200.SPH.Run(grp.ranks[0])
+    grp.close()

@@ -22,3 +22,4 @@ def test_slabs_match_single_domain(built_lib, world, p2p):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PBF_SLAB_P2P=p2p[0], PBF_SLAB_FUSED="1" if p2p.endswith("f") else "0"))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MGPU_RESULT ok=True p2p=%s" % (p2p[0] == "1") in r.stdout, r.stdout[-3000:]
+    print([l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT")][0])      # kept in the committed pytest -s logs
