@@ -190,7 +190,8 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     ALLOC(s->ktmp[0], cap); ALLOC(s->ktmp[1], cap); ALLOC(s->vtmp[0], cap); ALLOC(s->vtmp[1], cap);
     ALLOC(s->skey, cap); ALLOC(s->perm, cap); ALLOC(s->home, cap);
     s->max_tiles = sort_max_tiles(cap);
-    ALLOC(s->hist, 8 * PBF_RADIX); ALLOC(s->gbase, 8 * PBF_RADIX);   // second halves: pbf_sort_pairs ALLOC(s->tile_counter, 4);
+    ALLOC(s->hist, 8 * PBF_RADIX); ALLOC(s->gbase, 8 * PBF_RADIX);   // second halves: pbf_sort_pairs
+    ALLOC(s->tile_counter, 4);
     ALLOC(s->status, (size_t)4 * s->max_tiles * PBF_RADIX);
     ALLOC(s->cells, s->ncell); ALLOC(s->runs3, s->ncell);
     ALLOC(s->bufA, cap); ALLOC(s->bufB, cap); ALLOC(s->svel, cap); ALLOC(s->vprime, cap); ALLOC(s->omega, cap);
@@ -213,6 +214,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     launch_fill_tables(s);   // start = -1 (gridtexture clear, src/NeighbourCellFinder.cpp:116-126), end = 0, runs empty
     for (int i = 0; i < 6; i++) cudaEventCreate(&s->ev[i]);
     e = cudaStreamSynchronize(s->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();   // a rejected memset / launch above is not sticky: ask explicitly
     if (e != cudaSuccess) {
         std::string m = std::string("pbf_create: ") + cudaGetErrorString(e);
         pbf_destroy(s);
