@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs.  The product package (pbf_b200) never imports this module.
-PARITY UNPINNED: see the header of pbf_oracle.c.
+PARITY PINNED against the reference's own shaders compiled by g++ (oracle/ref.py, tests/test_oracle_ref.py); see the
+header of pbf_oracle.c.
 """
 import ctypes as C
 import os

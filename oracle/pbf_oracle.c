@@ -5,11 +5,13 @@
  * file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it,
  * as the checker or as the reported CPU baseline -- never as the thing shipped.
  *
- * PARITY UNPINNED: the reference has no tests, golden vectors or fixtures of any kind, and its own
- * implementation of this path is GLSL 4.30 compute that cannot be compiled or run in this environment
- * (no GL/EGL/GLFW/glm/libpng).  This file is a line-by-line restatement of the shader
- * source; it is pinned only by analytic known-answer tests (tests/test_oracle.py) and by an independent
- * second restatement in NumPy (tests/golden/make_golden.py).
+ * PARITY PINNED by oracle/_ref: the reference has no tests or golden vectors of its own, and its GLSL cannot run here
+ * (no GL), but its compute shaders are plain C-like code: oracle/ref_harness.cpp compiles the files of
+ * /root/reference/shaders/{sph,radixsort,neighbourcellfinder} VERBATIM with g++ behind oracle/glsl_compat.h (work-group
+ * barriers as fibers) and runs them through SPH::Run's own dispatch sequence.  tests/test_oracle_ref.py checks this file
+ * against that library stage by stage and over whole runs -- bit for bit, floats included -- and against the golden files
+ * it minted (tests/golden/ref_*.npz: BASELINE configs[0] over 100 steps, the reference's own scene).  What remains a
+ * policy rather than reference behaviour is listed below ((ii), (iii) second sentence, (iv)).
  *
  * All arithmetic is IEEE binary32 in the source order of the GLSL, compiled with -ffp-contract=off.
  * Every function cites the reference file:line it follows (paths relative to /root/reference).

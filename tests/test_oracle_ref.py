@@ -1,0 +1,250 @@
+"""Pins the C oracle (oracle/pbf_oracle.c) to the REFERENCE'S OWN SOURCE TEXT.
+
+(1) Golden vectors minted by the reference's shaders compiled verbatim with g++ (tests/golden/make_ref_golden.py,
+    oracle/ref_harness.cpp): the oracle reproduces them BIT FOR BIT -- BASELINE configs[0] (32^3 particles, K = 3, 100
+    steps), the reference's own two-block scene, and a 4,096-particle scene with vorticity + XSPH.  These run anywhere.
+(2) Where oracle/_ref/libpbf_ref.so exists (built from /root/reference in this container, shipped prebuilt to the GPU
+    box), every stage of SPH::Run is compared live, shader against restatement, on the lattice scene and on the edge
+    scenes of tests/scenes.py: predictpos, the full 2-bit radix sort (counting / blockscan / addblocksum / globalsort with
+    their shared-memory scans run as fibers), findcells, neighbourcells, calclambda, updatepos, update, vorticity,
+    clearhighlight + highlight.  Integers and floats alike: bit exact.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import scenes
+from oracle import ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GRID = (128, 64, 128)
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).view(np.uint8).tobytes()).hexdigest()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def kinetic(vel):
+    v = vel[:, :3].astype(np.float64)
+    return float(0.5 * np.sum(v * v))
+
+
+# ---- (1) committed golden vectors of the reference ------------------------------------------------------------------------
+def test_oracle_reproduces_reference_c1_100_steps():
+    """BASELINE configs[0]: the golden run is the reference's GLSL (compiled by g++ instead of llvmpipe)."""
+    G = np.load(os.path.join(HERE, "golden", "ref_c1_trace.npz"))
+    pos, vel = oracle.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
+    sim = oracle.Sim(pos.shape[0], oracle.make_grid(*G["grid"].tolist(), ref_quirks=1))
+    P = oracle.default_params()
+    ke = []
+    for step in range(1, int(G["steps"]) + 1):
+        sim.step(pos, vel, P, int(G["iters"]), vorticity=bool(G["vorticity"]))
+        ke.append(kinetic(vel))
+        if step in (1, 10, 100):
+            assert digest(pos) == str(G["pos_sha_%d" % step]), step
+            assert digest(vel) == str(G["vel_sha_%d" % step]), step
+    assert np.array_equal(np.array(ke), G["kinetic_energy"])
+
+
+def test_oracle_reproduces_reference_two_block_scene():
+    """The reference's own scene and defaults (src/Simulation.cpp:200-246, K = 5, src/SPH.cpp:26)."""
+    G = np.load(os.path.join(HERE, "golden", "ref_reference_scene.npz"))
+    p1, v1 = oracle.dam_break(32, 32, 32)
+    p2, v2 = oracle.dam_break(32, 32, 32, origin=(32.5 + 63.0, 0.5, 32.5 + 63.0), mirror=True, id0=32768)
+    pos, vel = np.concatenate([p1, p2]), np.concatenate([v1, v2])
+    sim = oracle.Sim(pos.shape[0], oracle.make_grid(*GRID, ref_quirks=1))
+    P = oracle.default_params()
+    for step in range(1, 6):
+        sim.step(pos, vel, P, int(G["iters"]), vorticity=bool(G["vorticity"]))
+        if step in (1, 5):
+            assert digest(pos) == str(G["pos_sha_%d" % step]) and digest(vel) == str(G["vel_sha_%d" % step]), step
+
+
+def test_oracle_reproduces_reference_small_scene_with_vorticity():
+    G = np.load(os.path.join(HERE, "golden", "ref_small.npz"))
+    pos, vel = oracle.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
+    assert np.array_equal(bits(pos), bits(G["pos0"]))
+    g = oracle.make_grid(*G["grid"].tolist(), ref_quirks=1)
+    sim = oracle.Sim(pos.shape[0], g)
+    P = oracle.default_params()
+    ke = []
+    for step in range(1, 101):
+        sim.step(pos, vel, P, 3, vorticity=True)
+        ke.append(kinetic(vel))
+        if step == 1:
+            assert np.array_equal(bits(sim.sorted)[:, 3], bits(G["sorted1"])[:, 3])      # the permutation (positions moved on)
+            assert np.array_equal(sim.start, G["start1"])
+            # the golden run fetched out-of-grid cells as 0 (GL robust access), the oracle reads them as empty (-1): an EMPTY
+            # run over such a row is spelled (0, 0) there and (-1, 0) here; every other word is identical
+            packed = (sim.run_start.astype(np.int64) + (sim.run_count.astype(np.int64) << 24)).astype(np.int32)
+            same = packed == G["runs1"]
+            assert np.all(same | ((sim.run_count == 0) & (G["runs1"] == 0)))
+            assert same.mean() > 0.8
+        if step in (1, 10, 100):
+            assert np.array_equal(bits(pos), bits(G["pos%d" % step])), step
+            assert np.array_equal(bits(vel), bits(G["vel%d" % step])), step
+    assert np.array_equal(np.array(ke), G["kinetic_energy"])
+    # lambda of the first solver iteration of step 1
+    pos, vel = oracle.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
+    rec = oracle.predict(pos, vel, P, g)
+    srt, _ = oracle.sort(rec, g)
+    assert np.array_equal(bits(srt), bits(G["sorted1"]))
+    start, end = oracle.findcells(srt, g)
+    rs, rc = oracle.neighbourcells(srt, g, start, end)
+    lam, _ = oracle.calclambda(srt, rs, rc, P)
+    assert np.array_equal(bits(lam), bits(G["lambda1"]))
+
+
+# ---- (2) live, shader against restatement ------------------------------------------------------------------------------------
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libpbf_ref.so not built and no /root/reference to build it from")
+
+
+def stage_by_stage(pos, vel, grid, quirk_free_tables=False, extforce=False, highlight=None, oob=-1, iters=2, params=None):
+    """One SPH::Run, stage by stage, reference shader vs oracle function; everything bit exact."""
+    n = pos.shape[0]
+    g = oracle.make_grid(*grid, ref_quirks=1)
+    P = params or oracle.default_params()
+    r = ref.RefSim(n, grid)
+    r.set_params(P)
+    r.set_oob_fetch(oob)          # -1 = the oracle's policy (iv): an out-of-grid cell reads "empty"
+    r.set_extforce(extforce)
+    hl = np.zeros(n, np.uint32) if highlight is None else highlight.copy()
+    r.upload(pos, vel, hl)
+    assert r.numbits == oracle.sortbits(g) or r.numbits + 1 == oracle.sortbits(g)     # oracle counts 2-bit passes * 2
+    # K1
+    r.predict()
+    orec = oracle.predict(pos, vel, P, g, extforce)
+    assert np.array_equal(bits(r.records()), bits(orec)), "predictpos"
+    # RadixSort::Run
+    r.sort()
+    osorted, okeys = oracle.sort(orec, g)
+    assert np.array_equal(bits(r.records()), bits(osorted)), "radix sort"
+    # K6 (+ the one policy that is not reference behaviour: the end of the last occupied cell)
+    r.find_cells()
+    r.policy_define_last_end()
+    ostart, oend = oracle.findcells(osorted, g)
+    rstart, rend = r.grid_tables()
+    assert np.array_equal(rstart, ostart), "findcells start"
+    occ = ostart != -1
+    assert np.array_equal(rend[occ], oend[occ]), "findcells end"
+    # K7
+    r.neighbour_cells()
+    ors, orc = oracle.neighbourcells(osorted, g, ostart, oend)
+    packed, pad = r.packed_runs()
+    assert not pad.any()
+    if oob == -1:
+        opacked = (ors.astype(np.int64) + (orc.astype(np.int64) << 24)).astype(np.int32)
+        assert np.array_equal(packed, opacked), "neighbourcells"
+    else:                          # robust-access zeros: runs over out-of-grid rows decode as (0, 0) instead of (-1, 0)
+        cnt, st = packed >> 24, packed & 0xFFFFFF
+        live = orc > 0
+        assert np.array_equal(cnt[live], orc[live]) and np.array_equal(st[live], ors[live])
+    # K12
+    r.highlight()
+    ohl = hl.copy()
+    ohl &= 1
+    oracle.highlight(osorted, ors, orc, ohl)
+    assert np.array_equal(r.download()[2], ohl), "highlight"
+    # K x (K8, K9)
+    cur = osorted
+    for it in range(iters):
+        r.calclambda()
+        olam, _ = oracle.calclambda(cur, ors, orc, P)
+        assert np.array_equal(bits(r.lam()), bits(olam)), ("calclambda", it)
+        r.updatepos(ref.ORDER_JACOBI)
+        cur = oracle.updatepos(cur, ors, orc, olam, P, g)
+        assert np.array_equal(bits(r.records()), bits(cur)), ("updatepos", it)
+    # K10
+    r.update()
+    opos, ovel = pos.copy(), vel.copy()
+    oracle.update(cur, P, opos, ovel)
+    rp, rv, _ = r.download()
+    assert np.array_equal(bits(rp), bits(opos)) and np.array_equal(bits(rv), bits(ovel)), "update"
+    # K11
+    r.vorticity(ref.ORDER_JACOBI)
+    ow = oracle.vorticity(cur, ors, orc, P, ovel)
+    assert np.array_equal(bits(r.vort()), bits(ow)), "vorticity |omega|"
+    assert np.array_equal(bits(r.download()[1]), bits(ovel)), "vorticity velocity"
+    return r
+
+
+@needs_ref
+@pytest.mark.parametrize("extforce", [False, True])
+def test_every_stage_matches_the_reference_shaders_on_the_lattice(extforce):
+    pos, vel = oracle.dam_break(32, 32, 32)
+    vel[:, :3] = np.random.default_rng(3).normal(0, 2.0, (pos.shape[0], 3)).astype(np.float32)
+    hl = np.zeros(pos.shape[0], np.uint32)
+    hl[[7, 300, 20000]] = 1
+    hl[[8, 9]] = 2                      # stale marks: cleared by clearhighlight.glsl
+    hl[[11]] = 3
+    stage_by_stage(pos, vel, GRID, extforce=extforce, highlight=hl, iters=3)
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", ["sparse_gas", "clump", "escapees", "splash"])
+def test_every_stage_matches_the_reference_shaders_on_edge_scenes(scene):
+    """Almost-empty runs, 96-candidate runs (the 8-bit count of the packed word holds 127), particles outside the grid on
+    all six sides and on the y = gy plane, two blocks thrown at each other."""
+    pos, vel = getattr(scenes, scene)()
+    stage_by_stage(pos, vel, GRID)
+
+
+@needs_ref
+def test_robust_access_zero_fetches_are_equivalent_inside_the_walls():
+    """Policy (iv): the oracle reads an out-of-grid cell as empty; a GL driver with robust buffer access returns 0.  Inside
+    the walls (every BASELINE scene) the two differ only in how an EMPTY run is spelled."""
+    pos, vel = oracle.dam_break(32, 32, 32)
+    stage_by_stage(pos, vel, GRID, oob=0)
+
+
+@needs_ref
+def test_other_grid_and_parameters():
+    pos, vel = oracle.dam_break(24, 16, 16, origin=(20.5, 0.5, 18.5))
+    P = oracle.default_params()
+    P.one_over_rho_0, P.epsilon, P.timestep, P.tensile_instability_k, P.xsph_viscosity_c = 0.9, 3.0, 0.01, 0.2, 0.05
+    stage_by_stage(pos, vel, (100, 50, 90), params=P)
+
+
+@needs_ref
+def test_reference_schedule_dependence_exceeds_the_one_step_tolerance():
+    """updatepos.glsl updates in place while neighbours read (updatepos.glsl:53-55) and vorticity.glsl reads other work
+    groups' |omega| behind a group-local barrier: the reference's result depends on the GPU's schedule.  Jacobi (the
+    policy of the oracle and of the CUDA path) against one in-order schedule of the SAME shaders: after a single step the
+    two differ by MORE than the north star's one-step tolerance (1e-5 x 128 = 1.28e-3) -- the reference cannot meet that
+    tolerance against itself, so parity is defined against one fixed schedule, Jacobi.  The bulk
+    of the particles still agrees closely; both runs are equally valid outputs of the reference."""
+    pos, vel = oracle.dam_break(32, 32, 32)
+    out = []
+    for order in (ref.ORDER_JACOBI, ref.ORDER_AS_DISPATCHED):
+        r = ref.RefSim(pos.shape[0], GRID)
+        r.upload(pos, vel)
+        r.step(3, vorticity=True, order=order)
+        out.append(r.download())
+    d = np.abs(out[0][0] - out[1][0]).max(axis=1)
+    assert 1e-5 * 128 < d.max() < 0.1, d.max()
+    assert np.median(d) < 5e-3
+
+
+@needs_ref
+def test_whole_steps_live():
+    pos, vel = oracle.dam_break(16, 16, 32)
+    hl = np.zeros(pos.shape[0], np.uint32)
+    hl[[5, 100, 2000]] = 1
+    r = ref.RefSim(pos.shape[0], GRID)
+    r.upload(pos, vel, hl)
+    sim = oracle.Sim(pos.shape[0], oracle.make_grid(*GRID, ref_quirks=1))
+    P = oracle.default_params()
+    op, ov, oh = pos.copy(), vel.copy(), hl.copy()
+    for step in range(10):
+        r.step(4, vorticity=True)
+        sim.step(op, ov, P, 4, vorticity=True, highlight=oh)
+        rp, rv, rh = r.download()
+        assert np.array_equal(bits(rp), bits(op)) and np.array_equal(bits(rv), bits(ov)) and np.array_equal(rh, oh), step
+        assert np.array_equal(bits(r.vort()), bits(sim.vort)), step
