@@ -198,6 +198,10 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     ALLOC(s->flags, 4); ALLOC(s->diag, 2);
     ALLOC(s->tile_desc, plan_desc_ints(cap)); ALLOC(s->tile_runs, plan_run_words(cap));
 #undef ALLOC
+    if (sort_init() != 0) {
+        pbf_destroy(s);
+        return fail(PBF_ERR_CUDA, "pbf_create: the sort kernel needs 56 KB of opt-in shared memory per block");
+    }
     if (sweeps_init() != 0) {
         pbf_destroy(s);
         return fail(PBF_ERR_CUDA, "pbf_create: the sweep kernels need 90 KB of opt-in shared memory per block");

@@ -12,7 +12,7 @@
 typedef uint32_t u32;
 
 #define PBF_KEY_NOCELL 0x80000000u   // bit 31 of a cell key: the clamped cell lies outside the cell images
-#define PBF_RADIX 256
+#define PBF_RADIX 512   // digit slots of a sort pass (up to 9 bits per pass; sort.cu)
 
 // what the reference injects into every shader as GLSL header constants (src/SPH.cpp:28-60)
 struct GridInfo {
@@ -50,7 +50,7 @@ struct HaloPush {
 
 struct SortPlan {
     int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
-    int passes;      // 8-bit onesweep passes
+    int passes;      // onesweep passes of up to 9 bits
     int shift[4];
     u32 mask[4];
 };
@@ -181,6 +181,7 @@ void slab_free(pbf_sim *s);
 bool slab_borrows_stream(const pbf_sim *s);
 // sort.cu
 SortPlan make_sort_plan(int bits);
+int sort_init(void);                     // opt-in shared-memory size of the onesweep kernel (once per device)
 u32 sort_max_tiles(u32 cap);
 int launch_sort_scan(pbf_sim *s);
 int launch_sort_passes(pbf_sim *s);

@@ -2,11 +2,23 @@
 //
 // Replaces RadixSort::Run (reference src/RadixSort.cpp:124-200 and shaders/radixsort/*.glsl): the reference
 // sorts the 16-byte records themselves with 2 bits per pass (10-13 passes x 4 dispatches, ~60 B/particle/pass).
-// Here 8 bits per pass on 8-byte (key, index) pairs, one kernel per pass: warp-level digit ranking with
-// match.any, per-tile digit counts chained between tiles by decoupled look-back, and a shared-memory staged
-// scatter so that global stores are runs of consecutive addresses.  The result is the same permutation: a
-// STABLE sort on the low plan.bits bits of the key (globalsort.glsl:62-64 proves the reference is stable; bits
-// above plan.bits, e.g. the ceiling wrap of SURVEY.md a3, ride along unsorted exactly as in the reference).
+// Here up to 9 bits per pass on 8-byte (key, index) pairs, one kernel per pass: digit ranking inside a warp, per-tile
+// digit counts chained between tiles by decoupled look-back, and a shared-memory staged scatter so that global stores are
+// runs of consecutive addresses.  The result is the same permutation: a STABLE sort on the low plan.bits bits of the key
+// (globalsort.glsl:62-64 proves the reference is stable; bits above plan.bits, e.g. the ceiling wrap of SURVEY.md a3,
+// ride along unsorted exactly as in the reference).
+//
+// Digit widths: the sorted bits are split evenly over ceil(bits / 9) passes -- 26 bits (512 x 256 x 512 cells, the
+// headline grid) = 9 + 9 + 8, i.e. THREE passes whose digits are exactly the cell's x, z and y; 20 and 23 bits take three
+// passes of 7 and 8 bits; only grids beyond 2^27 cells need a fourth.
+//
+// Ranking inside a warp.  Lanes hold consecutive elements, and cell keys of consecutive elements are either equal in a
+// digit (the x and z passes of a lattice: whole warps share one digit) or increasing (the y pass: 32 lanes, ~30 distinct
+// digits -- the case in which match.any, which loops over the distinct values, cost 2.4x a normal pass).  Equal digits
+// therefore sit in RUNS of neighbouring lanes: one ballot of the run heads gives every lane its run and its place in it,
+// the head lane adds the run length to the warp's digit counter.  That is only valid if no two runs of the warp share a
+// digit; the heads check by writing their lane number into a per-digit slot and reading it back, and a warp that finds a
+// clash ranks that one item with match.any instead (random keys, e.g. pbf_sort_pairs on arbitrary input, always do).
 //
 // Algorithmic traffic: 4 B/particle for the digit histograms (read back from L2 right after k_predict wrote the keys)
 // and 16 B per pass.
@@ -14,29 +26,44 @@
 
 namespace {
 
-constexpr int SORT_BLOCK = 256;                   // = PBF_RADIX, one thread per digit in the look-back
+constexpr int SORT_BLOCK = 256;
 #ifndef PBF_SORT_ITEMS
 #define PBF_SORT_ITEMS 16
 #endif
 #ifndef PBF_SORT_CTAS
-#define PBF_SORT_CTAS 4      // 64 registers, no spills: 4 blocks per SM instead of 3 (0.288 vs 0.300 ms for the four passes)
+#define PBF_SORT_CTAS 4      // 64 registers, no spills: 4 blocks per SM instead of 3 (0.288 vs 0.300 ms for four 8-bit passes)
 #endif
 constexpr int SORT_ITEMS = PBF_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_BLOCK * SORT_ITEMS;  // 4096 pairs per tile
 constexpr int SORT_WARPS = SORT_BLOCK / 32;
+constexpr int R = PBF_RADIX;                       // 512: digit slots per pass (a pass may use fewer)
+static_assert(R == 2 * SORT_BLOCK, "the look-back handles two digits per thread");
 
 constexpr u32 ST_AGG = 1u << 30;                  // tile aggregate published
 constexpr u32 ST_PREFIX = 2u << 30;               // inclusive prefix published
 constexpr u32 ST_VALUE = (1u << 30) - 1;
 
+// shared memory of k_onesweep (dynamic: 52 KB, above the 48 KB a static allocation may have; four blocks per SM fit)
+struct SortSmem {
+    u32 wh[SORT_WARPS][R];        // per-warp digit counts, then exclusive offsets over warps
+    u32 dstart[R];                // first tile-local slot of each digit
+    u32 goff[R];                  // global slot of tile-local slot 0 of each digit
+    u32 keys[SORT_TILE];          // staging; during the ranking its first 4 KB hold the clash-detection slots
+    u32 vals[SORT_TILE];
+    u32 wsum[2][SORT_WARPS];
+    u32 tile;
+};
+static_assert(sizeof(u32) * SORT_TILE >= (size_t)SORT_WARPS * R, "the clash-detection slots alias the key staging area");
+static_assert(4 * (sizeof(SortSmem) + 1024) <= 233472, "four blocks per SM");
+
 // exclusive scan of the per-pass digit histograms -> global digit bases; clears the histograms and the tile
 // counters for the next step.
-__global__ void __launch_bounds__(PBF_RADIX) k_sort_scan(u32 *__restrict__ hist, u32 *__restrict__ gbase,
-                                                          u32 *__restrict__ tile_counter) {
-    __shared__ u32 wsum[PBF_RADIX / 32];
+__global__ void __launch_bounds__(R) k_sort_scan(u32 *__restrict__ hist, u32 *__restrict__ gbase,
+                                                  u32 *__restrict__ tile_counter) {
+    __shared__ u32 wsum[R / 32];
     const int pass = blockIdx.x, d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    u32 c = hist[pass * PBF_RADIX + d];
-    hist[pass * PBF_RADIX + d] = 0;
+    u32 c = hist[pass * R + d];
+    hist[pass * R + d] = 0;
     u32 inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -47,9 +74,9 @@ __global__ void __launch_bounds__(PBF_RADIX) k_sort_scan(u32 *__restrict__ hist,
     __syncthreads();
     u32 base = 0;
 #pragma unroll
-    for (int w = 0; w < PBF_RADIX / 32; w++)
+    for (int w = 0; w < R / 32; w++)
         if (w < warp) base += wsum[w];
-    gbase[pass * PBF_RADIX + d] = base + inc - c;
+    gbase[pass * R + d] = base + inc - c;
     if (d == 0) tile_counter[pass] = 0;
 }
 
@@ -58,8 +85,8 @@ __global__ void __launch_bounds__(PBF_RADIX) k_sort_scan(u32 *__restrict__ hist,
 // keys and run-length encodes each digit stream in registers, one shared atomic per run.
 __global__ void __launch_bounds__(256) k_sort_hist(const u32 *__restrict__ keys, u32 n, SortPlan plan,
                                                     u32 *__restrict__ hist) {
-    __shared__ u32 sh[4 * PBF_RADIX];
-    for (int i = threadIdx.x; i < 4 * PBF_RADIX; i += blockDim.x) sh[i] = 0;
+    __shared__ u32 sh[4 * R];
+    for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u32 chunks = (n + 15u) >> 4;
     for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < chunks; c += gridDim.x * blockDim.x) {
@@ -87,16 +114,16 @@ __global__ void __launch_bounds__(256) k_sort_hist(const u32 *__restrict__ keys,
                 for (int j = 1; j < 16; j++) {
                     const u32 d = (k[j] >> sft) & msk;
                     if (j < cnt) {
-                        if (d != cur) { atomicAdd(&sh[p * PBF_RADIX + cur], run); cur = d; run = 0; }
+                        if (d != cur) { atomicAdd(&sh[p * R + cur], run); cur = d; run = 0; }
                         run++;
                     }
                 }
-                atomicAdd(&sh[p * PBF_RADIX + cur], run);
+                atomicAdd(&sh[p * R + cur], run);
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < plan.passes * PBF_RADIX; i += blockDim.x)
+    for (int i = threadIdx.x; i < plan.passes * R; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
@@ -105,21 +132,16 @@ __global__ void __launch_bounds__(SORT_BLOCK, PBF_SORT_CTAS)
 k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32 *__restrict__ keys_out,
            u32 *__restrict__ vals_out, u32 n, int shift, u32 dmask, const u32 *__restrict__ gbase,
            u32 *status, u32 *tile_counter) {
-    __shared__ u32 s_wh[SORT_WARPS][PBF_RADIX];   // per-warp digit counts, then exclusive offsets over warps
-    __shared__ u32 s_dstart[PBF_RADIX];           // first tile-local slot of each digit
-    __shared__ u32 s_goff[PBF_RADIX];             // global slot of tile-local slot 0 of each digit
-    __shared__ u32 s_keys[SORT_TILE];
-    __shared__ u32 s_vals[SORT_TILE];
-    __shared__ u32 s_wsum[SORT_WARPS];
-    __shared__ u32 s_tile;
+    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+    SortSmem &S = *reinterpret_cast<SortSmem *>(sort_smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // tiles are handed out in launch order so that every tile a look-back waits on is already resident
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; w++) s_wh[w][tid] = 0;
+    for (int w = 0; w < SORT_WARPS; w++) { S.wh[w][tid] = 0; S.wh[w][tid + SORT_BLOCK] = 0; }
     __syncthreads();
-    const u32 tile = s_tile;
+    const u32 tile = S.tile;
     const u32 base = tile * SORT_TILE;
     if (base >= n) return;
 
@@ -132,69 +154,105 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
         key[i] = idx < n ? __ldg(keys_in + idx) : 0xffffffffu;
     }
 
-    // rank inside the warp, in element order: lanes holding the same digit find each other with match.any
-    const u32 lt = (1u << lane) - 1u;
-    unsigned short rank[SORT_ITEMS];
+    // rank inside the warp, in element order (see the header: runs of equal digits in neighbouring lanes)
+    const u32 le = 0xffffffffu >> (31 - lane);          // lanes 0..lane
+    u32 rank2[SORT_ITEMS / 2];                        // two 16-bit ranks per register
+    u32 *wh = S.wh[warp];
+    volatile unsigned char *own = reinterpret_cast<unsigned char *>(S.keys) + warp * R;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
-        u32 idx = wbase + i * 32;
-        u32 d = idx < n ? ((key[i] >> shift) & dmask) : dmask;   // padding ranks after all real keys
-        u32 m = __match_any_sync(0xffffffffu, d);
-        int leader = __ffs(m) - 1;
-        u32 prev = 0;
-        if (lane == leader) {
-            prev = s_wh[warp][d];
-            s_wh[warp][d] = prev + __popc(m);
+        const u32 idx = wbase + i * 32;
+        const u32 d = idx < n ? ((key[i] >> shift) & dmask) : dmask;   // padding ranks after all real keys
+        const u32 dprev = __shfl_up_sync(0xffffffffu, d, 1);
+        const bool head = lane == 0 || d != dprev;
+        const u32 heads = __ballot_sync(0xffffffffu, head);
+        const int start = 31 - __clz(heads & le);                       // my run's first lane
+        const u32 above = heads & ~le;
+        const int end = above ? __ffs(above) - 1 : 32;                  // one past my run's last lane
+        if (head) own[d] = (unsigned char)lane;
+        __syncwarp();
+        const bool clash = head && own[d] != (unsigned char)lane;       // another run of this warp holds the same digit
+        u32 prev = 0, rk;
+        if (!__any_sync(0xffffffffu, clash)) {
+            if (head) {
+                prev = wh[d];
+                wh[d] = prev + (u32)(end - start);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, start);
+            rk = prev + (u32)(lane - start);
+        } else {
+            const u32 m = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) {
+                prev = wh[d];
+                wh[d] = prev + __popc(m);
+            }
+            prev = __shfl_sync(0xffffffffu, prev, leader);
+            rk = prev + __popc(m & (le >> 1));
         }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[i] = (unsigned short)(prev + __popc(m & lt));
+        if (i & 1) rank2[i >> 1] |= rk << 16;
+        else rank2[i >> 1] = rk;
         __syncwarp();
     }
     __syncthreads();
 
-    // one thread per digit: offsets over warps, tile count, decoupled look-back over earlier tiles
+    // one thread per digit pair (d0 = tid, d1 = tid + 256): offsets over warps, tile count, decoupled look-back
     {
-        const int d = tid;
-        u32 run = 0;
+        const int d0 = tid, d1 = tid + SORT_BLOCK;
+        u32 run0 = 0, run1 = 0;
 #pragma unroll
         for (int w = 0; w < SORT_WARPS; w++) {
-            u32 t = s_wh[w][d];
-            s_wh[w][d] = run;
-            run += t;
+            const u32 t0 = S.wh[w][d0], t1 = S.wh[w][d1];
+            S.wh[w][d0] = run0; S.wh[w][d1] = run1;
+            run0 += t0; run1 += t1;
         }
-        const u32 count = run;
+        const u32 count0 = run0, count1 = run1;
+        const bool two = dmask >= (u32)SORT_BLOCK;       // digits above 255 exist in this pass
         volatile u32 *st = status;
-        u32 excl = 0;
+        u32 excl0 = 0, excl1 = 0;
         if (tile == 0) {
-            st[d] = ST_PREFIX | count;
+            st[d0] = ST_PREFIX | count0;
+            if (two) st[d1] = ST_PREFIX | count1;
         } else {
-            st[(size_t)tile * PBF_RADIX + d] = ST_AGG | count;
-            int t = (int)tile - 1;
-            while (true) {
-                u32 sv;
-                do { sv = st[(size_t)t * PBF_RADIX + d]; } while ((sv >> 30) == 0);
-                excl += sv & ST_VALUE;
-                if ((sv >> 30) == 2) break;
-                t--;
+            st[(size_t)tile * R + d0] = ST_AGG | count0;
+            if (two) st[(size_t)tile * R + d1] = ST_AGG | count1;
+            int t0 = (int)tile - 1, t1 = two ? t0 : -1;
+            while (t0 >= 0 || t1 >= 0) {                 // both chains advance in the same loop: their loads overlap
+                u32 s0 = 0, s1 = 0;
+                if (t0 >= 0) s0 = st[(size_t)t0 * R + d0];
+                if (t1 >= 0) s1 = st[(size_t)t1 * R + d1];
+                if (t0 >= 0 && (s0 >> 30) != 0) {
+                    excl0 += s0 & ST_VALUE;
+                    t0 = (s0 >> 30) == 2 ? -1 : t0 - 1;
+                }
+                if (t1 >= 0 && (s1 >> 30) != 0) {
+                    excl1 += s1 & ST_VALUE;
+                    t1 = (s1 >> 30) == 2 ? -1 : t1 - 1;
+                }
             }
-            st[(size_t)tile * PBF_RADIX + d] = ST_PREFIX | (excl + count);
+            st[(size_t)tile * R + d0] = ST_PREFIX | (excl0 + count0);
+            if (two) st[(size_t)tile * R + d1] = ST_PREFIX | (excl1 + count1);
         }
-        // exclusive scan of the digit counts inside the tile
-        u32 inc = count;
+        // exclusive scan of the 512 digit counts inside the tile: digits 0..255 over the threads, then 256..511
+        u32 inc0 = count0, inc1 = count1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            u32 t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            const u32 a = __shfl_up_sync(0xffffffffu, inc0, o), b = __shfl_up_sync(0xffffffffu, inc1, o);
+            if (lane >= o) { inc0 += a; inc1 += b; }
         }
-        if (lane == 31) s_wsum[warp] = inc;
+        if (lane == 31) { S.wsum[0][warp] = inc0; S.wsum[1][warp] = inc1; }
         __syncthreads();
-        u32 wb = 0;
+        u32 wb0 = 0, wb1 = 0, total0 = 0;
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; w++)
-            if (w < warp) wb += s_wsum[w];
-        const u32 dstart = wb + inc - count;
-        s_dstart[d] = dstart;
-        s_goff[d] = __ldg(gbase + d) + excl - dstart;
+        for (int w = 0; w < SORT_WARPS; w++) {
+            if (w < warp) { wb0 += S.wsum[0][w]; wb1 += S.wsum[1][w]; }
+            total0 += S.wsum[0][w];
+        }
+        const u32 ds0 = wb0 + inc0 - count0, ds1 = total0 + wb1 + inc1 - count1;
+        S.dstart[d0] = ds0;
+        S.dstart[d1] = ds1;
+        S.goff[d0] = __ldg(gbase + d0) + excl0 - ds0;
+        S.goff[d1] = two ? __ldg(gbase + d1) + excl1 - ds1 : 0u;
     }
     __syncthreads();
 
@@ -203,39 +261,39 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
     for (int i = 0; i < SORT_ITEMS; i++) {
         u32 idx = wbase + i * 32;
         u32 d = idx < n ? ((key[i] >> shift) & dmask) : dmask;
-        u32 slot = s_dstart[d] + s_wh[warp][d] + rank[i];
-        s_keys[slot] = key[i];
-        s_vals[slot] = IOTA ? idx : (idx < n ? __ldg(vals_in + idx) : 0u);
+        u32 slot = S.dstart[d] + S.wh[warp][d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+        S.keys[slot] = key[i];
+        S.vals[slot] = IOTA ? idx : (idx < n ? __ldg(vals_in + idx) : 0u);
     }
     __syncthreads();
 
     const u32 tile_n = min((u32)SORT_TILE, n - base);
 #pragma unroll 4
     for (u32 slot = tid; slot < tile_n; slot += SORT_BLOCK) {
-        u32 k = s_keys[slot];
-        u32 dst = s_goff[(k >> shift) & dmask] + slot;
+        u32 k = S.keys[slot];
+        u32 dst = S.goff[(k >> shift) & dmask] + slot;
         keys_out[dst] = k;
-        vals_out[dst] = s_vals[slot];
+        vals_out[dst] = S.vals[slot];
     }
 }
 
 int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, const u32 *gbase) {
     const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
     if (tiles == 0) return 0;
-    cudaMemsetAsync(s->status, 0, (size_t)plan.passes * tiles * PBF_RADIX * sizeof(u32), s->stream);
+    cudaMemsetAsync(s->status, 0, (size_t)plan.passes * tiles * R * sizeof(u32), s->stream);
     int launched = 0;
     for (int p = 0; p < plan.passes; p++) {
         const u32 *ki = p == 0 ? kin : s->ktmp[(p - 1) & 1];
         const u32 *vi = p == 0 ? vin : s->vtmp[(p - 1) & 1];
         u32 *ko = p == plan.passes - 1 ? kout : s->ktmp[p & 1];
         u32 *vo = p == plan.passes - 1 ? vout : s->vtmp[p & 1];
-        u32 *st = s->status + (size_t)p * tiles * PBF_RADIX;
+        u32 *st = s->status + (size_t)p * tiles * R;
         if (p == 0 && vin == nullptr)
-            k_onesweep<true><<<tiles, SORT_BLOCK, 0, s->stream>>>(ki, nullptr, ko, vo, n, plan.shift[p], plan.mask[p],
-                                                                  gbase + p * PBF_RADIX, st, s->tile_counter + p);
+            k_onesweep<true><<<tiles, SORT_BLOCK, sizeof(SortSmem), s->stream>>>(ki, nullptr, ko, vo, n, plan.shift[p], plan.mask[p],
+                                                                                 gbase + p * R, st, s->tile_counter + p);
         else
-            k_onesweep<false><<<tiles, SORT_BLOCK, 0, s->stream>>>(ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
-                                                                   gbase + p * PBF_RADIX, st, s->tile_counter + p);
+            k_onesweep<false><<<tiles, SORT_BLOCK, sizeof(SortSmem), s->stream>>>(ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
+                                                                                  gbase + p * R, st, s->tile_counter + p);
         launched++;
     }
     return launched;
@@ -243,14 +301,23 @@ int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin,
 
 }  // namespace
 
+int sort_init(void) {
+    cudaError_t e = cudaFuncSetAttribute(k_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_onesweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+    return e == cudaSuccess ? 0 : -1;
+}
+
 SortPlan make_sort_plan(int bits) {
     SortPlan plan{};
     plan.bits = bits;
-    plan.passes = (bits + 7) / 8;
+    plan.passes = (bits + 8) / 9;                       // up to 9 bits per pass ...
+    const int width = (bits + plan.passes - 1) / plan.passes;   // ... spread evenly: 26 -> 9 + 9 + 8
+    int at = 0;
     for (int p = 0; p < plan.passes; p++) {
-        int nb = bits - 8 * p < 8 ? bits - 8 * p : 8;
-        plan.shift[p] = 8 * p;
+        const int nb = bits - at < width ? bits - at : width;
+        plan.shift[p] = at;
         plan.mask[p] = (1u << nb) - 1u;
+        at += nb;
     }
     return plan;
 }
@@ -258,7 +325,7 @@ SortPlan make_sort_plan(int bits) {
 u32 sort_max_tiles(u32 cap) { return (cap + SORT_TILE - 1) / SORT_TILE; }
 
 int launch_sort_scan(pbf_sim *s) {
-    k_sort_scan<<<s->plan.passes, PBF_RADIX, 0, s->stream>>>(s->hist, s->gbase, s->tile_counter);
+    k_sort_scan<<<s->plan.passes, R, 0, s->stream>>>(s->hist, s->gbase, s->tile_counter);
     return 1;
 }
 
@@ -275,7 +342,7 @@ int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n) {
     if (blocks < 1) blocks = 1;
     // the histograms are accumulated with atomics: start from zero whatever ran before (pbf_predict twice, pbf_predict
     // followed by pbf_step, ... -- k_sort_scan also clears them, but only when a sort follows)
-    cudaMemsetAsync(s->hist, 0, 4 * PBF_RADIX * sizeof(u32), s->stream);
+    cudaMemsetAsync(s->hist, 0, 4 * R * sizeof(u32), s->stream);
     k_sort_hist<<<blocks, 256, 0, s->stream>>>(keys, n, s->plan, s->hist);
     return 1;
 }
@@ -288,9 +355,9 @@ int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32
     if (blocks < 1) blocks = 1;
     // own histogram / digit-base scratch (second half of the allocations): a standalone sort between pbf_predict and
     // pbf_sort must not disturb the histograms the simulation's sort is about to scan
-    u32 *hist = s->hist + 4 * PBF_RADIX, *gbase = s->gbase + 4 * PBF_RADIX;
-    cudaMemsetAsync(hist, 0, 4 * PBF_RADIX * sizeof(u32), s->stream);
+    u32 *hist = s->hist + 4 * R, *gbase = s->gbase + 4 * R;
+    cudaMemsetAsync(hist, 0, 4 * R * sizeof(u32), s->stream);
     k_sort_hist<<<blocks, 256, 0, s->stream>>>(kin, n, plan, hist);
-    k_sort_scan<<<plan.passes, PBF_RADIX, 0, s->stream>>>(hist, gbase, s->tile_counter);
+    k_sort_scan<<<plan.passes, R, 0, s->stream>>>(hist, gbase, s->tile_counter);
     return 2 + run_passes(s, plan, kin, vin, kout, vout, n, gbase);
 }
