@@ -46,8 +46,7 @@ int enqueue_step(pbf_sim *s, bool with_events, cudaEvent_t pos_ready = nullptr) 
     if (with_events) cudaEventRecord(s->ev[0], st);
     // [predict] :247-261   (+ reset of last step's cell starts, + histograms, + clearhighlight)
     cudaMemsetAsync(s->flags, 0, sizeof(u32), st);
-    k += launch_unclear_cells(s);
-    k += launch_predict(s);
+    k += launch_predict(s);            // also resets the cell-table entries the previous step wrote
     if (with_events) cudaEventRecord(s->ev[1], st);
     // [sort] :263-268
     k += launch_sort_scan(s);
@@ -64,16 +63,18 @@ int enqueue_step(pbf_sim *s, bool with_events, cudaEvent_t pos_ready = nullptr) 
         s->ev_solver.resize(2 * K + 1, nullptr);
         for (size_t i = have; i < s->ev_solver.size(); i++) cudaEventCreate(&s->ev_solver[i]);
     }
+    // K10 (update.glsl) runs in the epilogue of the LAST delta-p sweep (sweeps.cu); PBF_SEPARATE_UPDATE=1 keeps it apart
+    const bool fuse_update = K > 0 && s->fuse_update;
     for (int it = 0; it < K; it++) {
         if (with_events) cudaEventRecord(s->ev_solver[2 * it], st);
         k += launch_lambda(s);
         if (with_events) cudaEventRecord(s->ev_solver[2 * it + 1], st);
-        k += launch_delta_p(s);
+        k += (fuse_update && it == K - 1) ? launch_delta_p_update(s) : launch_delta_p(s);
     }
     if (with_events) { cudaEventRecord(s->ev_solver[2 * K], st); s->ev_solver_iters = K; }
     if (with_events) cudaEventRecord(s->ev[4], st);
     // [vorticity] :315-333
-    k += launch_update(s);
+    if (!fuse_update) k += launch_update(s);
     if (pos_ready) cudaEventRecord(pos_ready, st);
     if (s->params.vorticity_confinement) k += launch_vorticity(s);
     if (with_events) cudaEventRecord(s->ev[5], st);
@@ -167,6 +168,8 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     s->grid.bx = bx; s->grid.bz = bz;
     s->grid.zoff = 0; s->grid.gz_global = cfg->grid[2];
     s->plan = make_sort_plan(sortbits);
+    const char *su = getenv("PBF_SEPARATE_UPDATE");
+    s->fuse_update = !(su && su[0] == '1');
     const char *gs = getenv("PBF_GENERAL_SWEEPS");
     s->tiled_sweeps = !(gs && gs[0] == '1');
     pbf_default_params(&s->params);
@@ -537,9 +540,8 @@ int pbf_sync(pbf_handle s) {
 int pbf_predict(pbf_handle s) {
     STAGE_PROLOGUE(0, "pbf_predict");
     cudaMemsetAsync(s->flags, 0, sizeof(u32), s->stream);
-    s->launches += launch_unclear_cells(s);
+    s->launches += launch_predict(s);   // also resets the cell-table entries the previous step wrote
     s->n_prev_sorted = 0;   // table is clean until pbf_build_cells refills it
-    s->launches += launch_predict(s);
     PBF_CUDA(cudaGetLastError());
     s->stage = 1;
     return PBF_OK;

@@ -107,8 +107,15 @@ __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bo
     q.dx = make_float2(p.x - c.x.x, p.x - c.x.y);
     q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
     q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
+#ifdef PBF_SWEEP_SEPARATE_TINY
     q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));
     const float2 re = __fadd2_rn(q.r2, make_float2(TINY, TINY));
+#else
+    // TINY rides in the first multiply-add of the squared distance (one packed op fewer on the FP32 pipe): it is
+    // absorbed by rounding unless the two particles coincide to within 1e-12
+    q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __ffma2_rn(q.dx, q.dx, make_float2(TINY, TINY))));
+    const float2 re = q.r2;
+#endif
     const float2 rc = make_float2(fminf(v0 ? re.x : FAR2, H2), fminf(v1 ? re.y : FAR2, H2));
     q.il = make_float2(rsqrt_ftz(rc.x), rsqrt_ftz(rc.y));
     q.t2 = __ffma2_rn(rc, q.il, make_float2(-H, -H));                // l - h: 0 at and beyond the support radius

@@ -87,6 +87,7 @@ struct pbf_sim {
     // plan of the tiled sweeps (sweeps.cu): per 256-particle tile the nine sorted-index ranges that hold all its
     // candidates, per particle its nine neighbour runs relative to the tile's shared-memory image
     int *tile_desc; u32 *tile_runs;
+    bool fuse_update;                     // update.glsl in the epilogue of the last delta-p sweep (env PBF_SEPARATE_UPDATE=1: own kernel)
     bool tiled_sweeps;                    // false (env PBF_GENERAL_SWEEPS=1, debugging): every tile takes the general path
     // solver state in sorted order
     float4 *bufA;                         // {x,y,z,-}   positions (Jacobi ping)
@@ -159,6 +160,7 @@ int launch_reorder_cells(pbf_sim *s);
 int launch_highlight(pbf_sim *s);
 int launch_lambda(pbf_sim *s, const HaloPush *push = nullptr);
 int launch_delta_p(pbf_sim *s, const HaloPush *push = nullptr);
+int launch_delta_p_update(pbf_sim *s);   // sweeps.cu: last iteration, K10 fused into the epilogue
 int launch_update(pbf_sim *s);
 int launch_vorticity(pbf_sim *s);
 int launch_vorticity_a(pbf_sim *s, const HaloPush *push = nullptr);

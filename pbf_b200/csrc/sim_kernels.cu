@@ -28,11 +28,33 @@ __device__ __forceinline__ u32 cell_key(float x, float y, float z, const GridInf
     return k;
 }
 
+// Reset what the previous step wrote into the cell tables (replaces the per-step clear of the whole start image,
+// src/NeighbourCellFinder.cpp:116-126: 4 B per previously sorted particle instead of 4 B per cell).  i = a sorted slot of
+// the previous step.
+__device__ __forceinline__ void unclear_slot(u32 i, const u32 *__restrict__ skey, int2 *__restrict__ cells,
+                                             int2 *__restrict__ runs3, const GridInfo &g) {
+    const u32 k = skey[i];
+    if (!(k & PBF_KEY_NOCELL) && (i == 0 || skey[i - 1] != k)) {
+        cells[k].x = -1;
+        const int x = (int)(k % (u32)g.gx);
+        const int2 empty = make_int2(-1, 0);
+        if (x > 0) runs3[k - 1] = empty;
+        runs3[k] = empty;
+        if (x + 1 < g.gx) runs3[k + 1] = empty;
+    }
+    if (i == 0 && g.ref_quirks) { runs3[0] = make_int2(-1, 0); if (g.gx > 1) runs3[1] = make_int2(-1, 0); }
+}
+
 // ---- K1 predictpos.glsl:18-38 + cell key + clearhighlight.glsl: one particle per thread, pure streaming --------------
+// UNCLEAR: thread j also resets the table entries of the previous step's sorted slot j (the two jobs share nothing but the
+// launch: the scattered resets hide under the streaming loads).
+template <bool UNCLEAR>
 __global__ void __launch_bounds__(256)
 k_predict(u32 first, u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
-          float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ flags, GridInfo g, SimParams P) {
+          float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ flags, GridInfo g, SimParams P,
+          u32 n_prev, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (UNCLEAR && j < n_prev) unclear_slot(j, skey, cells, runs3, g);
     bool any_hl = false;
     if (j < n) {
         const u32 i = first + j;
@@ -74,23 +96,10 @@ __global__ void __launch_bounds__(256) k_fill_tables(size_t ncell, int2 *__restr
     runs3[c] = make_int2(-1, 0);
 }
 
-// Reset what the previous step wrote (replaces the per-step clear of the whole start image: 4 B per previously
-// sorted particle instead of 4 B per cell).
 __global__ void __launch_bounds__(256)
 k_unclear_cells(u32 n, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3, GridInfo g) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u32 k = skey[i];
-    if (k & PBF_KEY_NOCELL) return;
-    if (i == 0 || skey[i - 1] != k) {
-        cells[k].x = -1;
-        const int x = (int)(k % (u32)g.gx);
-        const int2 empty = make_int2(-1, 0);
-        if (x > 0) runs3[k - 1] = empty;
-        runs3[k] = empty;
-        if (x + 1 < g.gx) runs3[k + 1] = empty;
-    }
-    if (i == 0 && g.ref_quirks) { runs3[0] = make_int2(-1, 0); if (g.gx > 1) runs3[1] = make_int2(-1, 0); }
+    if (i < n) unclear_slot(i, skey, cells, runs3, g);
 }
 
 // packed unclamped cell of a position (neighbourcells.glsl:57 `ivec3(pos)`), each coordinate saturated to [-2, g+1]
@@ -315,13 +324,19 @@ int launch_unclear_cells(pbf_sim *s) {
 
 int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist) {
     if (count == 0) return 0;
-    k_predict<<<nblocks(count, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
-                                                          s->grid, sim_params(s));
+    k_predict<false><<<nblocks(count, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                                 s->grid, sim_params(s), 0u, nullptr, nullptr, nullptr);
     // digit histograms of all sort passes: the keys just written are still in L2
     return 1 + (with_hist ? launch_sort_hist(s, s->keys + first, count) : 0);
 }
 
-int launch_predict(pbf_sim *s) { return launch_predict_range(s, 0, s->n, true); }
+// whole-handle predict of the single-domain step: also undoes the previous step's cell-table writes (launch_unclear_cells)
+int launch_predict(pbf_sim *s) {
+    const u32 np = s->n_prev_sorted, m = s->n > np ? s->n : np;
+    k_predict<true><<<nblocks(m, 256), 256, 0, s->stream>>>(0u, s->n, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags, s->grid,
+                                                            sim_params(s), np, s->skey, s->cells, s->runs3);
+    return 1 + launch_sort_hist(s, s->keys, s->n);
+}
 
 int launch_keys_only(pbf_sim *s, u32 first, u32 count) {
     if (count == 0) return 0;

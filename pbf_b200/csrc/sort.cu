@@ -17,8 +17,9 @@
 // digits -- the case in which match.any, which loops over the distinct values, cost 2.4x a normal pass).  Equal digits
 // therefore sit in RUNS of neighbouring lanes: one ballot of the run heads gives every lane its run and its place in it,
 // the head lane adds the run length to the warp's digit counter.  That is only valid if no two runs of the warp share a
-// digit; the heads check by writing their lane number into a per-digit slot and reading it back, and a warp that finds a
-// clash ranks that one item with match.any instead (random keys, e.g. pbf_sort_pairs on arbitrary input, always do).
+// digit, which is certain when the digits do not decrease from lane to lane (one vote); a warp whose digits do ranks that
+// one item with match.any instead (random keys, e.g. pbf_sort_pairs on arbitrary input, almost always do).  A warp that
+// holds a single digit keeps that digit's count in a register from item to item.
 //
 // Algorithmic traffic: 4 B/particle for the digit histograms (read back from L2 right after k_predict wrote the keys)
 // and 16 B per pass.
@@ -48,12 +49,11 @@ struct SortSmem {
     u32 wh[SORT_WARPS][R];        // per-warp digit counts, then exclusive offsets over warps
     u32 dstart[R];                // first tile-local slot of each digit
     u32 goff[R];                  // global slot of tile-local slot 0 of each digit
-    u32 keys[SORT_TILE];          // staging; during the ranking its first 4 KB hold the clash-detection slots
+    u32 keys[SORT_TILE];
     u32 vals[SORT_TILE];
     u32 wsum[2][SORT_WARPS];
     u32 tile;
 };
-static_assert(sizeof(u32) * SORT_TILE >= (size_t)SORT_WARPS * R, "the clash-detection slots alias the key staging area");
 static_assert(4 * (sizeof(SortSmem) + 1024) <= 233472, "four blocks per SM");
 
 // exclusive scan of the per-pass digit histograms -> global digit bases; clears the histograms and the tile
@@ -158,7 +158,10 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
     const u32 le = 0xffffffffu >> (31 - lane);          // lanes 0..lane
     u32 rank2[SORT_ITEMS / 2];                        // two 16-bit ranks per register
     u32 *wh = S.wh[warp];
-    volatile unsigned char *own = reinterpret_cast<unsigned char *>(S.keys) + warp * R;
+    // A whole warp often holds ONE digit for several items in a row (the x and z passes of a lattice): that digit's count
+    // is then kept in a register (cd = the digit, cc = its count so far; both warp-uniform) and shared memory is only
+    // touched when the digit changes.
+    u32 cd = 0xffffffffu, cc = 0;
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
         const u32 idx = wbase + i * 32;
@@ -166,34 +169,50 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
         const u32 dprev = __shfl_up_sync(0xffffffffu, d, 1);
         const bool head = lane == 0 || d != dprev;
         const u32 heads = __ballot_sync(0xffffffffu, head);
-        const int start = 31 - __clz(heads & le);                       // my run's first lane
-        const u32 above = heads & ~le;
-        const int end = above ? __ffs(above) - 1 : 32;                  // one past my run's last lane
-        if (head) own[d] = (unsigned char)lane;
-        __syncwarp();
-        const bool clash = head && own[d] != (unsigned char)lane;       // another run of this warp holds the same digit
-        u32 prev = 0, rk;
-        if (!__any_sync(0xffffffffu, clash)) {
-            if (head) {
-                prev = wh[d];
-                wh[d] = prev + (u32)(end - start);
+        u32 rk;
+        if (heads == 1u) {                                               // one digit in the whole warp
+            if (d != cd) {
+                if (cd != 0xffffffffu && lane == 0) wh[cd] = cc;
+                __syncwarp();
+                cd = d;
+                cc = wh[d];
             }
-            prev = __shfl_sync(0xffffffffu, prev, start);
-            rk = prev + (u32)(lane - start);
+            rk = cc + (u32)lane;
+            cc += 32u;
         } else {
-            const u32 m = __match_any_sync(0xffffffffu, d);
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) {
-                prev = wh[d];
-                wh[d] = prev + __popc(m);
+            if (cd != 0xffffffffu) {
+                if (lane == 0) wh[cd] = cc;
+                cd = 0xffffffffu;
+                __syncwarp();
             }
-            prev = __shfl_sync(0xffffffffu, prev, leader);
-            rk = prev + __popc(m & (le >> 1));
+            u32 prev = 0;
+            // digits that do not decrease from lane to lane: equal digits are neighbours, so the runs are the whole story
+            if (__all_sync(0xffffffffu, lane == 0 || d >= dprev)) {
+                const int start = 31 - __clz(heads & le);               // my run's first lane
+                const u32 above = heads & ~le;
+                const int end = above ? __ffs(above) - 1 : 32;          // one past my run's last lane
+                if (head) {
+                    prev = wh[d];
+                    wh[d] = prev + (u32)(end - start);
+                }
+                prev = __shfl_sync(0xffffffffu, prev, start);
+                rk = prev + (u32)(lane - start);
+            } else {
+                const u32 m = __match_any_sync(0xffffffffu, d);
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) {
+                    prev = wh[d];
+                    wh[d] = prev + __popc(m);
+                }
+                prev = __shfl_sync(0xffffffffu, prev, leader);
+                rk = prev + __popc(m & (le >> 1));
+            }
+            __syncwarp();
         }
         if (i & 1) rank2[i >> 1] |= rk << 16;
         else rank2[i >> 1] = rk;
-        __syncwarp();
     }
+    if (cd != 0xffffffffu && lane == 0) wh[cd] = cc;
     __syncthreads();
 
     // one thread per digit pair (d0 = tid, d1 = tid + 256): offsets over warps, tile count, decoupled look-back

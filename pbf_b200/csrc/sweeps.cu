@@ -455,8 +455,13 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
     walk<1>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
-            const float2 cc = __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il);       // (h-l)^2 / l
+            const float2 tt = __fmul2_rn(q.t2, q.t2);                         // (h-l)^2
+            const float2 cc = __fmul2_rn(tt, q.il);                           // (h-l)^2 / l
+#ifdef PBF_SWEEP_S_FROM_GRAD
             S = __ffma2_rn(__fmul2_rn(cc, cc), q.r2, S);                      // sum |grad|^2 (up to a constant)
+#else
+            S = __ffma2_rn(tt, tt, S);                                        // |grad|^2 = ((h-l)^2 / l)^2 l^2 = (h-l)^4, one op less
+#endif
             gx = __ffma2_rn(cc, q.dx, gx);
             gy = __ffma2_rn(cc, q.dy, gy);
             gz = __ffma2_rn(cc, q.dz, gz);
@@ -489,8 +494,20 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
 }
 
 // ---- K9 updatepos.glsl:43-105, Jacobi: reads B {p, lambda}, writes A -----------------------------------------------
+// FINAL (the last solver iteration of a step): K10 update.glsl:16-28 runs in the epilogue -- the thread that has just
+// computed a particle's final position also derives its velocity and writes both back by particle id.  The gather of the
+// old position and the two scatters are uncoalesced 16-byte accesses (a separate kernel ran them at 2.7 TB/s, 0.19 ms);
+// here they hide under a sweep that leaves DRAM idle.  FINAL = 1: velocity by id; FINAL = 2: into the sorted array the
+// vorticity kernels read.
+struct UpdateArgs {
+    const u32 *perm;
+    float4 *pos, *vel, *svel;
+};
+
+template <int FINAL>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
-k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp) {
+k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp,
+          const UpdateArgs up) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
@@ -498,6 +515,12 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
     const u32 i = blockIdx.x * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    u32 id = 0;
+    float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (FINAL && live) {                                    // in flight while the sweep runs
+        id = __ldg(up.perm + i);
+        old = up.pos[id];
+    }
     float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
     // scorr = -k (scale W)^4 = -(k scale^4 POLY6^4) t^12 with t = max(h^2 - r^2, 0)        (updatepos.glsl:57-60)
     float sc4 = P.tensile_scale * POLY6;
@@ -523,6 +546,21 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
     z = fminf(fmaxf(z, g.wlo[2]), g.whi[2]);
     const float4 out = make_float4(x, y, z, 0.0f);
     if (live) A[i] = out;
+    if (FINAL && live) {                                    // update.glsl:16-28, same arithmetic as k_update
+        float4 v;
+        v.x = __fdiv_rn(__fsub_rn(x, old.x), P.timestep);
+        v.y = __fdiv_rn(__fsub_rn(y, old.y), P.timestep);
+        v.z = __fdiv_rn(__fsub_rn(z, old.z), P.timestep);
+        v.w = 0.0f;
+        if (P.restitution >= 0.0f) {
+            if ((x <= g.wlo[0] && v.x < 0.0f) || (x >= g.whi[0] && v.x > 0.0f)) v.x *= -P.restitution;
+            if ((y <= g.wlo[1] && v.y < 0.0f) || (y >= g.whi[1] && v.y > 0.0f)) v.y *= -P.restitution;
+            if ((z <= g.wlo[2] && v.z < 0.0f) || (z >= g.whi[2] && v.z > 0.0f)) v.z *= -P.restitution;
+        }
+        up.pos[id] = out;
+        if (FINAL == 2) up.svel[i] = v;
+        else up.vel[id] = v;
+    }
     halo_push(hp, i, live, out, true, tid);
 }
 
@@ -611,7 +649,9 @@ size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 int sweeps_init(void) {
     cudaError_t e = cudaFuncSetAttribute(k_lambda<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lambda<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vorticity_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vorticity_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM2);
     return e == cudaSuccess ? 0 : -1;
@@ -632,8 +672,18 @@ int launch_lambda(pbf_sim *s, const HaloPush *push) {
 }
 
 int launch_delta_p(pbf_sim *s, const HaloPush *push) {
-    k_delta_p<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s),
-                                                        push ? *push : NO_PUSH);
+    k_delta_p<0><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s),
+                                                           push ? *push : NO_PUSH, UpdateArgs{});
+    return 1;
+}
+
+// the last solver iteration of a step: delta-p with update.glsl in its epilogue (replaces launch_delta_p + launch_update)
+int launch_delta_p_update(pbf_sim *s) {
+    const UpdateArgs up = {s->perm, s->pos, s->vel, s->svel};
+    if (s->params.vorticity_confinement)
+        k_delta_p<2><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
+    else
+        k_delta_p<1><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
     return 1;
 }
 
