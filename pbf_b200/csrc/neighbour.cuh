@@ -93,9 +93,9 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 }
 
 // geometry of one candidate pair against particle p: d = p - c, r2, 1/l, and the two NEGATED factors
-// tn = rc - h^2 = -(h^2 - r^2)+ and t2n = l - h = -(h - l)+ with rc = min(r2 + TINY, h^2), l = rc / sqrt(rc): beyond the
+// tn = rc - h^2 = -(h^2 - r^2)+ and t2n = l - h = -(h - l)+ with rc = clamp(r2, TINY, h^2), l = rc / sqrt(rc): beyond the
 // support radius both factors vanish without a separate clamp to zero, at r = 0 rsqrt stays finite and c*d = 0 like
-// the l == 0 branch of gradWspiky (r2 + TINY == r2 in binary32 for every r2 > 1e-17).  Odd powers carry a minus sign the
+// the l == 0 branch of gradWspiky (callers multiply gradient magnitudes by the EXACT r2 or d, which are 0 there).  Odd powers carry a minus sign the
 // callers fold into their final constants.  Members outside the run (v0/v1 false) get rc = h^2, i.e. they leave kernel
 // support; their d is finite (a real record or a zeroed pad record), so 0 * d = 0.
 struct PairGeom {
@@ -107,16 +107,16 @@ __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bo
     q.dx = make_float2(p.x - c.x.x, p.x - c.x.y);
     q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
     q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
-#ifdef PBF_SWEEP_SEPARATE_TINY
-    q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));
+    q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));      // exact 0 for coincident particles
+#ifdef PBF_SWEEP_ADD_TINY
     const float2 re = __fadd2_rn(q.r2, make_float2(TINY, TINY));
-#else
-    // TINY rides in the first multiply-add of the squared distance (one packed op fewer on the FP32 pipe): it is
-    // absorbed by rounding unless the two particles coincide to within 1e-12
-    q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __ffma2_rn(q.dx, q.dx, make_float2(TINY, TINY))));
-    const float2 re = q.r2;
-#endif
     const float2 rc = make_float2(fminf(v0 ? re.x : FAR2, H2), fminf(v1 ? re.y : FAR2, H2));
+#else
+    // clamp to [TINY, h^2] with min/max (ALU pipe) instead of adding TINY (one packed op less on the FP32 pipe, which is
+    // what bounds the sweeps); a candidate outside the run gets the lower bound h^2, i.e. it leaves kernel support
+    const float cx_ = fminf(fmaxf(q.r2.x, TINY), H2), cy_ = fminf(fmaxf(q.r2.y, TINY), H2);
+    const float2 rc = make_float2(v0 ? cx_ : H2, v1 ? cy_ : H2);
+#endif
     q.il = make_float2(rsqrt_ftz(rc.x), rsqrt_ftz(rc.y));
     q.t2 = __ffma2_rn(rc, q.il, make_float2(-H, -H));                // l - h: 0 at and beyond the support radius
     q.t = __fadd2_rn(rc, make_float2(-H2, -H2));                     // r^2 - h^2, exactly <= 0

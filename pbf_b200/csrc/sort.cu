@@ -329,7 +329,10 @@ int sort_init(void) {
 SortPlan make_sort_plan(int bits) {
     SortPlan plan{};
     plan.bits = bits;
-    plan.passes = (bits + 8) / 9;                       // up to 9 bits per pass ...
+#ifndef PBF_SORT_MAX_BITS
+#define PBF_SORT_MAX_BITS 9
+#endif
+    plan.passes = (bits + PBF_SORT_MAX_BITS - 1) / PBF_SORT_MAX_BITS;   // up to 9 bits per pass ...
     const int width = (bits + plan.passes - 1) / plan.passes;   // ... spread evenly: 26 -> 9 + 9 + 8
     int at = 0;
     for (int p = 0; p < plan.passes; p++) {

@@ -457,11 +457,9 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 tt = __fmul2_rn(q.t2, q.t2);                         // (h-l)^2
             const float2 cc = __fmul2_rn(tt, q.il);                           // (h-l)^2 / l
-#ifdef PBF_SWEEP_S_FROM_GRAD
-            S = __ffma2_rn(__fmul2_rn(cc, cc), q.r2, S);                      // sum |grad|^2 (up to a constant)
-#else
-            S = __ffma2_rn(tt, tt, S);                                        // |grad|^2 = ((h-l)^2 / l)^2 l^2 = (h-l)^4, one op less
-#endif
+            // sum |grad|^2 (up to a constant).  Not (h-l)^4 = tt * tt, one op less: the exact r2 is what makes a coincident
+            // particle (and the particle itself) contribute nothing, as gradWspiky's l == 0 branch demands
+            S = __ffma2_rn(__fmul2_rn(cc, cc), q.r2, S);
             gx = __ffma2_rn(cc, q.dx, gx);
             gy = __ffma2_rn(cc, q.dy, gy);
             gz = __ffma2_rn(cc, q.dz, gz);

@@ -42,7 +42,7 @@ def launches(path):
     hdr = rows[0]
     ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
     L = [(short(r[ki]), float(r[vi].replace(',', ''))) for r in rows[1:]]
-    starts = [i for i, (k, _) in enumerate(L) if k.startswith('k_unclear')]
+    starts = [i for i, (k, _) in enumerate(L) if k.startswith('k_predict')]
     print("# ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`), %d launches captured\n" % len(L))
     print("Per-launch times are cold-cache and serialised; compare SHARES, not absolutes.\n")
     if len(starts) >= 3:
