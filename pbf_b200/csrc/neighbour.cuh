@@ -93,7 +93,7 @@ __device__ __forceinline__ float rsqrt_ftz(float x) {
 }
 
 // geometry of one candidate pair against particle p: d = p - c, r2, 1/l, and the two NEGATED factors
-// tn = rc - h^2 = -(h^2 - r^2)+ and t2n = l - h = -(h - l)+ with rc = clamp(r2, TINY, h^2), l = rc / sqrt(rc): beyond the
+// tn = rc - h^2 = -(h^2 - r^2)+ and t2n = l - h = -(h - l)+ with rc = min(r2 + TINY, h^2), l = rc / sqrt(rc): beyond the
 // support radius both factors vanish without a separate clamp to zero, at r = 0 rsqrt stays finite and c*d = 0 like
 // the l == 0 branch of gradWspiky (callers multiply gradient magnitudes by the EXACT r2 or d, which are 0 there).  Odd powers carry a minus sign the
 // callers fold into their final constants.  Members outside the run (v0/v1 false) get rc = h^2, i.e. they leave kernel
@@ -108,12 +108,15 @@ __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bo
     q.dy = make_float2(p.y - c.y.x, p.y - c.y.y);
     q.dz = make_float2(p.z - c.z.x, p.z - c.z.y);
     q.r2 = __ffma2_rn(q.dz, q.dz, __ffma2_rn(q.dy, q.dy, __fmul2_rn(q.dx, q.dx)));      // exact 0 for coincident particles
-#ifdef PBF_SWEEP_ADD_TINY
+#ifndef PBF_SWEEP_CLAMP_TINY
+    // Measured at 8M particles (lambda / delta-p sweep, ms): this form 0.346 / 0.356; TINY folded into the first
+    // multiply-add of r2 and S from (h-l)^4 0.327 / 0.345 -- two instructions fewer, but a coincident particle then adds 16
+    // to S (gradWspiky's l == 0 branch says 0; particles clamped into the same corner do coincide), so not adopted;
+    // clamp(r2, TINY, h^2) with min/max on the ALU pipe instead of the add 0.350 / 0.360 -- one instruction MORE and slower:
+    // the sweeps are bound by issue slots, not by the FP32 pipe alone.
     const float2 re = __fadd2_rn(q.r2, make_float2(TINY, TINY));
     const float2 rc = make_float2(fminf(v0 ? re.x : FAR2, H2), fminf(v1 ? re.y : FAR2, H2));
 #else
-    // clamp to [TINY, h^2] with min/max (ALU pipe) instead of adding TINY (one packed op less on the FP32 pipe, which is
-    // what bounds the sweeps); a candidate outside the run gets the lower bound h^2, i.e. it leaves kernel support
     const float cx_ = fminf(fmaxf(q.r2.x, TINY), H2), cy_ = fminf(fmaxf(q.r2.y, TINY), H2);
     const float2 rc = make_float2(v0 ? cx_ : H2, v1 ? cy_ : H2);
 #endif

@@ -32,7 +32,8 @@ constexpr int SORT_BLOCK = 256;
 #define PBF_SORT_ITEMS 16
 #endif
 #ifndef PBF_SORT_CTAS
-#define PBF_SORT_CTAS 4      // 64 registers, no spills: 4 blocks per SM instead of 3 (0.288 vs 0.300 ms for four 8-bit passes)
+#define PBF_SORT_CTAS 3      // measured at 8M particles, three 9-bit passes: 3 blocks per SM 0.241 ms, 4 blocks (64 registers) 0.261 ms,
+                             // 8 items per thread 0.290 ms; four 8-bit passes 0.288 ms
 #endif
 constexpr int SORT_ITEMS = PBF_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_BLOCK * SORT_ITEMS;  // 4096 pairs per tile
@@ -54,7 +55,7 @@ struct SortSmem {
     u32 wsum[2][SORT_WARPS];
     u32 tile;
 };
-static_assert(4 * (sizeof(SortSmem) + 1024) <= 233472, "four blocks per SM");
+static_assert(PBF_SORT_CTAS * (sizeof(SortSmem) + 1024) <= 233472, "blocks per SM");
 
 // exclusive scan of the per-pass digit histograms -> global digit bases; clears the histograms and the tile
 // counters for the next step.
