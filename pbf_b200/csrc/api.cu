@@ -198,7 +198,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     ALLOC(s->status, (size_t)4 * s->max_tiles * PBF_RADIX);
     ALLOC(s->cells, s->ncell); ALLOC(s->runs3, s->ncell);
     ALLOC(s->bufA, cap); ALLOC(s->bufB, cap); ALLOC(s->svel, cap); ALLOC(s->vprime, cap); ALLOC(s->omega, cap);
-    ALLOC(s->flags, 4); ALLOC(s->diag, 2);
+    ALLOC(s->flags, 4); ALLOC(s->diag, 2); ALLOC(s->dn, DN_WORDS);
     ALLOC(s->tile_desc, plan_desc_ints(cap)); ALLOC(s->tile_runs, plan_run_words(cap));
 #undef ALLOC
     if (sort_init() != 0) {
@@ -216,6 +216,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     cudaMemsetAsync(s->hist, 0, 8 * PBF_RADIX * 4, s->stream);
     cudaMemsetAsync(s->tile_counter, 0, 16, s->stream);
     cudaMemsetAsync(s->flags, 0, 16, s->stream);
+    cudaMemsetAsync(s->dn, 0, DN_WORDS * sizeof(u32), s->stream);
     for (float4 *b : {s->pred, s->bufA, s->bufB, s->svel, s->vprime, s->omega})   // pair loads may touch one slot of padding
         cudaMemsetAsync(b, 0, (size_t)cap * 16 + 16, s->stream);
     launch_fill_tables(s);   // start = -1 (gridtexture clear, src/NeighbourCellFinder.cpp:116-126), end = 0, runs empty
@@ -243,7 +244,7 @@ int pbf_destroy(pbf_handle s) {
     invalidate_graph(s);
     void *ptrs[] = {s->pos_own, s->vel_own, s->hl_own, s->pred, s->keys, s->ktmp[0], s->ktmp[1], s->vtmp[0], s->vtmp[1],
                     s->skey, s->perm, s->home, s->hist, s->gbase, s->tile_counter, s->status, s->cells, s->runs3, s->bufA, s->bufB,
-                    s->svel, s->vprime, s->omega, s->flags, s->diag, s->tile_desc, s->tile_runs};
+                    s->svel, s->vprime, s->omega, s->flags, s->diag, s->tile_desc, s->tile_runs, s->dn};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 6; i++)

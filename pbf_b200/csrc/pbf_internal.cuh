@@ -48,6 +48,23 @@ struct HaloPush {
     u32 count[2];                    // boundary particles per face (a flag is only published for a non-empty face)
 };
 
+// A particle count as kernels take it.  Single-domain handles know their count on the host: p is null and n is the value.
+// A slab rank's count changes every step ON THE DEVICE (migration, ghosts) and the host never waits for it: p points at the
+// device-side value and n is only the bound the grid was sized for.  Kernels loop over their tiles / elements up to the
+// device value, so a bound that is too small costs time, never particles.
+struct NRef {
+    u32 n;
+    const u32 *p;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ u32 nref(const NRef &r) { return r.p ? *r.p : r.n; }
+#endif
+
+// slots of pbf_sim::dn, the device-side counters of a slab rank (slab.cu)
+enum { DN_TOTAL = 0, DN_LOCAL = 1, DN_PREV = 2, DN_STAY = 3, DN_LEAVE = 4 /* lo, hi */, DN_BND = 6 /* lo, hi */,
+       DN_ARRIVE = 8 /* lo, hi */, DN_GHOST = 10 /* lo, hi */, DN_MOVERS = 12, DN_HOLES = 13, DN_OVERFLOW = 14, DN_STEP = 15,
+       DN_HALO_N = 16 /* boundary + ghost totals for the halo kernels: push lo, push hi, pull lo, pull hi */, DN_WORDS = 24 };
+
 struct SortPlan {
     int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
     int passes;      // onesweep passes of up to 9 bits
@@ -62,7 +79,9 @@ struct pbf_sim {
     int device;
     int sm_count;
     cudaStream_t stream;
-    u32 n;           // particles held
+    u32 n;           // particles held (slab rank with device-side counts: the bound its grids are sized for)
+    u32 *dn;         // device-side counters (DN_*); n_dev / n_prev_dev point into it on a slab rank, null otherwise
+    const u32 *n_dev, *n_prev_dev;
     u32 cap;
     GridInfo grid;
     SortPlan plan;
@@ -112,6 +131,9 @@ struct pbf_sim {
     struct pbf_slab_state *slab;          // non-null once pbf_slab_init has run (slab.cu)
 };
 
+inline NRef nref_total(const pbf_sim *s) { return NRef{s->n, s->n_dev}; }
+inline NRef nref_prev(const pbf_sim *s) { return NRef{s->n_prev_sorted, s->n_prev_dev}; }
+
 struct DeviceGuard {   // every entry point runs on the handle's device and restores the caller's
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -154,7 +176,7 @@ void pbf_set_error(const std::string &msg);
 int launch_fill_tables(pbf_sim *s);
 int launch_unclear_cells(pbf_sim *s);
 int launch_predict(pbf_sim *s);
-int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist);
+int launch_predict_range(pbf_sim *s, u32 first, NRef count, bool with_hist);
 int launch_keys_only(pbf_sim *s, u32 first, u32 count);
 int launch_reorder_cells(pbf_sim *s);
 int launch_highlight(pbf_sim *s);
@@ -187,5 +209,5 @@ int sort_init(void);                     // opt-in shared-memory size of the one
 u32 sort_max_tiles(u32 cap);
 int launch_sort_scan(pbf_sim *s);
 int launch_sort_passes(pbf_sim *s);
-int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n);
+int launch_sort_hist(pbf_sim *s, const u32 *keys, NRef n);
 int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, int bits);

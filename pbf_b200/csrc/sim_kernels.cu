@@ -50,10 +50,12 @@ __device__ __forceinline__ void unclear_slot(u32 i, const u32 *__restrict__ skey
 // launch: the scattered resets hide under the streaming loads).
 template <bool UNCLEAR>
 __global__ void __launch_bounds__(256)
-k_predict(u32 first, u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
+k_predict(u32 first, NRef nr, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
           float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ flags, GridInfo g, SimParams P,
-          u32 n_prev, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3) {
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+          NRef nprev, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3) {
+    const u32 n = nref(nr), n_prev = UNCLEAR ? nref(nprev) : 0u, m = n > n_prev ? n : n_prev;
+    // one element per thread; the loop only turns when the grid was sized for fewer particles than there are (NRef)
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < ((m + 31u) & ~31u); j += gridDim.x * blockDim.x) {
     if (UNCLEAR && j < n_prev) unclear_slot(j, skey, cells, runs3, g);
     bool any_hl = false;
     if (j < n) {
@@ -77,6 +79,7 @@ k_predict(u32 first, u32 n, const float4 *__restrict__ pos, const float4 *__rest
         any_hl = (h & 1u) != 0;
     }
     if (__any_sync(0xffffffffu, any_hl) && (threadIdx.x & 31) == 0) flags[0] = 1u;
+    }
 }
 
 // appended halo records already hold p*: cell keys only
@@ -97,9 +100,9 @@ __global__ void __launch_bounds__(256) k_fill_tables(size_t ncell, int2 *__restr
 }
 
 __global__ void __launch_bounds__(256)
-k_unclear_cells(u32 n, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3, GridInfo g) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) unclear_slot(i, skey, cells, runs3, g);
+k_unclear_cells(NRef nr, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3, GridInfo g) {
+    const u32 n = nref(nr);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) unclear_slot(i, skey, cells, runs3, g);
 }
 
 // packed unclamped cell of a position (neighbourcells.glsl:57 `ivec3(pos)`), each coordinate saturated to [-2, g+1]
@@ -112,10 +115,10 @@ __device__ __forceinline__ u32 pack_home(float x, float y, float z, const GridIn
 
 // ---- reorder (gather the predicted record of each sorted slot) + K6 findcells.glsl:34-53 -----------------------
 __global__ void __launch_bounds__(256)
-k_reorder_cells(u32 n, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const float4 *__restrict__ pred,
+k_reorder_cells(NRef nr, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const float4 *__restrict__ pred,
                 float4 *__restrict__ bufA, u32 *__restrict__ home, int2 *__restrict__ cells, GridInfo g) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const u32 n = nref(nr);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     u32 id = perm[i];
     const float4 p = pred[id];
     bufA[i] = p;
@@ -132,25 +135,27 @@ k_reorder_cells(u32 n, const u32 *__restrict__ skey, const u32 *__restrict__ per
         }
     }
     if (i == n - 1 && !(k & PBF_KEY_NOCELL)) cells[k].y = (int)n;   // policy: end of the last occupied cell
+    }
 }
 
 // one thread per first-particle-of-a-cell: refresh the merged runs of the cells whose window contains that cell
 __global__ void __launch_bounds__(256)
-k_build_runs(u32 n, const u32 *__restrict__ skey, const int2 *__restrict__ cells, int2 *__restrict__ runs3, GridInfo g) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (i == 0 && g.ref_quirks) {                                // start[(0,0,0)] = 0 is visible to cells 0 and 1
-        runs3[0] = merge3(cells, 0, 0, g.gx);
-        if (g.gx > 1) runs3[1] = merge3(cells, 0, 1, g.gx);
-    }
-    u32 k = skey[i];
-    if (k & PBF_KEY_NOCELL) return;
-    if (i != 0 && skey[i - 1] == k) return;
-    const int x = (int)(k % (u32)g.gx);
-    const int base = (int)k - x;
+k_build_runs(NRef nr, const u32 *__restrict__ skey, const int2 *__restrict__ cells, int2 *__restrict__ runs3, GridInfo g) {
+    const u32 n = nref(nr);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i == 0 && g.ref_quirks) {                                // start[(0,0,0)] = 0 is visible to cells 0 and 1
+            runs3[0] = merge3(cells, 0, 0, g.gx);
+            if (g.gx > 1) runs3[1] = merge3(cells, 0, 1, g.gx);
+        }
+        u32 k = skey[i];
+        if (k & PBF_KEY_NOCELL) continue;
+        if (i != 0 && skey[i - 1] == k) continue;
+        const int x = (int)(k % (u32)g.gx);
+        const int base = (int)k - x;
 #pragma unroll
-    for (int t = x - 1; t <= x + 1; t++)
-        if (t >= 0 && t < g.gx) runs3[base + t] = merge3(cells, base, t, g.gx);
+        for (int t = x - 1; t <= x + 1; t++)
+            if (t >= 0 && t < g.gx) runs3[base + t] = merge3(cells, base, t, g.gx);
+    }
 }
 
 // ---- K10 update.glsl:16-28 -------------------------------------------------------------------------------------------
@@ -158,10 +163,10 @@ k_build_runs(u32 n, const u32 *__restrict__ skey, const int2 *__restrict__ cells
 // vorticity kernels read (the by-id velocity is then written once, by k_vorticity_b).
 template <bool VORT>
 __global__ void __launch_bounds__(256)
-k_update(u32 n, const float4 *__restrict__ A, const u32 *__restrict__ perm, float4 *__restrict__ pos,
+k_update(NRef nr, const float4 *__restrict__ A, const u32 *__restrict__ perm, float4 *__restrict__ pos,
          float4 *__restrict__ vel, float4 *__restrict__ svel, SimParams P, GridInfo g) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const u32 n = nref(nr);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = A[i];
     const u32 id = perm[i];
     const float4 o = pos[id];
@@ -178,14 +183,16 @@ k_update(u32 n, const float4 *__restrict__ A, const u32 *__restrict__ perm, floa
     pos[id] = make_float4(p.x, p.y, p.z, 0.0f);
     if (VORT) svel[i] = v;
     else vel[id] = v;
+    }
 }
 
 // ---- K12 highlight.glsl:17-30 (clearhighlight is fused into k_predict) ---------------------------------------------------
 __global__ void __launch_bounds__(NB_BLOCK)
-k_highlight(u32 n, const u32 *__restrict__ home, const u32 *__restrict__ perm, const int2 *__restrict__ runs3,
+k_highlight(NRef nr, const u32 *__restrict__ home, const u32 *__restrict__ perm, const int2 *__restrict__ runs3,
             const int2 *__restrict__ cells, u32 *__restrict__ hl, const u32 *__restrict__ flags, GridInfo g) {
     __shared__ int2 srun[9 * NB_BLOCK];
     if (flags[0] == 0u) return;                      // nobody carries bit 0: the kernel is a no-op
+    const u32 n = nref(nr);
     const int tid = threadIdx.x;
     for (u32 i = blockIdx.x * NB_BLOCK + tid; i < n; i += gridDim.x * NB_BLOCK) {
         if ((hl[perm[i]] & 1u) == 0u) continue;
@@ -316,16 +323,19 @@ int launch_fill_tables(pbf_sim *s) {
 }
 
 int launch_unclear_cells(pbf_sim *s) {
+    if (s->n_prev_dev) {     // slab rank with device-side counts: always the same launch (capturable), the device knows how many
+        k_unclear_cells<<<nblocks(s->n ? s->n : 1, 256), 256, 0, s->stream>>>(NRef{s->n, s->n_prev_dev}, s->skey, s->cells, s->runs3, s->grid);
+        return 1;
+    }
     if (s->n_prev_sorted == 0) return 0;
-    k_unclear_cells<<<nblocks(s->n_prev_sorted, 256), 256, 0, s->stream>>>(s->n_prev_sorted, s->skey, s->cells, s->runs3,
-                                                                           s->grid);
+    k_unclear_cells<<<nblocks(s->n_prev_sorted, 256), 256, 0, s->stream>>>(nref_prev(s), s->skey, s->cells, s->runs3, s->grid);
     return 1;
 }
 
-int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist) {
-    if (count == 0) return 0;
-    k_predict<false><<<nblocks(count, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
-                                                                 s->grid, sim_params(s), 0u, nullptr, nullptr, nullptr);
+int launch_predict_range(pbf_sim *s, u32 first, NRef count, bool with_hist) {
+    if (count.n == 0) return 0;
+    k_predict<false><<<nblocks(count.n, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                                   s->grid, sim_params(s), NRef{0u, nullptr}, nullptr, nullptr, nullptr);
     // digit histograms of all sort passes: the keys just written are still in L2
     return 1 + (with_hist ? launch_sort_hist(s, s->keys + first, count) : 0);
 }
@@ -333,9 +343,9 @@ int launch_predict_range(pbf_sim *s, u32 first, u32 count, bool with_hist) {
 // whole-handle predict of the single-domain step: also undoes the previous step's cell-table writes (launch_unclear_cells)
 int launch_predict(pbf_sim *s) {
     const u32 np = s->n_prev_sorted, m = s->n > np ? s->n : np;
-    k_predict<true><<<nblocks(m, 256), 256, 0, s->stream>>>(0u, s->n, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags, s->grid,
-                                                            sim_params(s), np, s->skey, s->cells, s->runs3);
-    return 1 + launch_sort_hist(s, s->keys, s->n);
+    k_predict<true><<<nblocks(m, 256), 256, 0, s->stream>>>(0u, nref_total(s), s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                            s->grid, sim_params(s), nref_prev(s), s->skey, s->cells, s->runs3);
+    return 1 + launch_sort_hist(s, s->keys, nref_total(s));
 }
 
 int launch_keys_only(pbf_sim *s, u32 first, u32 count) {
@@ -345,9 +355,9 @@ int launch_keys_only(pbf_sim *s, u32 first, u32 count) {
 }
 
 int launch_reorder_cells(pbf_sim *s) {
-    k_reorder_cells<<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->skey, s->perm, s->pred, s->bufA, s->home,
+    k_reorder_cells<<<nblocks(s->n, 256), 256, 0, s->stream>>>(nref_total(s), s->skey, s->perm, s->pred, s->bufA, s->home,
                                                                s->cells, s->grid);
-    k_build_runs<<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->skey, s->cells, s->runs3, s->grid);
+    k_build_runs<<<nblocks(s->n, 256), 256, 0, s->stream>>>(nref_total(s), s->skey, s->cells, s->runs3, s->grid);
     s->n_prev_sorted = s->n;
     return 2 + launch_plan(s);   // staging plan of the tiled sweeps (sweeps.cu), valid until the next sort
 }
@@ -356,16 +366,16 @@ int launch_highlight(pbf_sim *s) {
     // a few blocks per SM striding over the particles: the usual case is "nothing selected", a no-op worth ~2 us
     int blocks = nblocks(s->n, NB_BLOCK);
     if (blocks > s->sm_count * 4) blocks = s->sm_count * 4;
-    k_highlight<<<blocks, NB_BLOCK, 0, s->stream>>>(s->n, s->home, s->perm, s->runs3, s->cells, s->hl, s->flags, s->grid);
+    k_highlight<<<blocks, NB_BLOCK, 0, s->stream>>>(nref_total(s), s->home, s->perm, s->runs3, s->cells, s->hl, s->flags, s->grid);
     return 1;
 }
 
 int launch_update(pbf_sim *s) {
     if (s->params.vorticity_confinement)
-        k_update<true><<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->bufA, s->perm, s->pos, s->vel, s->svel,
+        k_update<true><<<nblocks(s->n, 256), 256, 0, s->stream>>>(nref_total(s), s->bufA, s->perm, s->pos, s->vel, s->svel,
                                                                   sim_params(s), s->grid);
     else
-        k_update<false><<<nblocks(s->n, 256), 256, 0, s->stream>>>(s->n, s->bufA, s->perm, s->pos, s->vel, s->svel,
+        k_update<false><<<nblocks(s->n, 256), 256, 0, s->stream>>>(nref_total(s), s->bufA, s->perm, s->pos, s->vel, s->svel,
                                                                    sim_params(s), s->grid);
     return 1;
 }

@@ -80,13 +80,39 @@ struct pbf_slab_state {
     bool pushed;                        // the sweep just launched has pushed refresh number xseq already
     bool fused;                         // PBF_SLAB_FUSED=1: the producing sweep pushes its halo itself (default: a separate push kernel)
     unsigned long long xseq;            // halo refreshes so far: the same number on every rank
+    // ---- step without host round trips (peer-memory transport, csrc/slab.cu "device-side counts") -------------------------
+    bool devcount;                      // counts live in pbf_sim::dn; the host only knows bounds
+    char *peer_inbox[2];                // base of the record area I fill in the lo / hi neighbour's mailbox
+    u32 *rec_done;                      // last-block counters of the record pushes [4]
+    u32 *h_ring;                        // pinned: RING x DN_WORDS counters read back after every step, never waited for
+    cudaEvent_t ring_ev[4];
+    uint64_t ring_step[4];              // step each ring slot belongs to (0 = empty)
+    uint64_t step;                      // steps enqueued so far
+    u32 bound_local;                    // grid bound for the local particles (pbf_sim::n is the bound incl. ghosts)
+    bool bounds_exact;                  // bounds were set from exact host knowledge (upload), not from a read-back
+    cudaGraph_t graph; cudaGraphExec_t graph_exec;   // the captured step of this rank (rank 0: of the whole virtual group)
+    uint64_t graph_key;
+    u32 graph_kernels;
+    bool use_graph;
 };
 
 constexpr int MB_SLOTS = 4;   // 2 would do: a rank pushes refresh e+2 only after it received e+1, which its neighbour
                               // pushed after consuming e (push e+1 follows pull e in stream order)
+constexpr int RING = 4;
 inline size_t mbox_slot_bytes(const pbf_slab_state *b) { return (size_t)b->halo_cap * 16; }
 inline size_t mbox_flags_offset(const pbf_slab_state *b) { return 2 * (size_t)MB_SLOTS * mbox_slot_bytes(b); }
-inline size_t mbox_bytes(const pbf_slab_state *b) { return mbox_flags_offset(b) + 2 * MB_SLOTS * sizeof(unsigned long long); }
+// After the halo slots and their flags: the record inbox.  Per side (0 = written by my lo neighbour, 1 = by my hi
+// neighbour) and step parity one area: migration records, ghost records, then a 64-byte header
+//   {u32 migrants; u32 ghosts; u64 migrants_ready; u64 ghosts_ready}   (ready = the step number, release/acquire).
+struct InboxHeader {
+    u32 n_mig, n_ghost;
+    unsigned long long mig_ready, ghost_ready;
+    unsigned long long pad[5];
+};
+static_assert(sizeof(InboxHeader) == 64, "inbox header is one 64-byte line");
+inline size_t inbox_offset(const pbf_slab_state *b) { return (mbox_flags_offset(b) + 2 * MB_SLOTS * sizeof(unsigned long long) + 255) & ~(size_t)255; }
+inline size_t inbox_area_bytes(const pbf_slab_state *b) { return (size_t)b->halo_cap * (sizeof(MigRec) + sizeof(GhostRec)) + sizeof(InboxHeader); }
+inline size_t mbox_bytes(const pbf_slab_state *b) { return inbox_offset(b) + 4 * inbox_area_bytes(b); }
 
 namespace {
 
@@ -131,11 +157,11 @@ __device__ __forceinline__ int global_layer(float z, const GridInfo &g) {
 
 // which local particles left the slab with their predicted position (predictpos.glsl:34)
 __global__ void __launch_bounds__(256)
-k_mark_leavers(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, int z_hi, bool has_lo, bool has_hi,
+k_mark_leavers(NRef nr, const float4 *__restrict__ pred, GridInfo g, int z_lo, int z_hi, bool has_lo, bool has_hi,
                u32 *__restrict__ btag, u32 *__restrict__ leave_lo, u32 *__restrict__ leave_hi, u32 *__restrict__ cnt,
                u32 cap) {
-    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    const u32 n = nref(nr);
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     const int cz = global_layer(pred[s].z, g);
     u32 tag = 0;
     if (has_lo && cz < z_lo) {
@@ -148,6 +174,7 @@ k_mark_leavers(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, int
         tag = LEAVER;
     }
     btag[s] = tag;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -213,10 +240,10 @@ k_unpack_migrants(u32 count, u32 base, const MigRec *__restrict__ in, float4 *po
 
 // boundary layers z_lo and z_hi-1: their particles are the neighbours' ghosts
 __global__ void __launch_bounds__(256)
-k_mark_boundary(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, int z_hi, bool has_lo, bool has_hi,
+k_mark_boundary(NRef nr, const float4 *__restrict__ pred, GridInfo g, int z_lo, int z_hi, bool has_lo, bool has_hi,
                 u32 *__restrict__ btag, u32 *__restrict__ bnd_lo, u32 *__restrict__ bnd_hi, u32 *__restrict__ cnt, u32 cap) {
-    u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+    const u32 n = nref(nr);
+    for (u32 s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
     const int cz = global_layer(pred[s].z, g);
     u32 tag = 0;
     if (has_lo && cz == z_lo) {
@@ -227,6 +254,7 @@ k_mark_boundary(u32 n, const float4 *__restrict__ pred, GridInfo g, int z_lo, in
         if (k < cap) { bnd_hi[k] = s; tag = 0x80000000u | (k + 1u); }
     }
     btag[s] = tag;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -265,11 +293,11 @@ k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *po
 
 // after the sort: where did the boundary particles (to pack) and the ghosts (to overwrite) land?
 __global__ void __launch_bounds__(256)
-k_halo_index(u32 n, u32 n_local, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
+k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
              u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, u32 *__restrict__ push_map,
              u32 *__restrict__ push_tiles, u32 tile_size, GridInfo g) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const u32 n = nref(nr), n_local = nref(nloc);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u32 kraw = skey[i];
     const u32 k = kraw & ~PBF_KEY_NOCELL;
     const int cz = (int)((k % (u32)g.gxgz) / (u32)g.gx);
@@ -280,12 +308,13 @@ k_halo_index(u32 n, u32 n_local, const u32 *__restrict__ skey, const u32 *__rest
     const u32 id = edge ? perm[i] : 0u;
     if (edge && id < n_local) t = btag[id];
     push_map[i] = t;
-    if (!edge) return;
-    if (id >= n_local) { ghost_sorted[id - n_local] = i; return; }
-    if (t == 0) return;
+    if (!edge) continue;
+    if (id >= n_local) { ghost_sorted[id - n_local] = i; continue; }
+    if (t == 0) continue;
     if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
     if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
     else send_lo[t - 1u] = i;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -368,6 +397,274 @@ k_halo_pull(HaloSide lo, HaloSide hi, const u32 *__restrict__ ghost_sorted, floa
         buf[i] = make_float4(q[0], q[1], q[2], q[3]);
     } else {
         buf[i].w = reinterpret_cast<const volatile float *>(src)[j];
+    }
+}
+
+// ======================================================================================================================
+// Device-side counts: the slab step without a single host round trip (peer-memory transport only).
+//
+// Which particles leave, how many arrive and how many ghosts a rank holds is decided on the device every step; the old
+// path read those counts back twice per step to size its NCCL transfers and its launches (2 x cudaStreamSynchronize,
+// ~50 direct launches: all of the 1 -> 2 GPU loss).  Here
+//   * migration and ghost records go as plain stores into the neighbour's record inbox over NVLink, followed by the count
+//     and a release flag that carries the step number; the receiver's unpack kernel spins on the flag (acquire);
+//   * every count lives in pbf_sim::dn; kernels get it as NRef (device pointer + the bound the grid was sized for) and
+//     loop over their tiles / elements, so a stale bound costs time, never particles;
+//   * nothing in the step depends on host knowledge any more, so the whole step is captured as ONE CUDA graph and
+//     replayed; the host reads the counters back asynchronously (pinned ring) only to keep the bounds tight.
+// ======================================================================================================================
+__device__ __forceinline__ InboxHeader *inbox_header(char *area, u32 cap) {
+    return reinterpret_cast<InboxHeader *>(area + (size_t)cap * (sizeof(MigRec) + sizeof(GhostRec)));
+}
+__device__ __forceinline__ MigRec *inbox_mig(char *area) { return reinterpret_cast<MigRec *>(area); }
+__device__ __forceinline__ GhostRec *inbox_ghost(char *area, u32 cap) { return reinterpret_cast<GhostRec *>(area + (size_t)cap * sizeof(MigRec)); }
+__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p) { return *reinterpret_cast<const volatile u32 *>(p); }
+
+// first kernel of a step: the step number (flags carry it) and the stay count of the coming compaction are reset
+__global__ void k_step_begin(u32 *dn) {
+    if (threadIdx.x == 0) { dn[DN_STEP] += 1u; }
+}
+
+// after k_mark_leavers: how many stay.  Leavers beyond the record capacity cannot be sent: overflow (reported by the host)
+__global__ void k_counts_leave(u32 *dn, const u32 *__restrict__ cnt, u32 cap, bool has_lo, bool has_hi) {
+    if (threadIdx.x != 0) return;
+    u32 lo = has_lo ? cnt[0] : 0u, hi = has_hi ? cnt[1] : 0u;
+    if (lo > cap || hi > cap) { dn[DN_OVERFLOW] |= 1u; lo = min(lo, cap); hi = min(hi, cap); }
+    dn[DN_LEAVE] = lo; dn[DN_LEAVE + 1] = hi;
+    dn[DN_STAY] = dn[DN_LOCAL] - lo - hi;
+    dn[20] += lo + hi;                                   // particles migrated away so far (pbf_slab_stats)
+}
+
+// pack the leavers of one side straight into the neighbour's inbox (its area for this step's parity); the block that
+// finishes last publishes the count and the step number
+__global__ void __launch_bounds__(256)
+k_push_migrants(const u32 *__restrict__ dn, int side, const u32 *__restrict__ list, const float4 *__restrict__ pos,
+                const float4 *__restrict__ vel, const float4 *__restrict__ pred, const u32 *__restrict__ gid,
+                const u32 *__restrict__ hl, char *peer_area0, size_t area_bytes, u32 cap, u32 *done) {
+    const u32 step = dn[DN_STEP], count = dn[DN_LEAVE + side];
+    char *area = peer_area0 + (size_t)(step & 1u) * area_bytes;
+    MigRec *out = inbox_mig(area);
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const u32 s = list[k];
+        MigRec r;
+        r.pos = pos[s]; r.vel = vel[s]; r.pred = pred[s]; r.gid = gid[s]; r.hl = hl[s]; r.pad0 = r.pad1 = 0;
+        out[k] = r;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+        *done = 0u;
+        InboxHeader *h = inbox_header(area, cap);
+        h->n_mig = count;
+        __threadfence_system();
+        st_release_sys(&h->mig_ready, (unsigned long long)step);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_find_movers_dev(const u32 *__restrict__ dn, const u32 *__restrict__ btag, u32 *__restrict__ movers, u32 *__restrict__ cnt) {
+    const u32 n_stay = dn[DN_STAY], n = dn[DN_LOCAL];
+    for (u32 s = n_stay + blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+        if (btag[s] != LEAVER) movers[atomicAdd(&cnt[4], 1u)] = s;
+}
+__global__ void __launch_bounds__(256)
+k_find_holes_dev(const u32 *__restrict__ dn, int side, const u32 *__restrict__ list, u32 *__restrict__ holes, u32 *__restrict__ cnt) {
+    const u32 n_stay = dn[DN_STAY], count = dn[DN_LEAVE + side];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const u32 s = list[k];
+        if (s < n_stay) holes[atomicAdd(&cnt[5], 1u)] = s;
+    }
+}
+__global__ void __launch_bounds__(256)
+k_fill_holes_dev(const u32 *__restrict__ cnt, const u32 *__restrict__ holes, const u32 *__restrict__ movers, float4 *pos,
+                 float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys) {
+    const u32 count = cnt[5];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const u32 d = holes[k], s = movers[k];
+        pos[d] = pos[s]; vel[d] = vel[s]; gid[d] = gid[s]; hl[d] = hl[s]; keys[d] = keys[s];
+        float4 p = pred[s];
+        p.w = __int_as_float((int)d);
+        pred[d] = p;
+    }
+}
+
+// wait for both neighbours' migrants of this step and append them after the stayers (lo first, then hi)
+__global__ void __launch_bounds__(256)
+k_pull_migrants(const u32 *__restrict__ dn, char *my_area_lo0, char *my_area_hi0, size_t area_bytes, u32 cap, u32 part_cap,
+                bool has_lo, bool has_hi, float4 *pos, float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys, GridInfo g) {
+    const u32 step = dn[DN_STEP];
+    char *alo = my_area_lo0 + (size_t)(step & 1u) * area_bytes, *ahi = my_area_hi0 + (size_t)(step & 1u) * area_bytes;
+    if (threadIdx.x == 0) {
+        if (has_lo) while (ld_acquire_sys(&inbox_header(alo, cap)->mig_ready) < step) __nanosleep(64);
+        if (has_hi) while (ld_acquire_sys(&inbox_header(ahi, cap)->mig_ready) < step) __nanosleep(64);
+    }
+    __syncthreads();
+    const u32 in_lo = has_lo ? ld_volatile_u32(&inbox_header(alo, cap)->n_mig) : 0u;
+    const u32 in_hi = has_hi ? ld_volatile_u32(&inbox_header(ahi, cap)->n_mig) : 0u;
+    const u32 base = dn[DN_STAY];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < in_lo + in_hi; k += gridDim.x * blockDim.x) {
+        const u32 s = base + k;
+        if (s >= part_cap) continue;                                   // overflow: k_counts_arrive reports it
+        const MigRec *src = k < in_lo ? inbox_mig(alo) + k : inbox_mig(ahi) + (k - in_lo);
+        // the records were written by another GPU: ld.cv bypasses L1, which may hold the area's previous contents
+        const uint4 *q = reinterpret_cast<const uint4 *>(src);
+        uint4 a = __ldcv(q), b4 = __ldcv(q + 1), c = __ldcv(q + 2), d = __ldcv(q + 3);
+        MigRec r;
+        r.pos = *reinterpret_cast<float4 *>(&a); r.vel = *reinterpret_cast<float4 *>(&b4); r.pred = *reinterpret_cast<float4 *>(&c);
+        r.gid = d.x; r.hl = d.y;
+        pos[s] = r.pos; vel[s] = r.vel; gid[s] = r.gid; hl[s] = r.hl;
+        r.pred.w = __int_as_float((int)s);
+        pred[s] = r.pred;
+        keys[s] = window_key(r.pred.x, r.pred.y, r.pred.z, g);
+    }
+}
+
+// after the arrivals are in: the new local count
+__global__ void k_counts_arrive(u32 *dn, char *my_area_lo0, char *my_area_hi0, size_t area_bytes, u32 cap, u32 part_cap,
+                                bool has_lo, bool has_hi) {
+    if (threadIdx.x != 0) return;
+    const u32 step = dn[DN_STEP];
+    char *alo = my_area_lo0 + (size_t)(step & 1u) * area_bytes, *ahi = my_area_hi0 + (size_t)(step & 1u) * area_bytes;
+    const u32 in_lo = has_lo ? ld_volatile_u32(&inbox_header(alo, cap)->n_mig) : 0u;
+    const u32 in_hi = has_hi ? ld_volatile_u32(&inbox_header(ahi, cap)->n_mig) : 0u;
+    dn[DN_ARRIVE] = in_lo; dn[DN_ARRIVE + 1] = in_hi;
+    u32 n = dn[DN_STAY] + in_lo + in_hi;
+    if (n > part_cap) { dn[DN_OVERFLOW] |= 2u; n = part_cap; }
+    dn[DN_LOCAL] = n;
+}
+
+// after k_mark_boundary: the boundary counts (what the neighbours will hold as ghosts)
+__global__ void k_counts_boundary(u32 *dn, const u32 *__restrict__ cnt, u32 cap, bool has_lo, bool has_hi) {
+    if (threadIdx.x != 0) return;
+    u32 lo = has_lo ? cnt[2] : 0u, hi = has_hi ? cnt[3] : 0u;
+    if (lo > cap || hi > cap) { dn[DN_OVERFLOW] |= 4u; lo = min(lo, cap); hi = min(hi, cap); }
+    dn[DN_BND] = lo; dn[DN_BND + 1] = hi;
+}
+
+__global__ void __launch_bounds__(256)
+k_push_ghosts(const u32 *__restrict__ dn, int side, const u32 *__restrict__ list, const float4 *__restrict__ pred,
+              const float4 *__restrict__ pos, const u32 *__restrict__ hl, char *peer_area0, size_t area_bytes, u32 cap, u32 *done) {
+    const u32 step = dn[DN_STEP], count = dn[DN_BND + side];
+    char *area = peer_area0 + (size_t)(step & 1u) * area_bytes;
+    GhostRec *out = inbox_ghost(area, cap);
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const u32 s = list[k];
+        GhostRec r;
+        r.pred = pred[s];
+        r.old = pos[s];
+        r.old.w = __uint_as_float(hl[s] & 1u);           // the selection bit travels with the ghost (see k_pack_ghosts)
+        out[k] = r;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+        *done = 0u;
+        InboxHeader *h = inbox_header(area, cap);
+        h->n_ghost = count;
+        __threadfence_system();
+        st_release_sys(&h->ghost_ready, (unsigned long long)step);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_pull_ghosts(const u32 *__restrict__ dn, char *my_area_lo0, char *my_area_hi0, size_t area_bytes, u32 cap, u32 part_cap,
+              bool has_lo, bool has_hi, float4 *pos, float4 *vel, float4 *pred, u32 *hl, u32 *keys, u32 *flags, GridInfo g) {
+    const u32 step = dn[DN_STEP];
+    char *alo = my_area_lo0 + (size_t)(step & 1u) * area_bytes, *ahi = my_area_hi0 + (size_t)(step & 1u) * area_bytes;
+    if (threadIdx.x == 0) {
+        if (has_lo) while (ld_acquire_sys(&inbox_header(alo, cap)->ghost_ready) < step) __nanosleep(64);
+        if (has_hi) while (ld_acquire_sys(&inbox_header(ahi, cap)->ghost_ready) < step) __nanosleep(64);
+    }
+    __syncthreads();
+    const u32 g_lo = has_lo ? ld_volatile_u32(&inbox_header(alo, cap)->n_ghost) : 0u;
+    const u32 g_hi = has_hi ? ld_volatile_u32(&inbox_header(ahi, cap)->n_ghost) : 0u;
+    const u32 base = dn[DN_LOCAL];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < g_lo + g_hi; k += gridDim.x * blockDim.x) {
+        const u32 s = base + k;
+        if (s >= part_cap) continue;
+        const GhostRec *src = k < g_lo ? inbox_ghost(alo, cap) + k : inbox_ghost(ahi, cap) + (k - g_lo);
+        const uint4 *q = reinterpret_cast<const uint4 *>(src);
+        uint4 a = __ldcv(q), b4 = __ldcv(q + 1);
+        float4 prd = *reinterpret_cast<float4 *>(&a), old = *reinterpret_cast<float4 *>(&b4);
+        const u32 selected = __float_as_uint(old.w) & 1u;
+        old.w = 0.0f;
+        pos[s] = old;
+        vel[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        hl[s] = selected;
+        if (selected) flags[0] = 1u;
+        prd.w = __int_as_float((int)s);
+        pred[s] = prd;
+        keys[s] = window_key(prd.x, prd.y, prd.z, g);
+    }
+}
+
+// after the ghosts are in: the count every later kernel of the step runs on, and the sizes of the halo refreshes
+__global__ void k_counts_ghosts(u32 *dn, char *my_area_lo0, char *my_area_hi0, size_t area_bytes, u32 cap, u32 part_cap,
+                                bool has_lo, bool has_hi) {
+    if (threadIdx.x != 0) return;
+    const u32 step = dn[DN_STEP];
+    char *alo = my_area_lo0 + (size_t)(step & 1u) * area_bytes, *ahi = my_area_hi0 + (size_t)(step & 1u) * area_bytes;
+    const u32 g_lo = has_lo ? ld_volatile_u32(&inbox_header(alo, cap)->n_ghost) : 0u;
+    const u32 g_hi = has_hi ? ld_volatile_u32(&inbox_header(ahi, cap)->n_ghost) : 0u;
+    dn[DN_GHOST] = g_lo; dn[DN_GHOST + 1] = g_hi;
+    u32 n = dn[DN_LOCAL] + g_lo + g_hi;
+    if (n > part_cap) { dn[DN_OVERFLOW] |= 8u; n = part_cap; }
+    dn[DN_TOTAL] = n;
+    dn[DN_HALO_N] = dn[DN_BND]; dn[DN_HALO_N + 1] = dn[DN_BND + 1];
+    dn[DN_HALO_N + 2] = g_lo; dn[DN_HALO_N + 3] = g_hi;
+}
+
+// last kernel of a step: what the next step's table reset runs over
+__global__ void k_step_end(u32 *dn) {
+    if (threadIdx.x == 0) dn[DN_PREV] = dn[DN_TOTAL];
+}
+
+// halo refresh with device-side sizes: as k_halo_push / k_halo_pull, counts from dn, sequence number = 256 * step + e
+struct HaloSideDev {
+    const u32 *idx;
+    char *data;
+    unsigned long long *flag;
+};
+__global__ void __launch_bounds__(256)
+k_halo_push_dev(const u32 *__restrict__ dn, HaloSideDev lo, HaloSideDev hi, const float4 *__restrict__ buf, int wide, u32 e, u32 *done) {
+    const u32 nlo = dn[DN_HALO_N], nhi = dn[DN_HALO_N + 1];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nlo + nhi; k += gridDim.x * blockDim.x) {
+        const HaloSideDev &h = k < nlo ? lo : hi;
+        const u32 j = k < nlo ? k : k - nlo;
+        const float4 v = buf[h.idx[j]];
+        if (wide) reinterpret_cast<float4 *>(h.data)[j] = v;
+        else reinterpret_cast<float *>(h.data)[j] = v.w;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+        *done = 0u;
+        __threadfence_system();
+        const unsigned long long seq = 256ull * dn[DN_STEP] + e;
+        if (nlo) st_release_sys(lo.flag, seq);
+        if (nhi) st_release_sys(hi.flag, seq);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_halo_pull_dev(const u32 *__restrict__ dn, HaloSideDev lo, HaloSideDev hi, const u32 *__restrict__ ghost_sorted,
+                float4 *__restrict__ buf, int wide, u32 e) {
+    const u32 nlo = dn[DN_HALO_N + 2], nhi = dn[DN_HALO_N + 3];
+    const unsigned long long seq = 256ull * dn[DN_STEP] + e;
+    if (threadIdx.x == 0) {
+        if (nlo) while (ld_acquire_sys(lo.flag) < seq) __nanosleep(64);
+        if (nhi) while (ld_acquire_sys(hi.flag) < seq) __nanosleep(64);
+    }
+    __syncthreads();
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < nlo + nhi; k += gridDim.x * blockDim.x) {
+        const u32 i = ghost_sorted[k];
+        const char *src = k < nlo ? lo.data : hi.data;
+        const u32 j = k < nlo ? k : k - nlo;
+        if (wide) {
+            const volatile float *q = reinterpret_cast<const volatile float *>(src) + 4 * (size_t)j;
+            buf[i] = make_float4(q[0], q[1], q[2], q[3]);
+        } else {
+            buf[i].w = reinterpret_cast<const volatile float *>(src)[j];
+        }
     }
 }
 
@@ -566,9 +863,9 @@ int slab_step(pbf_sim **grp, int ng) {
         cudaMemsetAsync(b->counters, 0, 16 * sizeof(u32), s->stream);
         s->launches += launch_unclear_cells(s);
         s->n = b->n_local;
-        s->launches += launch_predict_range(s, 0, b->n_local, false);
+        s->launches += launch_predict_range(s, 0, NRef{b->n_local, nullptr}, false);
         if (b->n_local) {
-            k_mark_leavers<<<nb(b->n_local), 256, 0, s->stream>>>(b->n_local, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0],
+            k_mark_leavers<<<nb(b->n_local), 256, 0, s->stream>>>(NRef{b->n_local, nullptr}, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0],
                                                                    b->has[1], b->btag, b->list[0], b->list[1], b->counters,
                                                                    b->halo_cap);
             for (int side = 0; side < 2; side++)
@@ -616,7 +913,7 @@ int slab_step(pbf_sim **grp, int ng) {
         b->n_local = n_stay + n_arrive;
         b->migrated += n_leave;
         if (b->n_local) {
-            k_mark_boundary<<<nb(b->n_local), 256, 0, s->stream>>>(b->n_local, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0],
+            k_mark_boundary<<<nb(b->n_local), 256, 0, s->stream>>>(NRef{b->n_local, nullptr}, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0],
                                                                     b->has[1], b->btag, b->list[2], b->list[3], b->counters,
                                                                     b->halo_cap);
             s->launches++;
@@ -658,13 +955,13 @@ int slab_step(pbf_sim **grp, int ng) {
         }
         // ---- sort + cells over local + ghost particles ------------------------------------------------------------------
         s->n = base;
-        s->launches += launch_sort_hist(s, s->keys, s->n);
+        s->launches += launch_sort_hist(s, s->keys, NRef{s->n, nullptr});
         s->launches += launch_sort_scan(s);
         s->launches += launch_sort_passes(s);
         s->launches += launch_reorder_cells(s);
         if (b->n_ghost[0] + b->n_ghost[1] + b->n_bnd[0] + b->n_bnd[1]) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
-            k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(s->n, b->n_local, s->skey, s->perm, b->btag, b->send_idx[0],
+            k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(NRef{s->n, nullptr}, NRef{b->n_local, nullptr}, s->skey, s->perm, b->btag, b->send_idx[0],
                                                           b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
                                                           plan_tile_size(), s->grid);
             s->launches++;
@@ -702,6 +999,256 @@ int slab_step(pbf_sim **grp, int ng) {
     return PBF_OK;
 }
 
+// ---- host side of the device-count step -----------------------------------------------------------------------------------
+inline char *inbox_area(char *mbox, const pbf_slab_state *b, int side /* 0: filled by the lo neighbour */) {
+    return mbox + inbox_offset(b) + (size_t)side * 2 * inbox_area_bytes(b);          // parity 0; parity 1 follows
+}
+
+constexpr int REC_BLOCKS = 128;      // grid of the record / halo kernels (grid-stride over device-side counts)
+inline u32 round_up(u32 v, u32 q) { return (v + q - 1) / q * q; }
+
+// Bounds from exact knowledge (upload): local count + slack, ghosts unknown -> the most the inbox can deliver.
+// PBF_SLAB_STARVE_BOUNDS=1 (tests): bounds a third of what is needed, so that every kernel has to loop over its count
+bool starve_bounds() {
+    static const int v = [] { const char *e = getenv("PBF_SLAB_STARVE_BOUNDS"); return e && e[0] == '1' ? 1 : 0; }();
+    return v != 0;
+}
+
+void set_bounds_exact(pbf_sim *s, u32 n_local) {
+    pbf_slab_state *b = s->slab;
+    b->bound_local = min(s->cap, round_up(n_local + n_local / 64 + 4096, 4096));
+    s->n = min(s->cap, round_up(b->bound_local + 2 * b->halo_cap, 4096));
+    if (starve_bounds()) { b->bound_local = max(512u, n_local / 3); s->n = max(512u, n_local / 3); }
+    b->bounds_exact = true;
+}
+
+// Non-blocking: the newest counters the device has finished writing back tighten (or raise) the grid bounds.  The kernels
+// loop over the device-side counts, so a bound that lags only costs time.  Returns an error once a step has overflowed.
+int refresh_bounds(pbf_sim *s) {
+    pbf_slab_state *b = s->slab;
+    int best = -1;
+    for (int k = 0; k < RING; k++)
+        if (b->ring_step[k] && (best < 0 || b->ring_step[k] > b->ring_step[best]) && cudaEventQuery(b->ring_ev[k]) == cudaSuccess) best = k;
+    (void)cudaGetLastError();            // cudaErrorNotReady of a pending event is not an error
+    if (best < 0) return PBF_OK;
+    const u32 *h = b->h_ring + (size_t)best * DN_WORDS;
+    if (h[DN_OVERFLOW]) {
+        pbf_set_error("slab: capacity exceeded on the device (bit 0: leavers, 1: arrivals, 2: boundary layer, 3: ghosts > capacity): " +
+                      std::to_string(h[DN_OVERFLOW]) + "; raise the particle / halo capacity");
+        return PBF_ERR_CAPACITY;
+    }
+    const u32 lag = (u32)(b->step - b->ring_step[best]);
+    const u32 arrive = h[DN_ARRIVE] + h[DN_ARRIVE + 1], ghosts = h[DN_GHOST] + h[DN_GHOST + 1];
+    u32 want_local = round_up(h[DN_LOCAL] + (lag + 2) * 2 * arrive + 4096, 8192);
+    u32 want_total = round_up(want_local + ghosts + ghosts / 4 + 4096, 8192);
+    want_local = min(want_local, s->cap); want_total = min(want_total, s->cap);
+    if (starve_bounds()) { want_local = max(512u, h[DN_LOCAL] / 3); want_total = want_local; b->bound_local = want_local; s->n = want_total; }
+    if (want_local > b->bound_local || b->bound_local > want_local + want_local / 32 + 16384) b->bound_local = want_local;
+    if (want_total > s->n || s->n > want_total + want_total / 32 + 16384) s->n = want_total;
+    b->bounds_exact = false;
+    b->n_local = h[DN_LOCAL]; b->n_ghost[0] = h[DN_GHOST]; b->n_ghost[1] = h[DN_GHOST + 1];
+    b->n_bnd[0] = h[DN_BND]; b->n_bnd[1] = h[DN_BND + 1];
+    return PBF_OK;
+}
+
+int halo_refresh_dev(pbf_sim **grp, int ng, bool wide, u32 e) {
+    for (int r = 0; r < ng; r++) {          // all pushes first (virtual ranks share one stream)
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        b->exchanges++;
+        if (!b->has[0] && !b->has[1]) continue;
+        const size_t slot = e % MB_SLOTS;
+        HaloSideDev side[2];
+        for (int k = 0; k < 2; k++) {
+            side[k].idx = b->send_idx[k];
+            side[k].data = b->peer_data[k] ? b->peer_data[k] + slot * mbox_slot_bytes(b) : nullptr;
+            side[k].flag = b->peer_flag[k] ? b->peer_flag[k] + slot : nullptr;
+        }
+        k_halo_push_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side[0], side[1], wide ? s->bufA : s->bufB, wide ? 1 : 0, e, b->push_done);
+        s->launches++;
+    }
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        if (!b->has[0] && !b->has[1]) continue;
+        const size_t slot = e % MB_SLOTS;
+        HaloSideDev side[2];
+        for (int k = 0; k < 2; k++) {
+            side[k].idx = nullptr;
+            side[k].data = b->mbox + ((size_t)k * MB_SLOTS + slot) * mbox_slot_bytes(b);
+            side[k].flag = reinterpret_cast<unsigned long long *>(b->mbox + mbox_flags_offset(b)) + k * MB_SLOTS + slot;
+        }
+        k_halo_pull_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side[0], side[1], b->ghost_sorted, wide ? s->bufA : s->bufB, wide ? 1 : 0, e);
+        s->launches++;
+    }
+    return PBF_OK;
+}
+
+// One step of every rank of `grp`, enqueued without touching the host-side state the device decides (capturable).
+int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
+    // ---- predict, who leaves, leavers into the neighbours' inboxes, compaction ------------------------------------------
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        const NRef nloc = {b->bound_local, s->dn + DN_LOCAL};
+        cudaMemsetAsync(s->flags, 0, sizeof(u32), s->stream);
+        cudaMemsetAsync(b->counters, 0, 16 * sizeof(u32), s->stream);
+        k_step_begin<<<1, 32, 0, s->stream>>>(s->dn);
+        s->launches += 1 + launch_unclear_cells(s);
+        s->launches += launch_predict_range(s, 0, nloc, false);
+        k_mark_leavers<<<nb(b->bound_local), 256, 0, s->stream>>>(nloc, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0], b->has[1],
+                                                                  b->btag, b->list[0], b->list[1], b->counters, b->halo_cap);
+        k_counts_leave<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
+        s->launches += 2;
+        for (int side = 0; side < 2; side++)
+            if (b->has[side]) {
+                k_push_migrants<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[side], s->pos, s->vel, s->pred, b->gid, s->hl,
+                                                                   b->peer_inbox[side], inbox_area_bytes(b), b->halo_cap,
+                                                                   b->rec_done + side);
+                s->launches++;
+            }
+        if (b->has[0] || b->has[1]) {
+            k_find_movers_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, b->btag, b->movers, b->counters);
+            for (int side = 0; side < 2; side++)
+                if (b->has[side]) { k_find_holes_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[side], b->holes, b->counters); s->launches++; }
+            k_fill_holes_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(b->counters, b->holes, b->movers, s->pos, s->vel, s->pred, b->gid, s->hl, s->keys);
+            s->launches += 2;
+        }
+    }
+    // ---- arrivals, boundary layers, ghosts into the neighbours' inboxes --------------------------------------------------
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        const NRef nloc = {b->bound_local, s->dn + DN_LOCAL};
+        char *alo = inbox_area(b->mbox, b, 0), *ahi = inbox_area(b->mbox, b, 1);
+        if (b->has[0] || b->has[1]) {
+            k_pull_migrants<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1],
+                                                               s->pos, s->vel, s->pred, b->gid, s->hl, s->keys, s->grid);
+            s->launches++;
+        }
+        k_counts_arrive<<<1, 32, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1]);
+        k_mark_boundary<<<nb(b->bound_local), 256, 0, s->stream>>>(nloc, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0], b->has[1], b->btag,
+                                                                   b->list[2], b->list[3], b->counters, b->halo_cap);
+        k_counts_boundary<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
+        s->launches += 3;
+        for (int side = 0; side < 2; side++)
+            if (b->has[side]) {
+                k_push_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[2 + side], s->pred, s->pos, s->hl, b->peer_inbox[side],
+                                                                 inbox_area_bytes(b), b->halo_cap, b->rec_done + 2 + side);
+                s->launches++;
+            }
+    }
+    // ---- ghosts in, sort + cells over local + ghost particles --------------------------------------------------------------
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        char *alo = inbox_area(b->mbox, b, 0), *ahi = inbox_area(b->mbox, b, 1);
+        if (b->has[0] || b->has[1]) {
+            k_pull_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1],
+                                                             s->pos, s->vel, s->pred, s->hl, s->keys, s->flags, s->grid);
+            s->launches++;
+        }
+        k_counts_ghosts<<<1, 32, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1]);
+        s->launches++;
+        s->launches += launch_sort_hist(s, s->keys, nref_total(s));
+        s->launches += launch_sort_scan(s);
+        s->launches += launch_sort_passes(s);
+        s->launches += launch_reorder_cells(s);
+        if (b->has[0] || b->has[1]) {
+            cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
+            k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(nref_total(s), NRef{b->bound_local, s->dn + DN_LOCAL}, s->skey, s->perm, b->btag,
+                                                          b->send_idx[0], b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
+                                                          plan_tile_size(), s->grid);
+            s->launches++;
+        }
+        s->launches += launch_highlight(s);
+    }
+    // ---- solver, update, vorticity ------------------------------------------------------------------------------------------
+    const int K = grp[0]->params.num_solver_iterations;
+    u32 e = 0;
+    for (int it = 0; it < K; it++) {
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_lambda(grp[r], nullptr);
+        halo_refresh_dev(grp, ng, false, ++e);
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_delta_p(grp[r], nullptr);
+        halo_refresh_dev(grp, ng, true, ++e);
+    }
+    for (int r = 0; r < ng; r++) grp[r]->launches += launch_update(grp[r]);
+    if (grp[0]->params.vorticity_confinement) {
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_vorticity_a(grp[r], nullptr);
+        halo_refresh_dev(grp, ng, false, ++e);
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_vorticity_b(grp[r]);
+    }
+    for (int r = 0; r < ng; r++) {
+        k_step_end<<<1, 32, 0, grp[r]->stream>>>(grp[r]->dn);
+        grp[r]->launches++;
+    }
+    return PBF_OK;
+}
+
+uint64_t fnv(uint64_t h, const void *p, size_t n) {
+    const unsigned char *c = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) { h ^= c[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+int slab_step_dev(pbf_sim **grp, int ng) {
+    pbf_slab_state *b0 = grp[0]->slab;
+    if (grp[0]->params.num_solver_iterations > 60) { pbf_set_error("slab: more than 60 solver iterations per step"); return PBF_ERR_INVALID; }
+    uint64_t key = 1469598103934665603ull;
+    for (int r = 0; r < ng; r++) {
+        int rc = refresh_bounds(grp[r]);
+        if (rc) return rc;
+        key = fnv(key, &grp[r]->n, 4); key = fnv(key, &grp[r]->slab->bound_local, 4);
+        key = fnv(key, &grp[r]->params, sizeof(pbf_params)); key = fnv(key, &grp[r]->options, sizeof(pbf_options));
+    }
+    cudaStream_t st = grp[0]->stream;
+    const bool graph = b0->use_graph && !grp[0]->timing;
+    if (graph) {
+        if (!b0->graph_exec || b0->graph_key != key) {
+            if (b0->graph_exec) { cudaGraphExecDestroy(b0->graph_exec); cudaGraphDestroy(b0->graph); b0->graph_exec = nullptr; b0->graph = nullptr; }
+            std::vector<uint64_t> before(ng);
+            for (int r = 0; r < ng; r++) before[r] = grp[r]->launches;
+            PBF_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            enqueue_slab_step_dev(grp, ng);
+            cudaError_t e = cudaStreamEndCapture(st, &b0->graph);
+            if (e != cudaSuccess) { b0->graph = nullptr; pbf_set_error(std::string("slab graph capture: ") + cudaGetErrorString(e)); return PBF_ERR_CUDA; }
+            PBF_CUDA(cudaGraphInstantiate(&b0->graph_exec, b0->graph, 0));
+            for (int r = 0; r < ng; r++) { grp[r]->slab->graph_kernels = (u32)(grp[r]->launches - before[r]); grp[r]->launches = before[r]; }
+            b0->graph_key = key;
+        }
+        PBF_CUDA(cudaGraphLaunch(b0->graph_exec, st));
+        for (int r = 0; r < ng; r++) grp[r]->launches += grp[r]->slab->graph_kernels;
+    } else {
+        enqueue_slab_step_dev(grp, ng);
+    }
+    for (int r = 0; r < ng; r++) {
+        pbf_sim *s = grp[r];
+        pbf_slab_state *b = s->slab;
+        b->step++;
+        const int k = (int)(b->step % RING);
+        PBF_CUDA(cudaMemcpyAsync(b->h_ring + (size_t)k * DN_WORDS, s->dn, DN_WORDS * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+        PBF_CUDA(cudaEventRecord(b->ring_ev[k], s->stream));
+        b->ring_step[k] = b->step;
+        s->stage = 0;
+        PBF_CUDA(cudaGetLastError());
+    }
+    return PBF_OK;
+}
+
+// exact counts on the host (download, statistics): waits for the stream
+int sync_counts(pbf_sim *s) {
+    pbf_slab_state *b = s->slab;
+    if (!b->devcount) return PBF_OK;
+    u32 h[DN_WORDS];
+    PBF_CUDA(cudaMemcpyAsync(h, s->dn, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    PBF_CUDA(cudaStreamSynchronize(s->stream));
+    if (h[DN_OVERFLOW]) { pbf_set_error("slab: capacity exceeded on the device; raise the particle / halo capacity"); return PBF_ERR_CAPACITY; }
+    b->n_local = h[DN_LOCAL]; b->n_ghost[0] = h[DN_GHOST]; b->n_ghost[1] = h[DN_GHOST + 1];
+    b->n_bnd[0] = h[DN_BND]; b->n_bnd[1] = h[DN_BND + 1];
+    b->migrated = h[20];
+    return PBF_OK;
+}
+
 int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_global, u32 halo_cap) {
     if (s->slab) { pbf_set_error("slab: already initialised"); return PBF_ERR_STATE; }
     if (z_hi - z_lo < 2) { pbf_set_error("slab: a slab must own at least 2 cell layers"); return PBF_ERR_INVALID; }
@@ -735,11 +1282,20 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     A((void **)&b->mbox, mbox_bytes(b)); A((void **)&b->push_done, 16); A((void **)&b->push_map, (size_t)s->cap * 4);
     b->max_tiles = (s->cap + plan_tile_size() - 1) / plan_tile_size();
     A((void **)&b->push_tiles, (size_t)(1 + b->max_tiles) * 4);
+    A((void **)&b->rec_done, 16);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_counters, 16 * 4);
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_ring, (size_t)RING * DN_WORDS * 4);
+    for (int k = 0; k < RING && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&b->ring_ev[k], cudaEventDisableTiming);
     if (e != cudaSuccess) { pbf_set_error(std::string("slab: allocation failed: ") + cudaGetErrorString(e)); return PBF_ERR_CUDA; }
     cudaMemsetAsync(b->gid, 0, (size_t)s->cap * 4, s->stream);
     cudaMemsetAsync(b->mbox, 0, mbox_bytes(b), s->stream);
     cudaMemsetAsync(b->push_done, 0, 16, s->stream);
+    cudaMemsetAsync(b->rec_done, 0, 16, s->stream);
+    cudaMemsetAsync(s->dn, 0, DN_WORDS * sizeof(u32), s->stream);
+    {
+        const char *g = getenv("PBF_SLAB_GRAPH");
+        b->use_graph = !(g && g[0] == '0');
+    }
     cudaStreamSynchronize(s->stream);      // the mailbox flags are zero before any neighbour can see them
     s->slab = b;
     if (s->graph_valid) { cudaGraphExecDestroy(s->graph_exec); cudaGraphDestroy(s->graph); s->graph_valid = false; s->graph = nullptr; s->graph_exec = nullptr; }
@@ -751,6 +1307,23 @@ void p2p_attach(pbf_slab_state *b, int side, char *peer_mbox) {
     const int theirs = side == 0 ? 1 : 0;
     b->peer_data[side] = peer_mbox + (size_t)theirs * MB_SLOTS * mbox_slot_bytes(b);
     b->peer_flag[side] = reinterpret_cast<unsigned long long *>(peer_mbox + mbox_flags_offset(b)) + theirs * MB_SLOTS;
+    b->peer_inbox[side] = inbox_area(peer_mbox, b, theirs);
+}
+
+// Device-side counts need the peer-memory transport (records go into the neighbour's inbox) and the separate push kernels;
+// PBF_SLAB_DEVCOUNT=0 keeps the step that reads its counts back twice (the baseline it is measured against).
+void enable_devcount(pbf_sim *s) {
+    pbf_slab_state *b = s->slab;
+    const char *dc = getenv("PBF_SLAB_DEVCOUNT");
+    b->devcount = b->p2p && !b->fused && !(dc && dc[0] == '0');
+    if (!b->devcount) return;
+    s->n_dev = s->dn + DN_TOTAL;
+    s->n_prev_dev = s->dn + DN_PREV;
+    const u32 n = b->n_local;
+    cudaMemcpyAsync(s->dn + DN_LOCAL, &n, 4, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(s->dn + DN_TOTAL, &n, 4, cudaMemcpyHostToDevice, s->stream);
+    cudaStreamSynchronize(s->stream);
+    set_bounds_exact(s, n);
 }
 
 }  // namespace
@@ -767,6 +1340,11 @@ void slab_free(pbf_sim *s) {
     if (b->push_done) cudaFree(b->push_done);
     if (b->push_map) cudaFree(b->push_map);
     if (b->push_tiles) cudaFree(b->push_tiles);
+    if (b->rec_done) cudaFree(b->rec_done);
+    if (b->h_ring) cudaFreeHost(b->h_ring);
+    for (int k = 0; k < RING; k++)
+        if (b->ring_ev[k]) cudaEventDestroy(b->ring_ev[k]);
+    if (b->graph_exec) { cudaGraphExecDestroy(b->graph_exec); cudaGraphDestroy(b->graph); }
     void *ptrs[] = {b->gid, b->btag, b->list[0], b->list[1], b->list[2], b->list[3], b->movers, b->holes, b->counters, b->send[0],
                     b->send[1], b->recv[0], b->recv[1], b->send_idx[0], b->send_idx[1], b->ghost_sorted};
     for (void *p : ptrs)
@@ -805,6 +1383,10 @@ int pbf_slab_init(pbf_handle s, const void *id128, int rank, int nranks, int z_l
         ncclResult_t r = g_nccl.CommInitRank(&s->slab->comm, nranks, id, rank);
         if (r != ncclSuccess) { pbf_set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r)); rc = PBF_ERR_NCCL; }
     }
+    if (rc == PBF_OK && nranks == 1) {      // a lone rank has nobody to exchange with: device-side counts need no connection
+        s->slab->p2p = true;
+        enable_devcount(s);
+    }
     cudaSetDevice(prev);
     return rc;
 }
@@ -841,6 +1423,7 @@ int pbf_slab_p2p_connect(pbf_handle s, const void *lo64, const void *hi64) {
     b->p2p = true;
     const char *fz = getenv("PBF_SLAB_FUSED");     // measured slower than the separate push kernel: opt in
     b->fused = fz && fz[0] == '1';
+    enable_devcount(s);
     return PBF_OK;
 }
 
@@ -869,6 +1452,7 @@ int pbf_slab_init_group(pbf_handle *hs, int n, const int32_t *z_planes, int gz_g
             b->p2p = true;
             const char *fz = getenv("PBF_SLAB_FUSED");
             b->fused = fz && fz[0] == '1';
+            enable_devcount(hs[r]);
         }
     return PBF_OK;
 }
@@ -886,9 +1470,14 @@ int pbf_slab_upload(pbf_handle s, const float *pos4, const float *vel4, const ui
     else PBF_CUDA(cudaMemsetAsync(s->vel, 0, (size_t)n * 16, s->stream));
     PBF_CUDA(cudaMemsetAsync(s->hl, 0, (size_t)n * 4, s->stream));
     PBF_CUDA(cudaMemcpyAsync(s->slab->gid, gid, (size_t)n * 4, cudaMemcpyHostToDevice, s->stream));
+    if (s->slab->devcount) {
+        const u32 nn = n;
+        PBF_CUDA(cudaMemcpyAsync(s->dn + DN_LOCAL, &nn, 4, cudaMemcpyHostToDevice, s->stream));
+    }
     PBF_CUDA(cudaStreamSynchronize(s->stream));
     s->n = n;
     s->slab->n_local = n;
+    if (s->slab->devcount) set_bounds_exact(s, n);
     cudaSetDevice(prev);
     return PBF_OK;
 }
@@ -898,6 +1487,7 @@ int pbf_slab_download(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, uin
     int prev;
     cudaGetDevice(&prev);
     cudaSetDevice(s->device);
+    { const int rc = sync_counts(s); if (rc) { cudaSetDevice(prev); return rc; } }
     const u32 m = s->slab->n_local;
     if (n) *n = m;
     if (pos4) PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)m * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -912,6 +1502,7 @@ int pbf_slab_download(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, uin
 int pbf_slab_download_highlight(pbf_handle s, uint32_t *highlight) {
     if (!s || !s->slab || !highlight) { pbf_set_error("pbf_slab_download_highlight: slab not initialised or null buffer"); return PBF_ERR_STATE; }
     DeviceGuard guard(s->device);
+    { const int rc = sync_counts(s); if (rc) return rc; }
     PBF_CUDA(cudaMemcpyAsync(highlight, s->hl, (size_t)s->slab->n_local * 4, cudaMemcpyDeviceToHost, s->stream));
     PBF_CUDA(cudaStreamSynchronize(s->stream));
     return PBF_OK;
@@ -925,8 +1516,10 @@ int pbf_slab_step(pbf_handle s, int nsteps) {
     cudaSetDevice(s->device);
     int rc = PBF_OK;
     for (int i = 0; i < nsteps && rc == PBF_OK; i++) {
-        if (s->slab->group) rc = slab_step(s->slab->group, s->slab->group_size);
-        else { pbf_sim *one[1] = {s}; rc = slab_step(one, 1); }
+        pbf_sim *one[1] = {s};
+        pbf_sim **grp = s->slab->group ? s->slab->group : one;
+        const int ng = s->slab->group ? s->slab->group_size : 1;
+        rc = grp[0]->slab->devcount ? slab_step_dev(grp, ng) : slab_step(grp, ng);
     }
     cudaSetDevice(prev);
     return rc;
@@ -947,8 +1540,16 @@ int pbf_slab_step_host(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, ui
     PBF_CUDA(cudaMemcpyAsync(s->slab->gid, gid, (size_t)n_in * 4, cudaMemcpyHostToDevice, s->stream));
     s->n = n_in;
     s->slab->n_local = n_in;
-    const int rc = pbf_slab_step(s, nsteps);
+    if (s->slab->devcount) {
+        PBF_CUDA(cudaMemcpyAsync(s->dn + DN_LOCAL, &n_in, 4, cudaMemcpyHostToDevice, s->stream));
+        set_bounds_exact(s, n_in);
+    }
+    int rc = pbf_slab_step(s, nsteps);
     if (rc) return rc;
+    if (s->slab->devcount) {       // the one wait of the call: the counts the copies below are sized by
+        rc = sync_counts(s);
+        if (rc) return rc;
+    }
     const u32 m = s->slab->n_local;
     if (m > capacity) { pbf_set_error("pbf_slab_step_host: more particles than the caller's arrays hold"); return PBF_ERR_CAPACITY; }
     PBF_CUDA(cudaMemcpyAsync(pos4, s->pos, (size_t)m * 16, cudaMemcpyDeviceToHost, s->stream));
@@ -964,6 +1565,7 @@ int pbf_slab_step_host(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, ui
 int pbf_slab_stats(pbf_handle s, uint64_t out[8]) {
     if (!s || !s->slab || !out) { pbf_set_error("pbf_slab_stats: slab not initialised"); return PBF_ERR_STATE; }
     pbf_slab_state *b = s->slab;
+    { DeviceGuard guard(s->device); const int rc = sync_counts(s); if (rc) return rc; }
     out[0] = b->n_local; out[1] = b->n_ghost[0]; out[2] = b->n_ghost[1]; out[3] = b->n_bnd[0]; out[4] = b->n_bnd[1];
     out[5] = b->migrated; out[6] = b->exchanges; out[7] = b->bytes_sent;
     return PBF_OK;

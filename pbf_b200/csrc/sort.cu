@@ -84,9 +84,10 @@ __global__ void __launch_bounds__(R) k_sort_scan(u32 *__restrict__ hist, u32 *__
 // digit histograms of every pass.  Cell keys of neighbouring ids share most digits (plain shared atomics would
 // serialise 32 lanes on one bin, match.any costs a pass over the distinct values): every thread takes 16 consecutive
 // keys and run-length encodes each digit stream in registers, one shared atomic per run.
-__global__ void __launch_bounds__(256) k_sort_hist(const u32 *__restrict__ keys, u32 n, SortPlan plan,
+__global__ void __launch_bounds__(256) k_sort_hist(const u32 *__restrict__ keys, NRef nr, SortPlan plan,
                                                     u32 *__restrict__ hist) {
     __shared__ u32 sh[4 * R];
+    const u32 n = nref(nr);
     for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const u32 chunks = (n + 15u) >> 4;
@@ -131,13 +132,18 @@ __global__ void __launch_bounds__(256) k_sort_hist(const u32 *__restrict__ keys,
 template <bool IOTA>
 __global__ void __launch_bounds__(SORT_BLOCK, PBF_SORT_CTAS)
 k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32 *__restrict__ keys_out,
-           u32 *__restrict__ vals_out, u32 n, int shift, u32 dmask, const u32 *__restrict__ gbase,
+           u32 *__restrict__ vals_out, NRef nr, int shift, u32 dmask, const u32 *__restrict__ gbase,
            u32 *status, u32 *tile_counter) {
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
     SortSmem &S = *reinterpret_cast<SortSmem *>(sort_smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // tiles are handed out in launch order so that every tile a look-back waits on is already resident
+    const u32 n = nref(nr);
+    // Tiles are handed out in launch order so that every tile a look-back waits on is already resident (or done).  A block
+    // takes tiles until none is left: normally exactly one (the grid is sized for n), more when the grid was sized for a
+    // stale bound of a count that lives on the device (NRef).
+    for (;;) {
+    __syncthreads();                                   // the previous tile's staging area is free
     if (tid == 0) S.tile = atomicAdd(tile_counter, 1u);
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; w++) { S.wh[w][tid] = 0; S.wh[w][tid + SORT_BLOCK] = 0; }
@@ -295,19 +301,22 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
         keys_out[dst] = k;
         vals_out[dst] = S.vals[slot];
     }
+    if (nr.p == nullptr) return;                       // count known on the host: the grid has one block per tile
+    }
 }
 
-int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, u32 n, const u32 *gbase) {
-    const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
+int run_passes(pbf_sim *s, const SortPlan &plan, const u32 *kin, const u32 *vin, u32 *kout, u32 *vout, NRef n, const u32 *gbase) {
+    // status words for every tile the count could ever need (capacity), blocks for the bound
+    const u32 tiles = (n.n + SORT_TILE - 1) / SORT_TILE, st_tiles = n.p ? s->max_tiles : tiles;
     if (tiles == 0) return 0;
-    cudaMemsetAsync(s->status, 0, (size_t)plan.passes * tiles * R * sizeof(u32), s->stream);
+    cudaMemsetAsync(s->status, 0, (size_t)plan.passes * st_tiles * R * sizeof(u32), s->stream);
     int launched = 0;
     for (int p = 0; p < plan.passes; p++) {
         const u32 *ki = p == 0 ? kin : s->ktmp[(p - 1) & 1];
         const u32 *vi = p == 0 ? vin : s->vtmp[(p - 1) & 1];
         u32 *ko = p == plan.passes - 1 ? kout : s->ktmp[p & 1];
         u32 *vo = p == plan.passes - 1 ? vout : s->vtmp[p & 1];
-        u32 *st = s->status + (size_t)p * tiles * R;
+        u32 *st = s->status + (size_t)p * st_tiles * R;
         if (p == 0 && vin == nullptr)
             k_onesweep<true><<<tiles, SORT_BLOCK, sizeof(SortSmem), s->stream>>>(ki, nullptr, ko, vo, n, plan.shift[p], plan.mask[p],
                                                                                  gbase + p * R, st, s->tile_counter + p);
@@ -354,12 +363,12 @@ int launch_sort_scan(pbf_sim *s) {
 
 // the simulation's sort: keys by id (histograms already accumulated by k_predict), values = iota
 int launch_sort_passes(pbf_sim *s) {
-    return run_passes(s, s->plan, s->keys, nullptr, s->skey, s->perm, s->n, s->gbase);
+    return run_passes(s, s->plan, s->keys, nullptr, s->skey, s->perm, nref_total(s), s->gbase);
 }
 
 // digit histograms of every pass of the handle's plan over keys[0..n) (slab mode: keys change after k_predict)
-int launch_sort_hist(pbf_sim *s, const u32 *keys, u32 n) {
-    int blocks = (int)(((n + 15) / 16 + 255) / 256);
+int launch_sort_hist(pbf_sim *s, const u32 *keys, NRef n) {
+    int blocks = (int)(((n.n + 15) / 16 + 255) / 256);
     int maxb = s->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
@@ -380,7 +389,7 @@ int launch_sort_pairs(pbf_sim *s, const u32 *kin, const u32 *vin, u32 *kout, u32
     // pbf_sort must not disturb the histograms the simulation's sort is about to scan
     u32 *hist = s->hist + 4 * R, *gbase = s->gbase + 4 * R;
     cudaMemsetAsync(hist, 0, 4 * R * sizeof(u32), s->stream);
-    k_sort_hist<<<blocks, 256, 0, s->stream>>>(kin, n, plan, hist);
+    k_sort_hist<<<blocks, 256, 0, s->stream>>>(kin, NRef{n, nullptr}, plan, hist);
     k_sort_scan<<<plan.passes, R, 0, s->stream>>>(hist, gbase, s->tile_counter);
-    return 2 + run_passes(s, plan, kin, vin, kout, vout, n, gbase);
+    return 2 + run_passes(s, plan, kin, vin, kout, vout, NRef{n, nullptr}, gbase);
 }

@@ -61,14 +61,17 @@ constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays
 
 // ---- the plan: one block per tile ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TL)
-k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
+k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
        int *__restrict__ desc, u32 *__restrict__ runs, GridInfo g, int allow) {
     constexpr int NW = TL / 32;
     __shared__ int wS[NW][9], wE[NW][9];          // per warp: first / one-past-last sorted slot its runs of row o touch
     __shared__ int sS[9], sN[9], sBase[9];         // per tile: range start, length, (image offset of the range) - start
     __shared__ int sMeta[4];                       // phases, records, cuts, "every range fits one image"
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 i = blockIdx.x * (u32)TL + tid;
+    const u32 n = nref(nr);
+    // one tile per block; the loop only turns when the grid was sized for fewer particles than there are (NRef)
+    for (u32 tile = blockIdx.x; tile * (u32)TL < n; tile += gridDim.x) {
+    const u32 i = tile * (u32)TL + tid;
     int2 r[9];
 #pragma unroll
     for (int o = 0; o < 9; o++) r[o] = make_int2(-1, 0);
@@ -160,17 +163,21 @@ k_plan(u32 n, const u32 *__restrict__ home, const int2 *__restrict__ runs3, cons
         for (int o = 0; o < 9; o++) self_in = self_in || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);
     }
     if (self_in) w[4] |= 1u << 16;
-    u32 *out = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
+    u32 *out = runs + (size_t)tile * RUN_WORDS * TL + tid;
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
     fits = __syncthreads_and(fits) && sMeta[3] && nph <= TL_PHASES && allow;
-    int *d = desc + (size_t)blockIdx.x * TL_DESC;
+    int *d = desc + (size_t)tile * TL_DESC;
     if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = sMeta[1]; d[D_CUT] = sMeta[2]; }
     if (tid < 9) { d[D_S + tid] = sS[tid]; d[D_N + tid] = sN[tid]; }
+    __syncthreads();                               // the shared tables are free for the next tile
+    }
 }
 
 // ---- tile frame of the sweeps -------------------------------------------------------------------------------------------
 struct TileCtx {
+    u32 tile;            // this block's tile (normally blockIdx.x) and the number of tiles of the launch's particle count
+    u32 ntiles;
     int mode;            // staging phases of the tiled path (1 for almost every tile), 0 = general path
     u32 cut;             // first range of every phase, 4 bits each, closed by 9
     bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
@@ -233,13 +240,15 @@ __device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, cons
 template <int NSRC>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
-                                              const u32 *__restrict__ runs, int tid) {
-    const int *dg = desc + (size_t)blockIdx.x * TL_DESC;
+                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_) {
+    const int *dg = desc + (size_t)tile * TL_DESC;
     TileCtx c;
+    c.tile = tile;
+    c.ntiles = ntiles_;
     c.mode = __ldg(dg + D_MODE);
     c.cut = (u32)__ldg(dg + D_CUT);
     c.img = (unsigned)__cvta_generic_to_shared(dsm);
-    const u32 *rp = runs + (size_t)blockIdx.x * RUN_WORDS * TL + tid;
+    const u32 *rp = runs + (size_t)tile * RUN_WORDS * TL + tid;
     u32 w[RUN_WORDS];
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) w[k] = __ldg(rp + k * TL);   // in flight while the bulk copies land
@@ -253,8 +262,8 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     // two DRAM round trips.  Warp 2 does this while the block waits for its own image anyway.
     constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the ten prefetching threads
     if (tid >= PF0 && tid < PF0 + 10) {
-        const u32 ft = blockIdx.x + (u32)PBF_PREFETCH_DIST;
-        if (ft < gridDim.x) {
+        const u32 ft = tile + (u32)PBF_PREFETCH_DIST;
+        if (ft < ntiles_) {
             const int *fd = desc + (size_t)ft * TL_DESC;
             const int o = tid - PF0;
             if (o < 9) {
@@ -365,7 +374,7 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
         const int hi = (int)((c.cut >> (4 * ph + 4)) & 15u);
         if (ph > 0) {
             __syncthreads();                               // everybody is done with the previous phase's image
-            if (tid == 0) tile_stage<NSRC>(dsm, mb, src0, src1, desc + (size_t)blockIdx.x * TL_DESC, lo, hi);
+            if (tid == 0) tile_stage<NSRC>(dsm, mb, src0, src1, desc + (size_t)c.tile * TL_DESC, lo, hi);
         }
         mbar_wait(mb, (unsigned)(ph & 1));
 #pragma unroll 1
@@ -433,6 +442,21 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
     }
 }
 
+// Every sweep kernel: one tile per block; the loop only turns when the grid was sized for fewer particles than there are
+// (NRef: a slab rank's count lives on the device).  Before a block reuses its image and its mbarrier for another tile
+// everybody must be done with them and the barrier object must be invalidated.
+#define TILE_LOOP_BEGIN                                                                  \
+    const u32 n = nref(nr), ntl = (n + (u32)TL - 1u) / (u32)TL;                          \
+    for (u32 tile = blockIdx.x; tile < ntl; tile += gridDim.x) {
+#define TILE_LOOP_END(tc)                                                                \
+        if (tile + gridDim.x < ntl) {                                                    \
+            __syncthreads();                                                             \
+            if ((tc).mode && tid == 0)                                                   \
+                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&mbar)) : "memory"); \
+            __syncthreads();                                                             \
+        }                                                                                \
+    }
+
 #define TILE_ARGS const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,   \
                   const int *__restrict__ desc, const u32 *__restrict__ runs
 
@@ -440,13 +464,14 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
 // out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
 template <bool DIAG>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
-k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag,
+k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag,
          const HaloPush hp) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    TileCtx tc = tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid);
-    const u32 i = blockIdx.x * TL + tid;
+    TILE_LOOP_BEGIN
+    TileCtx tc = tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
+    const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -488,7 +513,9 @@ k_lambda(u32 n, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B,
             for (int w = 0; w < TL / 32; w++) s += (double)red[w];
             atomicAdd(diag, s);
         }
+        __syncthreads();
     }
+    TILE_LOOP_END(tc)
 }
 
 // ---- K9 updatepos.glsl:43-105, Jacobi: reads B {p, lambda}, writes A -----------------------------------------------
@@ -504,13 +531,14 @@ struct UpdateArgs {
 
 template <int FINAL>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
-k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp,
+k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp,
           const UpdateArgs up) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
-    const u32 i = blockIdx.x * TL + tid;
+    TILE_LOOP_BEGIN
+    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     u32 id = 0;
@@ -560,18 +588,20 @@ k_delta_p(u32 n, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A
         else up.vel[id] = v;
     }
     halo_push(hp, i, live, out, true, tid);
+    TILE_LOOP_END(tc)
 }
 
 // ---- K11 vorticity.glsl:34-60 (first sweep): XSPH + vorticity ------------------------------------------------------------
 // out: vprime = v + c*sum v_ij W, omega = sum v_ij x gradW, B = {p, |omega|}
 __global__ void __launch_bounds__(TL)
-k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
+k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
               float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P, const HaloPush hp) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    TileCtx tc = tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid);
-    const u32 i = blockIdx.x * TL + tid;
+    TILE_LOOP_BEGIN
+    TileCtx tc = tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl);
+    const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -602,17 +632,19 @@ k_vorticity_a(u32 n, const float4 *__restrict__ A, const float4 *__restrict__ sv
         B[i] = out;
     }
     halo_push(hp, i, live, out, false, tid);
+    TILE_LOOP_END(tc)
 }
 
 // ---- K11 vorticity.glsl:65-85 (second sweep): confinement force, velocity[id] written once -------------------------------
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
-k_vorticity_b(u32 n, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
+k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
               const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
-    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid);
-    const u32 i = blockIdx.x * TL + tid;
+    TILE_LOOP_BEGIN
+    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
@@ -623,15 +655,17 @@ k_vorticity_b(u32 n, const float4 *__restrict__ B, const float4 *__restrict__ vp
         ey = __ffma2_rn(cc, q.dy, ey);
         ez = __ffma2_rn(cc, q.dz, ez);
     });
-    if (!live) return;
-    float nx = SPIKY_GRAD * (ex.x + ex.y), ny = SPIKY_GRAD * (ey.x + ey.y), nz = SPIKY_GRAD * (ez.x + ez.y);
-    const float l = sqrtf(nx * nx + ny * ny + nz * nz);
-    if (l > 0.0f) { nx /= l; ny /= l; nz /= l; }
-    const float4 w = omega[i];
-    const float4 v = vprime[i];
-    const float s = P.timestep * P.vort_eps;
-    vel[perm[i]] = make_float4(v.x + s * (ny * w.z - w.y * nz), v.y + s * (nz * w.x - w.z * nx),
-                               v.z + s * (nx * w.y - w.x * ny), 0.0f);       // cross(N, omega)
+    if (live) {
+        float nx = SPIKY_GRAD * (ex.x + ex.y), ny = SPIKY_GRAD * (ey.x + ey.y), nz = SPIKY_GRAD * (ez.x + ez.y);
+        const float l = sqrtf(nx * nx + ny * ny + nz * nz);
+        if (l > 0.0f) { nx /= l; ny /= l; nz /= l; }
+        const float4 w = omega[i];
+        const float4 v = vprime[i];
+        const float s = P.timestep * P.vort_eps;
+        vel[perm[i]] = make_float4(v.x + s * (ny * w.z - w.y * nz), v.y + s * (nz * w.x - w.z * nx),
+                                   v.z + s * (nx * w.y - w.x * ny), 0.0f);   // cross(N, omega)
+    }
+    TILE_LOOP_END(tc)
 }
 
 inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
@@ -656,7 +690,7 @@ int sweeps_init(void) {
 }
 
 int launch_plan(pbf_sim *s) {
-    k_plan<<<ntiles(s->n), TL, 0, s->stream>>>(s->n, s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
+    k_plan<<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
                                                s->tiled_sweeps ? 1 : 0);
     return 1;
 }
@@ -664,13 +698,13 @@ int launch_plan(pbf_sim *s) {
 static const HaloPush NO_PUSH = {};
 
 int launch_lambda(pbf_sim *s, const HaloPush *push) {
-    k_lambda<false><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
+    k_lambda<false><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
                                                               nullptr, push ? *push : NO_PUSH);
     return 1;
 }
 
 int launch_delta_p(pbf_sim *s, const HaloPush *push) {
-    k_delta_p<0><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s),
+    k_delta_p<0><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s),
                                                            push ? *push : NO_PUSH, UpdateArgs{});
     return 1;
 }
@@ -679,20 +713,20 @@ int launch_delta_p(pbf_sim *s, const HaloPush *push) {
 int launch_delta_p_update(pbf_sim *s) {
     const UpdateArgs up = {s->perm, s->pos, s->vel, s->svel};
     if (s->params.vorticity_confinement)
-        k_delta_p<2><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
+        k_delta_p<2><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
     else
-        k_delta_p<1><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
+        k_delta_p<1><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
     return 1;
 }
 
 int launch_vorticity_a(pbf_sim *s, const HaloPush *push) {
-    k_vorticity_a<<<ntiles(s->n), TL, TL_SMEM2, s->stream>>>(s->n, s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
+    k_vorticity_a<<<ntiles(s->n), TL, TL_SMEM2, s->stream>>>(nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
                                                             s->omega, s->grid, sim_params(s), push ? *push : NO_PUSH);
     return 1;
 }
 
 int launch_vorticity_b(pbf_sim *s) {
-    k_vorticity_b<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
+    k_vorticity_b<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
                                                             s->vel, s->grid, sim_params(s));
     return 1;
 }
@@ -700,7 +734,7 @@ int launch_vorticity_b(pbf_sim *s) {
 int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s, nullptr) + launch_vorticity_b(s); }
 
 int launch_density_diag(pbf_sim *s) {
-    k_lambda<true><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(s->n, s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
+    k_lambda<true><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
                                                              s->diag, NO_PUSH);
     return 1;
 }

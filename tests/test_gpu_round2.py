@@ -323,3 +323,50 @@ def test_cuda_against_reference_shaders_live(built_lib):
             gp, gv = sph.download()
             assert np.max(np.abs(gp - rp)) < POS_TOL and np.max(np.abs(gv - rv)) < VEL_TOL, step
             sph.upload(rp, rv)                    # continue from identical states: the comparison stays a one-step one
+
+
+@pytest.mark.parametrize("mode", ["graph", "direct", "starved", "readback"])
+def test_virtual_slabs_device_side_counts(built_lib, mode, monkeypatch):
+    """The slab step without host round trips (device-side counts, records through the neighbour's inbox, one CUDA graph
+    per step) against the single-domain run, on the splash scene (whole layers change owner): as a replayed graph, as
+    direct launches, with grid bounds a third of the particle count (every kernel loops over its device-side count), and
+    the older step that reads its counts back twice per step."""
+    import scenes
+    from pbf_b200 import slab
+    monkeypatch.setenv("PBF_SLAB_GRAPH", "0" if mode == "direct" else "1")
+    monkeypatch.setenv("PBF_SLAB_STARVE_BOUNDS", "1" if mode == "starved" else "0")
+    monkeypatch.setenv("PBF_SLAB_DEVCOUNT", "0" if mode == "readback" else "1")
+    grid = (128, 64, 128)
+    pos, vel = scenes.splash()
+    single = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+    single.SetNumSolverIterations(3)
+    single.SetVorticityConfinementEnabled(True)
+    single.upload(pos, vel)
+    grp = slab.VirtualGroup(pos, vel, 3, grid, halo_capacity=8192, slack=2.5)
+    grp.set_params(num_solver_iterations=3, vorticity_confinement=1)
+    single.Run(8)
+    grp.Run(5)                                   # several steps enqueued back to back: nothing waits for the device
+    grp.Run(3)
+    spos, svel = single.download()
+    gpos, gvel = grp.gather()
+    assert np.max(np.abs(spos - gpos)) < 5e-4
+    assert np.max(np.abs(svel - gvel)) < 5e-4 / 0.016
+    st = [s.stats() for s in grp.ranks]
+    assert sum(x["n_local"] for x in st) == pos.shape[0]
+    assert sum(x["migrated"] for x in st) > 500
+    assert all(x["ghosts_lo"] + x["ghosts_hi"] > 0 for x in st)
+    grp.close()
+
+
+def test_slab_capacity_overflow_is_reported(built_lib):
+    """More leavers than the record capacity: the device flags it, the next call reports PBF_ERR_CAPACITY (no silent loss)."""
+    import scenes
+    from pbf_b200 import slab
+    pos, vel = scenes.splash()
+    vel[:, 2] = np.where(pos[:, 2] < 50, 400.0, -400.0)          # everybody crosses the plane at once
+    grp = slab.VirtualGroup(pos, vel, 2, (128, 64, 128), halo_capacity=512, slack=2.5)
+    grp.set_params(num_solver_iterations=1)
+    with pytest.raises(RuntimeError, match="capacity"):
+        grp.Run(2)
+        grp.gather()
+    grp.close()
