@@ -101,10 +101,15 @@ int pbf_get_params(pbf_handle h, pbf_params *p);
  *   wall_restitution   updatepos.glsl:98-100 clamps positions to the walls and update.glsl derives the velocity from the
  *                      clamped position, which leaves a particle pressed against a wall with whatever normal velocity
  *                      the clamp implies.  >= 0: a particle on a wall moving outwards gets v_n <- -e * v_n in update
- *                      (0 = sticks, 1 = elastic).  < 0: off. */
+ *                      (0 = sticks, 1 = elastic).  < 0: off.
+ *   full_support       the kernels have support h = 2 cells, but FOR_EACH_NEIGHBOUR only visits the 27 cells around a
+ *                      particle (neighbourcells.glsl:37-47), so every sum is truncated at about one cell; 1 visits all
+ *                      5 x 5 x 5 cells the support reaches (25 rows of five cells).  Several times the work per sweep; the
+ *                      neighbour runs walk from global memory, not through the tiled shared-memory path. */
 typedef struct {
     int32_t density_self_term;
     float wall_restitution;
+    int32_t full_support;
 } pbf_options;
 int pbf_set_options(pbf_handle h, const pbf_options *o);
 int pbf_get_options(pbf_handle h, pbf_options *o);

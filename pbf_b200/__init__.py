@@ -32,7 +32,7 @@ class Params(C.Structure):
 
 class Options(C.Structure):
     """pbf_options (include/pbf_c.h): opt-in corrections of reference defects, all off by default."""
-    _fields_ = [("density_self_term", C.c_int32), ("wall_restitution", C.c_float)]
+    _fields_ = [("density_self_term", C.c_int32), ("wall_restitution", C.c_float), ("full_support", C.c_int32)]
 
 
 class StateInfo(C.Structure):
@@ -168,7 +168,7 @@ def write_state_file(path, pos, vel=None, highlight=None, grid=(128, 64, 128), w
     highlight = None if highlight is None else np.ascontiguousarray(highlight, np.uint32)
     info = StateInfo(pos.shape[0], (C.c_int32 * 3)(*grid), (C.c_float * 3)(*wall), int(ref_quirks),
                      params if params is not None else default_params(), steps,
-                     options if options is not None else Options(0, -1.0))
+                     options if options is not None else Options(0, -1.0, 0))
     _check(lib().pbf_state_file_write(os.fsencode(path), C.byref(info), _ptr(pos), _ptr(vel), _ptr(highlight)))
 
 
@@ -236,14 +236,17 @@ class SPH:
     def set_params(self, p):
         _check(lib().pbf_set_params(self._h, C.byref(p)))
 
-    def set_options(self, density_self_term=None, wall_restitution=None):
-        """Opt-in corrections (not in the reference): self term in the density, velocity reflection at the walls."""
+    def set_options(self, density_self_term=None, wall_restitution=None, full_support=None):
+        """Opt-in corrections (not in the reference): self term in the density, velocity reflection at the walls, neighbour
+        search over the whole kernel support (5 x 5 x 5 cells instead of 3 x 3 x 3)."""
         o = Options()
         _check(lib().pbf_get_options(self._h, C.byref(o)))
         if density_self_term is not None:
             o.density_self_term = int(bool(density_self_term))
         if wall_restitution is not None:
             o.wall_restitution = wall_restitution
+        if full_support is not None:
+            o.full_support = int(bool(full_support))
         _check(lib().pbf_set_options(self._h, C.byref(o)))
 
     def get_options(self):

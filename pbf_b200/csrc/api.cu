@@ -175,6 +175,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     pbf_default_params(&s->params);
     s->options.density_self_term = 0;
     s->options.wall_restitution = -1.0f;
+    s->options.full_support = 0;
 
     DeviceGuard guard(dev);
 #define ALLOC(ptr, count)                                                                                       \

@@ -37,7 +37,7 @@ struct Header {                 // 128 bytes
     int32_t self_term;          // pbf_options; all-zero (files written before the options existed) = everything off
     int32_t has_restitution;
     float restitution;
-    uint8_t reserved[4];
+    int32_t full_support;       // was reserved (zero) in files written before the option existed
 };
 static_assert(sizeof(Header) == 128, "state file header is 128 bytes");
 
@@ -85,6 +85,7 @@ void to_info(const Header &hd, pbf_state_info *info) {
     info->steps = hd.steps;
     info->options.density_self_term = hd.self_term;
     info->options.wall_restitution = hd.has_restitution ? hd.restitution : -1.0f;
+    info->options.full_support = hd.full_support;
 }
 
 }  // namespace
@@ -113,6 +114,7 @@ int pbf_state_file_write(const char *path, const pbf_state_info *info, const flo
     hd.self_term = info->options.density_self_term;
     hd.has_restitution = info->options.wall_restitution >= 0.0f ? 1 : 0;
     hd.restitution = hd.has_restitution ? info->options.wall_restitution : 0.0f;
+    hd.full_support = info->options.full_support;
     hd.checksum = payload_sum(pos4, vel4, highlight, n);
     // write next to the target and rename: a crash never leaves a half-written file under the final name
     const std::string tmp = std::string(path) + ".part";

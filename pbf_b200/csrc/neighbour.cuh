@@ -49,24 +49,61 @@ __device__ __forceinline__ void fetch_runs(const u32 home, const GridInfo &g, co
     }
 }
 
+// Opt-in "full support" search (pbf_options::full_support): the kernels have support h = 2 cells but
+// the reference only visits the 27 cells around a particle (neighbourcells.glsl:37-47), truncating every sum.  RAD = 2
+// visits 5 x 5 x 5 cells: 25 rows (dy, dz in -2..2, dy outermost as in gridoffsets[]), each the cells x-2..x+2 merged
+// like neighbourcells.glsl:62-84 merges three.
+template <int RAD>
+__device__ __forceinline__ int2 merge_row(const int2 *__restrict__ cells, int base, int x, int gx) {
+    int cell = -1, entries = 0;
+#pragma unroll
+    for (int j = -RAD; j <= RAD; j++) {
+        const int xx = x + j;
+        if (xx >= 0 && xx < gx) {
+            const int2 c = cells[base + xx];
+            if (cell == -1) cell = c.x;
+            if (c.x != -1) entries += c.y - c.x;
+        }
+    }
+    return make_int2(cell, cell == -1 ? 0 : entries);
+}
+
 // The thread's non-empty runs {start,end} into shared memory.  Returns their number; *slots = number of aligned
 // candidate pairs over all runs; *self_in = whether the particle's own slot lies in one of its runs, i.e. whether
 // FOR_EACH_NEIGHBOUR would have skipped `self`.
-template <int BLOCK>
+template <int BLOCK, int RAD = 1>
 __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const GridInfo &g, const int2 *__restrict__ runs3,
                                          const int2 *__restrict__ cells, int2 *srun, int tid, int *slots, bool *self_in) {
-    int2 r[9];
-    fetch_runs(home, g, runs3, cells, r);
     int cnt = 0, tot = 0;
     bool self = false;
+    if (RAD == 1) {
+        int2 r[9];
+        fetch_runs(home, g, runs3, cells, r);
 #pragma unroll
-    for (int o = 0; o < 9; o++) {
-        self = self || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);   // see k_plan: any run may hold the particle itself
-        if (r[o].y > 0) {
-            const int s = r[o].x, e = r[o].x + r[o].y;
-            srun[cnt * BLOCK + tid] = make_int2(s, e);
-            cnt++;
-            tot += ((e + 1) >> 1) - (s >> 1);
+        for (int o = 0; o < 9; o++) {
+            self = self || ((int)i >= r[o].x && (int)i < r[o].x + r[o].y);   // see k_plan: any run may hold the particle itself
+            if (r[o].y > 0) {
+                const int s = r[o].x, e = r[o].x + r[o].y;
+                srun[cnt * BLOCK + tid] = make_int2(s, e);
+                cnt++;
+                tot += ((e + 1) >> 1) - (s >> 1);
+            }
+        }
+    } else {
+        const int cx = (int)(home & ((1u << g.bx) - 1u)) - 2;
+        const int cz = (int)((home >> g.bx) & ((1u << g.bz) - 1u)) - 2;
+        const int cy = (int)(home >> (g.bx + g.bz)) - 2;
+#pragma unroll 1
+        for (int o = 0; o < (2 * RAD + 1) * (2 * RAD + 1); o++) {
+            const int yy = cy + (o / (2 * RAD + 1) - RAD), zz = cz + (o % (2 * RAD + 1) - RAD);
+            if (yy < 0 || yy >= g.gy || zz < 0 || zz >= g.gz) continue;
+            const int2 r = merge_row<RAD>(cells, yy * g.gxgz + zz * g.gx, cx, g.gx);
+            self = self || ((int)i >= r.x && (int)i < r.x + r.y);
+            if (r.y > 0) {
+                srun[cnt * BLOCK + tid] = make_int2(r.x, r.x + r.y);
+                cnt++;
+                tot += ((r.x + r.y + 1) >> 1) - (r.x >> 1);
+            }
         }
     }
     *self_in = self;

@@ -65,6 +65,14 @@ enum { DN_TOTAL = 0, DN_LOCAL = 1, DN_PREV = 2, DN_STAY = 3, DN_LEAVE = 4 /* lo,
        DN_ARRIVE = 8 /* lo, hi */, DN_GHOST = 10 /* lo, hi */, DN_MOVERS = 12, DN_HOLES = 13, DN_OVERFLOW = 14, DN_STEP = 15,
        DN_HALO_N = 16 /* boundary + ghost totals for the halo kernels: push lo, push hi, pull lo, pull hi */, DN_WORDS = 24 };
 
+// slab ranks: k_predict also decides which particles left the slab (what k_mark_leavers does as a pass of its own)
+struct LeaveArgs {
+    int z_lo, z_hi;
+    bool has_lo, has_hi;
+    u32 *btag, *leave_lo, *leave_hi, *cnt;
+    u32 cap;
+};
+
 struct SortPlan {
     int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
     int passes;      // onesweep passes of up to 9 bits
@@ -177,6 +185,7 @@ int launch_fill_tables(pbf_sim *s);
 int launch_unclear_cells(pbf_sim *s);
 int launch_predict(pbf_sim *s);
 int launch_predict_range(pbf_sim *s, u32 first, NRef count, bool with_hist);
+int launch_predict_slab(pbf_sim *s, NRef n_local, const LeaveArgs &la);   // predict + table reset + leaver lists
 int launch_keys_only(pbf_sim *s, u32 first, u32 count);
 int launch_reorder_cells(pbf_sim *s);
 int launch_highlight(pbf_sim *s);

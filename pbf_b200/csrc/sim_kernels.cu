@@ -48,11 +48,12 @@ __device__ __forceinline__ void unclear_slot(u32 i, const u32 *__restrict__ skey
 // ---- K1 predictpos.glsl:18-38 + cell key + clearhighlight.glsl: one particle per thread, pure streaming --------------
 // UNCLEAR: thread j also resets the table entries of the previous step's sorted slot j (the two jobs share nothing but the
 // launch: the scattered resets hide under the streaming loads).
-template <bool UNCLEAR>
+// SLAB: the thread also files its particle under "left through z-" / "left through z+" (slab.cu, migration).
+template <bool UNCLEAR, bool SLAB>
 __global__ void __launch_bounds__(256)
 k_predict(u32 first, NRef nr, const float4 *__restrict__ pos, const float4 *__restrict__ vel, u32 *__restrict__ hl,
           float4 *__restrict__ pred, u32 *__restrict__ keys, u32 *__restrict__ flags, GridInfo g, SimParams P,
-          NRef nprev, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3) {
+          NRef nprev, const u32 *__restrict__ skey, int2 *__restrict__ cells, int2 *__restrict__ runs3, LeaveArgs la) {
     const u32 n = nref(nr), n_prev = UNCLEAR ? nref(nprev) : 0u, m = n > n_prev ? n : n_prev;
     // one element per thread; the loop only turns when the grid was sized for fewer particles than there are (NRef)
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < ((m + 31u) & ~31u); j += gridDim.x * blockDim.x) {
@@ -77,6 +78,20 @@ k_predict(u32 first, NRef nr, const float4 *__restrict__ pos, const float4 *__re
         // clearhighlight.glsl: flag &= 1 (written back only when it changes anything)
         if (h & ~1u) hl[i] = h & 1u;
         any_hl = (h & 1u) != 0;
+        if (SLAB) {
+            const int cz = (int)fminf(fmaxf(p.z, 0.0f), (float)g.gz_global);     // global cell layer of p*
+            u32 tag = 0;
+            if (la.has_lo && cz < la.z_lo) {
+                const u32 k = atomicAdd(&la.cnt[0], 1u);
+                if (k < la.cap) la.leave_lo[k] = i;
+                tag = 0xffffffffu;
+            } else if (la.has_hi && cz >= la.z_hi) {
+                const u32 k = atomicAdd(&la.cnt[1], 1u);
+                if (k < la.cap) la.leave_hi[k] = i;
+                tag = 0xffffffffu;
+            }
+            la.btag[i] = tag;
+        }
     }
     if (__any_sync(0xffffffffu, any_hl) && (threadIdx.x & 31) == 0) flags[0] = 1u;
     }
@@ -334,8 +349,9 @@ int launch_unclear_cells(pbf_sim *s) {
 
 int launch_predict_range(pbf_sim *s, u32 first, NRef count, bool with_hist) {
     if (count.n == 0) return 0;
-    k_predict<false><<<nblocks(count.n, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
-                                                                   s->grid, sim_params(s), NRef{0u, nullptr}, nullptr, nullptr, nullptr);
+    k_predict<false, false><<<nblocks(count.n, 256), 256, 0, s->stream>>>(first, count, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                                          s->grid, sim_params(s), NRef{0u, nullptr}, nullptr, nullptr, nullptr,
+                                                                          LeaveArgs{});
     // digit histograms of all sort passes: the keys just written are still in L2
     return 1 + (with_hist ? launch_sort_hist(s, s->keys + first, count) : 0);
 }
@@ -343,9 +359,19 @@ int launch_predict_range(pbf_sim *s, u32 first, NRef count, bool with_hist) {
 // whole-handle predict of the single-domain step: also undoes the previous step's cell-table writes (launch_unclear_cells)
 int launch_predict(pbf_sim *s) {
     const u32 np = s->n_prev_sorted, m = s->n > np ? s->n : np;
-    k_predict<true><<<nblocks(m, 256), 256, 0, s->stream>>>(0u, nref_total(s), s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
-                                                            s->grid, sim_params(s), nref_prev(s), s->skey, s->cells, s->runs3);
+    k_predict<true, false><<<nblocks(m, 256), 256, 0, s->stream>>>(0u, nref_total(s), s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                                   s->grid, sim_params(s), nref_prev(s), s->skey, s->cells, s->runs3,
+                                                                   LeaveArgs{});
     return 1 + launch_sort_hist(s, s->keys, nref_total(s));
+}
+
+// slab rank (device-side counts): predict of the local particles + reset of the previous step's table entries + leavers
+int launch_predict_slab(pbf_sim *s, NRef n_local, const LeaveArgs &la) {
+    const u32 m = s->n > n_local.n ? s->n : n_local.n;
+    k_predict<true, true><<<nblocks(m ? m : 1, 256), 256, 0, s->stream>>>(0u, n_local, s->pos, s->vel, s->hl, s->pred, s->keys, s->flags,
+                                                                         s->grid, sim_params(s), NRef{s->n, s->n_prev_dev}, s->skey,
+                                                                         s->cells, s->runs3, la);
+    return 1;
 }
 
 int launch_keys_only(pbf_sim *s, u32 first, u32 count) {

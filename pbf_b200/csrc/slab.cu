@@ -614,6 +614,19 @@ __global__ void k_counts_ghosts(u32 *dn, char *my_area_lo0, char *my_area_hi0, s
     dn[DN_HALO_N + 2] = g_lo; dn[DN_HALO_N + 3] = g_hi;
 }
 
+// After the last position refresh: a ghost's sorted velocity from its owner's final position and the owner's old position
+// (which k_pull_ghosts stored by slot), exactly what update.glsl computes for the particle on its own rank.
+__global__ void __launch_bounds__(256)
+k_ghost_velocity(const u32 *__restrict__ dn, const u32 *__restrict__ ghost_sorted, const float4 *__restrict__ A,
+                 const u32 *__restrict__ perm, const float4 *__restrict__ pos, float4 *__restrict__ svel, float dt) {
+    const u32 ng = dn[DN_GHOST] + dn[DN_GHOST + 1];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < ng; k += gridDim.x * blockDim.x) {
+        const u32 i = ghost_sorted[k];
+        const float4 p = A[i], o = pos[perm[i]];
+        svel[i] = make_float4(__fdiv_rn(__fsub_rn(p.x, o.x), dt), __fdiv_rn(__fsub_rn(p.y, o.y), dt), __fdiv_rn(__fsub_rn(p.z, o.z), dt), 0.0f);
+    }
+}
+
 // last kernel of a step: what the next step's table reset runs over
 __global__ void k_step_end(u32 *dn) {
     if (threadIdx.x == 0) dn[DN_PREV] = dn[DN_TOTAL];
@@ -1037,14 +1050,18 @@ int refresh_bounds(pbf_sim *s) {
                       std::to_string(h[DN_OVERFLOW]) + "; raise the particle / halo capacity");
         return PBF_ERR_CAPACITY;
     }
-    const u32 lag = (u32)(b->step - b->ring_step[best]);
+    // the counters are at most RING steps old; headroom = that many steps of arrivals at twice the last observed rate.  A
+    // bound only changes (and the graph is only captured again) when the need outgrows it or falls well below it.
     const u32 arrive = h[DN_ARRIVE] + h[DN_ARRIVE + 1], ghosts = h[DN_GHOST] + h[DN_GHOST + 1];
-    u32 want_local = round_up(h[DN_LOCAL] + (lag + 2) * 2 * arrive + 4096, 8192);
-    u32 want_total = round_up(want_local + ghosts + ghosts / 4 + 4096, 8192);
+    u32 need_local = h[DN_LOCAL] + (RING + 1) * 2 * arrive + 4096;
+    u32 need_total = need_local + ghosts + ghosts / 4 + 4096;
+    u32 want_local = need_local > b->bound_local || b->bound_local > need_local + need_local / 16 + 32768
+                         ? round_up(need_local + need_local / 64, 8192) : b->bound_local;
+    u32 want_total = need_total > s->n || s->n > need_total + need_total / 16 + 32768 ? round_up(need_total + need_total / 64, 8192) : s->n;
     want_local = min(want_local, s->cap); want_total = min(want_total, s->cap);
     if (starve_bounds()) { want_local = max(512u, h[DN_LOCAL] / 3); want_total = want_local; b->bound_local = want_local; s->n = want_total; }
-    if (want_local > b->bound_local || b->bound_local > want_local + want_local / 32 + 16384) b->bound_local = want_local;
-    if (want_total > s->n || s->n > want_total + want_total / 32 + 16384) s->n = want_total;
+    b->bound_local = want_local;
+    s->n = want_total;
     b->bounds_exact = false;
     b->n_local = h[DN_LOCAL]; b->n_ghost[0] = h[DN_GHOST]; b->n_ghost[1] = h[DN_GHOST + 1];
     b->n_bnd[0] = h[DN_BND]; b->n_bnd[1] = h[DN_BND + 1];
@@ -1094,12 +1111,11 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         cudaMemsetAsync(s->flags, 0, sizeof(u32), s->stream);
         cudaMemsetAsync(b->counters, 0, 16 * sizeof(u32), s->stream);
         k_step_begin<<<1, 32, 0, s->stream>>>(s->dn);
-        s->launches += 1 + launch_unclear_cells(s);
-        s->launches += launch_predict_range(s, 0, nloc, false);
-        k_mark_leavers<<<nb(b->bound_local), 256, 0, s->stream>>>(nloc, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0], b->has[1],
-                                                                  b->btag, b->list[0], b->list[1], b->counters, b->halo_cap);
+        // one pass over the local particles: predict, reset of the previous step's table entries, who leaves
+        const LeaveArgs la = {b->z_lo, b->z_hi, b->has[0], b->has[1], b->btag, b->list[0], b->list[1], b->counters, b->halo_cap};
+        s->launches += 1 + launch_predict_slab(s, nloc, la);
         k_counts_leave<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
-        s->launches += 2;
+        s->launches += 1;
         for (int side = 0; side < 2; side++)
             if (b->has[side]) {
                 k_push_migrants<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[side], s->pos, s->vel, s->pred, b->gid, s->hl,
@@ -1166,13 +1182,30 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
     // ---- solver, update, vorticity ------------------------------------------------------------------------------------------
     const int K = grp[0]->params.num_solver_iterations;
     u32 e = 0;
+    // update.glsl runs in the epilogue of the last delta-p sweep as on a single GPU.  A ghost's own sweep result is
+    // meaningless (half its neighbourhood is missing) and is replaced by its owner's position right after; with vorticity
+    // on, its sorted velocity -- which the neighbours' vorticity sweeps read -- is then derived again from that position.
+    const bool vort = grp[0]->params.vorticity_confinement != 0;
     for (int it = 0; it < K; it++) {
         for (int r = 0; r < ng; r++) grp[r]->launches += launch_lambda(grp[r], nullptr);
         halo_refresh_dev(grp, ng, false, ++e);
-        for (int r = 0; r < ng; r++) grp[r]->launches += launch_delta_p(grp[r], nullptr);
+        const bool last = it == K - 1 && grp[0]->fuse_update;
+        for (int r = 0; r < ng; r++) grp[r]->launches += last ? launch_delta_p_update(grp[r]) : launch_delta_p(grp[r], nullptr);
         halo_refresh_dev(grp, ng, true, ++e);
     }
-    for (int r = 0; r < ng; r++) grp[r]->launches += launch_update(grp[r]);
+    if (K > 0 && grp[0]->fuse_update) {
+        for (int r = 0; r < ng; r++) {
+            pbf_sim *s = grp[r];
+            pbf_slab_state *b = s->slab;
+            if (vort && (b->has[0] || b->has[1])) {
+                k_ghost_velocity<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, b->ghost_sorted, s->bufA, s->perm, s->pos, s->svel,
+                                                                    sim_params(s).timestep);
+                s->launches++;
+            }
+        }
+    } else {
+        for (int r = 0; r < ng; r++) grp[r]->launches += launch_update(grp[r]);
+    }
     if (grp[0]->params.vorticity_confinement) {
         for (int r = 0; r < ng; r++) grp[r]->launches += launch_vorticity_a(grp[r], nullptr);
         halo_refresh_dev(grp, ng, false, ++e);

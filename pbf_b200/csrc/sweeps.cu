@@ -390,14 +390,15 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
 }
 
 // General walk of one particle: its nine merged runs from global memory (aligned pairs, masked edges).
-template <int NSRC, class F>
+template <int NSRC, int RAD, class F>
 __device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, const float4 *__restrict__ src0,
                                              const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                              const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
                                              const GridInfo &g, u32 i, int tid, F body) {
-    int2 *srun = reinterpret_cast<int2 *>(dsm);            // 9 x TL run descriptors
+    int2 *srun = reinterpret_cast<int2 *>(dsm);            // 9 (25 with full support) x TL run descriptors
+    static_assert((size_t)(2 * RAD + 1) * (2 * RAD + 1) * TL * sizeof(int2) <= TL_SMEM1, "run descriptors fit the image area");
     int slots_;
-    load_runs<TL>(home[i], i, g, runs3, cells, srun, tid, &slots_, &c.self_in);
+    load_runs<TL, RAD>(home[i], i, g, runs3, cells, srun, tid, &slots_, &c.self_in);
     for_each_pair<TL>(srun, tid, slots_, [&](int m, bool v0, bool v1) {
         const Pair p = ldg_pair(src0 + 2 * (size_t)m);
         if (NSRC == 2) body(p, ldg_pair(src1 + 2 * (size_t)m), v0, v1);
@@ -406,13 +407,25 @@ __device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, con
 }
 
 // both paths; every thread of the block calls this (the tiled path synchronises the block), `live` = has a particle
-template <int NSRC, class F>
+template <int NSRC, bool FULL, class F>
 __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                      const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                      const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
                                      const int *__restrict__ desc, const GridInfo &g, u32 i, bool live, int tid, F body) {
-    if (c.mode) tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body);
-    else if (live) general_walk<NSRC>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+    if (FULL) {                                            // full-support search: 25 rows of five cells from global memory
+        if (live) general_walk<NSRC, 2>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+    } else if (c.mode) {
+        tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body);
+    } else if (live) {
+        general_walk<NSRC, 1>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+    }
+}
+
+// tile frame of a FULL kernel: no plan, no image
+__device__ __forceinline__ TileCtx tile_none(u32 tile, u32 ntiles_) {
+    TileCtx c;
+    c.tile = tile; c.ntiles = ntiles_; c.mode = 0; c.cut = 0; c.self_in = false; c.img = 0;
+    return c;
 }
 
 // Fused halo push (slab runtime): `wide` sends the 16-byte record, otherwise its .w; every thread of the block calls this
@@ -462,7 +475,7 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
 
 // ---- K8 calclambda.glsl:66-103 ------------------------------------------------------------------------------------
 // out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
-template <bool DIAG>
+template <bool DIAG, bool FULL>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag,
          const HaloPush hp) {
@@ -470,14 +483,14 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
-    walk<1>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 tt = __fmul2_rn(q.t2, q.t2);                         // (h-l)^2
@@ -527,9 +540,11 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
 struct UpdateArgs {
     const u32 *perm;
     float4 *pos, *vel, *svel;
+    const u32 *n_local;      // slab rank: ids at and beyond *n_local are ghosts, whose by-slot position (the owner's OLD
+                             // position) must survive for k_ghost_velocity; null on a single domain
 };
 
-template <int FINAL>
+template <int FINAL, bool FULL>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp,
           const UpdateArgs up) {
@@ -537,7 +552,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -554,7 +569,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     sc4 *= sc4;
     const float nk = -P.tensile_k * sc4;
     const float2 nk2 = make_float2(nk, nk), li2 = make_float2(pi.w, pi.w);
-    walk<1>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         float2 t3 = __fmul2_rn(__fmul2_rn(q.t, q.t), q.t);
         t3 = __fmul2_rn(t3, t3);
@@ -583,9 +598,11 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
             if ((y <= g.wlo[1] && v.y < 0.0f) || (y >= g.whi[1] && v.y > 0.0f)) v.y *= -P.restitution;
             if ((z <= g.wlo[2] && v.z < 0.0f) || (z >= g.whi[2] && v.z > 0.0f)) v.z *= -P.restitution;
         }
-        up.pos[id] = out;
+        if (up.n_local == nullptr || id < *up.n_local) {
+            up.pos[id] = out;
+            if (FINAL == 1) up.vel[id] = v;
+        }
         if (FINAL == 2) up.svel[i] = v;
-        else up.vel[id] = v;
     }
     halo_push(hp, i, live, out, true, tid);
     TILE_LOOP_END(tc)
@@ -593,6 +610,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
 
 // ---- K11 vorticity.glsl:34-60 (first sweep): XSPH + vorticity ------------------------------------------------------------
 // out: vprime = v + c*sum v_ij W, omega = sum v_ij x gradW, B = {p, |omega|}
+template <bool FULL>
 __global__ void __launch_bounds__(TL)
 k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
               float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P, const HaloPush hp) {
@@ -600,14 +618,14 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
     const float2 neg1 = make_float2(-1.0f, -1.0f);
-    walk<2>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
+    walk<2, FULL>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
         const float2 uy = make_float2(u.y.x - vi.y, u.y.y - vi.y);
@@ -636,6 +654,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
 }
 
 // ---- K11 vorticity.glsl:65-85 (second sweep): confinement force, velocity[id] written once -------------------------------
+template <bool FULL>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
               const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P) {
@@ -643,12 +662,12 @@ k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
-    walk<1>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 cc = __fmul2_rn(c.w, __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il));   // |omega_j| * grad factor
         ex = __ffma2_rn(cc, q.dx, ex);
@@ -679,62 +698,76 @@ size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
 size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 
 int sweeps_init(void) {
-    cudaError_t e = cudaFuncSetAttribute(k_lambda<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lambda<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_delta_p<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vorticity_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_vorticity_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM2);
+    cudaError_t e = cudaSuccess;
+    auto opt = [&](const void *f, size_t bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    opt((const void *)k_lambda<false, false>, TL_SMEM1); opt((const void *)k_lambda<true, false>, TL_SMEM1);
+    opt((const void *)k_lambda<false, true>, TL_SMEM1); opt((const void *)k_lambda<true, true>, TL_SMEM1);
+    opt((const void *)k_delta_p<0, false>, TL_SMEM1); opt((const void *)k_delta_p<1, false>, TL_SMEM1); opt((const void *)k_delta_p<2, false>, TL_SMEM1);
+    opt((const void *)k_delta_p<0, true>, TL_SMEM1); opt((const void *)k_delta_p<1, true>, TL_SMEM1); opt((const void *)k_delta_p<2, true>, TL_SMEM1);
+    opt((const void *)k_vorticity_b<false>, TL_SMEM1); opt((const void *)k_vorticity_b<true>, TL_SMEM1);
+    opt((const void *)k_vorticity_a<false>, TL_SMEM2); opt((const void *)k_vorticity_a<true>, TL_SMEM2);
     return e == cudaSuccess ? 0 : -1;
 }
 
+// pbf_options::full_support: the 5 x 5 x 5 search needs no plan (every particle walks its 25 rows from global memory)
+static inline bool full(const pbf_sim *s) { return s->options.full_support != 0; }
+
 int launch_plan(pbf_sim *s) {
+    if (full(s)) return 0;
     k_plan<<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
                                                s->tiled_sweeps ? 1 : 0);
     return 1;
 }
 
 static const HaloPush NO_PUSH = {};
+#define SWEEP_LAUNCH(kern_normal, kern_full, smem, ...)                                                          \
+    do {                                                                                                          \
+        if (full(s)) kern_full<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);                               \
+        else kern_normal<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);                                     \
+    } while (0)
 
 int launch_lambda(pbf_sim *s, const HaloPush *push) {
-    k_lambda<false><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
-                                                              nullptr, push ? *push : NO_PUSH);
+    SWEEP_LAUNCH((k_lambda<false, false>), (k_lambda<false, true>), TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
+                 sim_params(s), nullptr, push ? *push : NO_PUSH);
     return 1;
 }
 
 int launch_delta_p(pbf_sim *s, const HaloPush *push) {
-    k_delta_p<0><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s),
-                                                           push ? *push : NO_PUSH, UpdateArgs{});
+    SWEEP_LAUNCH((k_delta_p<0, false>), (k_delta_p<0, true>), TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
+                 sim_params(s), push ? *push : NO_PUSH, UpdateArgs{});
     return 1;
 }
 
 // the last solver iteration of a step: delta-p with update.glsl in its epilogue (replaces launch_delta_p + launch_update)
 int launch_delta_p_update(pbf_sim *s) {
-    const UpdateArgs up = {s->perm, s->pos, s->vel, s->svel};
+    const UpdateArgs up = {s->perm, s->pos, s->vel, s->svel, s->n_dev ? s->dn + DN_LOCAL : nullptr};
     if (s->params.vorticity_confinement)
-        k_delta_p<2><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
+        SWEEP_LAUNCH((k_delta_p<2, false>), (k_delta_p<2, true>), TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
+                     sim_params(s), NO_PUSH, up);
     else
-        k_delta_p<1><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid, sim_params(s), NO_PUSH, up);
+        SWEEP_LAUNCH((k_delta_p<1, false>), (k_delta_p<1, true>), TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
+                     sim_params(s), NO_PUSH, up);
     return 1;
 }
 
 int launch_vorticity_a(pbf_sim *s, const HaloPush *push) {
-    k_vorticity_a<<<ntiles(s->n), TL, TL_SMEM2, s->stream>>>(nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
-                                                            s->omega, s->grid, sim_params(s), push ? *push : NO_PUSH);
+    SWEEP_LAUNCH((k_vorticity_a<false>), (k_vorticity_a<true>), TL_SMEM2, nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
+                 s->omega, s->grid, sim_params(s), push ? *push : NO_PUSH);
     return 1;
 }
 
 int launch_vorticity_b(pbf_sim *s) {
-    k_vorticity_b<<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
-                                                            s->vel, s->grid, sim_params(s));
+    SWEEP_LAUNCH((k_vorticity_b<false>), (k_vorticity_b<true>), TL_SMEM1, nref_total(s), s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
+                 s->vel, s->grid, sim_params(s));
     return 1;
 }
 
 int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s, nullptr) + launch_vorticity_b(s); }
 
 int launch_density_diag(pbf_sim *s) {
-    k_lambda<true><<<ntiles(s->n), TL, TL_SMEM1, s->stream>>>(nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid, sim_params(s),
-                                                             s->diag, NO_PUSH);
+    SWEEP_LAUNCH((k_lambda<true, false>), (k_lambda<true, true>), TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
+                 sim_params(s), s->diag, NO_PUSH);
     return 1;
 }

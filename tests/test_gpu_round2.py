@@ -370,3 +370,92 @@ def test_slab_capacity_overflow_is_reported(built_lib):
         grp.Run(2)
         grp.gather()
     grp.close()
+
+
+def _brute_force_solver_iteration(rec, grid, P, radius):
+    """NumPy O(n^2): lambda (calclambda.glsl:66-103) and the new positions (updatepos.glsl:43-105, Jacobi) with candidates =
+    particles whose cell differs by at most `radius` in every axis (1 = the reference's 27 cells, 2 = the whole support)."""
+    p = rec[:, :3].astype(np.float32)
+    cell = np.floor(p).astype(np.int64)
+    n = p.shape[0]
+    lam = np.zeros(n, np.float32)
+    h = np.float32(2.0)
+    cand = []
+    for i in range(n):
+        m = np.all(np.abs(cell - cell[i]) <= radius, axis=1)
+        m[i] = False
+        j = np.nonzero(m)[0]
+        cand.append(j)
+        d = (p[i] - p[j]).astype(np.float32)
+        l = np.sqrt((d * d).sum(1, dtype=np.float32))
+        w = np.where(l <= h, np.float32(1.56668147106) * (h * h - l * l) ** 3 / np.float32(512.0), 0).astype(np.float32)
+        rho = w.sum(dtype=np.float32)
+        ok = (l <= h) & (l > 0)
+        g = np.zeros_like(d)
+        g[ok] = ((np.float32(-3 * 4.774648292756860) * (h - l[ok]) ** 2)[:, None] * d[ok] / (l[ok] * np.float32(64.0))[:, None])
+        g *= np.float32(P.one_over_rho_0)
+        s = (g * g).sum(dtype=np.float32) + (g.sum(0, dtype=np.float32) ** 2).sum(dtype=np.float32)
+        lam[i] = -(rho * np.float32(P.one_over_rho_0) - 1) / (s + np.float32(P.epsilon))
+    newp = p.copy()
+    for i in range(n):
+        j = cand[i]
+        d = (p[i] - p[j]).astype(np.float32)
+        l = np.sqrt((d * d).sum(1, dtype=np.float32))
+        w = np.where(l <= h, np.float32(1.56668147106) * (h * h - l * l) ** 3 / np.float32(512.0), 0).astype(np.float32)
+        sc = -np.float32(P.tensile_instability_k) * (np.float32(P.tensile_instability_scale) * w) ** 4
+        ok = (l <= h) & (l > 0)
+        g = np.zeros_like(d)
+        g[ok] = ((np.float32(-3 * 4.774648292756860) * (h - l[ok]) ** 2)[:, None] * d[ok] / (l[ok] * np.float32(64.0))[:, None])
+        dp = ((lam[i] + lam[j] + sc)[:, None] * g).sum(0, dtype=np.float32)
+        newp[i] = p[i] + np.float32(P.one_over_rho_0) * dp
+    lo = np.array([16.0, 0.0, 16.0], np.float32)
+    hi = np.array(grid, np.float32) - lo
+    return lam, np.clip(newp, lo, hi)
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_option_full_support_search(built_lib, full):
+    """pbf_options::full_support (SURVEY.md 8f row 3): candidates from all 5 x 5 x 5 cells the kernel support h = 2 reaches,
+    instead of the reference's 3 x 3 x 3 -- lambda and the position update of one solver iteration against an O(n^2) NumPy
+    evaluation over the same candidate set (radius 1 checks the default path the same way)."""
+    grid = (64, 32, 64)
+    pos, vel = oracle.dam_break(12, 14, 12, origin=(20.5, 0.5, 20.5))          # 2016 -> pad to 2048 with far-away particles
+    extra = np.zeros((2048 - pos.shape[0], 4), np.float32)
+    extra[:, :3] = np.random.default_rng(2).uniform([40, 5, 40], [46, 20, 46], (extra.shape[0], 3))
+    pos = np.concatenate([pos, extra]); vel = np.zeros_like(pos)
+    sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+    sph.set_options(full_support=full)
+    assert bool(sph.get_options().full_support) == full
+    sph.upload(pos, vel)
+    sph.predict(); sph.sort(); sph.build_cells()
+    _, perm, rec = sph.get_sorted()
+    P = oracle_params_of(sph)
+    lam_want, pos_want = _brute_force_solver_iteration(rec, grid, P, 2 if full else 1)
+    sph.calc_lambda()
+    lam = sph.get_lambda()
+    assert np.max(np.abs(lam - lam_want)) < 2e-5 * max(1.0, float(np.max(np.abs(lam_want))))
+    sph.update_positions()
+    _, _, rec2 = sph.get_sorted()
+    assert np.max(np.abs(rec2[:, :3] - pos_want)) < 2e-5
+    if full:                                     # and the wider search really sees more neighbours: lambda differs from the default
+        other = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+        other.upload(pos, vel)
+        other.predict(); other.sort(); other.build_cells(); other.calc_lambda()
+        assert np.max(np.abs(other.get_lambda() - lam)) > 1e-3
+    # whole steps run (graph, fused update, vorticity) and stay finite and inside the walls
+    sph.SetNumSolverIterations(3)
+    sph.SetVorticityConfinementEnabled(True)
+    sph.upload(pos, vel)
+    sph.Run(5)
+    p, v = sph.download()
+    assert np.isfinite(p).all() and np.isfinite(v).all()
+    assert p[:, 0].min() >= 16.0 and p[:, 0].max() <= grid[0] - 16.0 and p[:, 1].min() >= 0.0
+
+
+def oracle_params_of(sph):
+    P = oracle.default_params()
+    p = sph._get()
+    for k in ("one_over_rho_0", "epsilon", "gravity", "timestep", "tensile_instability_k",
+              "tensile_instability_scale", "xsph_viscosity_c", "vorticity_epsilon"):
+        setattr(P, k, getattr(p, k))
+    return P
