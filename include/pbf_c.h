@@ -280,6 +280,9 @@ int pbf_slab_step(pbf_handle h, int nsteps);
  * owns afterwards back out into the same arrays (*n_out of them; the arrays hold `capacity`) */
 int pbf_slab_step_host(pbf_handle h, float *pos4, float *vel4, uint32_t *gid, uint32_t n_in, uint32_t capacity,
                        uint32_t *n_out, int nsteps);
+/* with PBF_SLAB_PHASES=1 in the environment (direct launches): device ms of the last step's five phases on this rank:
+ * predict + migration out, arrivals + boundary + ghosts out, ghosts in + sort + cells, solver incl. halos, vorticity */
+int pbf_slab_phase_times(pbf_handle h, float ms[5]);
 /* out: local particles, ghosts from z-, ghosts from z+, boundary sent to z-, to z+, migrated away (total),
  * exchanges (total), bytes sent (total) */
 int pbf_slab_stats(pbf_handle h, uint64_t out[8]);

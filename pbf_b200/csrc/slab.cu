@@ -94,6 +94,9 @@ struct pbf_slab_state {
     uint64_t graph_key;
     u32 graph_kernels;
     bool use_graph;
+    bool phases;                        // PBF_SLAB_PHASES=1: direct launches with an event at every phase boundary
+    cudaEvent_t ph_ev[8];
+    bool ph_valid;
 };
 
 constexpr int MB_SLOTS = 4;   // 2 would do: a rank pushes refresh e+2 only after it received e+1, which its neighbour
@@ -1103,6 +1106,11 @@ int halo_refresh_dev(pbf_sim **grp, int ng, bool wide, u32 e) {
 
 // One step of every rank of `grp`, enqueued without touching the host-side state the device decides (capturable).
 int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
+    auto mark = [&](int k) {          // phase boundaries of rank 0 (pbf_slab_phase_times)
+        pbf_slab_state *b = grp[0]->slab;
+        if (b->phases) { cudaEventRecord(b->ph_ev[k], grp[0]->stream); b->ph_valid = true; }
+    };
+    mark(0);
     // ---- predict, who leaves, leavers into the neighbours' inboxes, compaction ------------------------------------------
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -1131,6 +1139,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
             s->launches += 2;
         }
     }
+    mark(1);
     // ---- arrivals, boundary layers, ghosts into the neighbours' inboxes --------------------------------------------------
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -1154,6 +1163,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
                 s->launches++;
             }
     }
+    mark(2);
     // ---- ghosts in, sort + cells over local + ghost particles --------------------------------------------------------------
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -1179,6 +1189,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         }
         s->launches += launch_highlight(s);
     }
+    mark(3);
     // ---- solver, update, vorticity ------------------------------------------------------------------------------------------
     const int K = grp[0]->params.num_solver_iterations;
     u32 e = 0;
@@ -1193,6 +1204,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         for (int r = 0; r < ng; r++) grp[r]->launches += last ? launch_delta_p_update(grp[r]) : launch_delta_p(grp[r], nullptr);
         halo_refresh_dev(grp, ng, true, ++e);
     }
+    mark(4);
     if (K > 0 && grp[0]->fuse_update) {
         for (int r = 0; r < ng; r++) {
             pbf_sim *s = grp[r];
@@ -1215,6 +1227,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         k_step_end<<<1, 32, 0, grp[r]->stream>>>(grp[r]->dn);
         grp[r]->launches++;
     }
+    mark(5);
     return PBF_OK;
 }
 
@@ -1235,7 +1248,7 @@ int slab_step_dev(pbf_sim **grp, int ng) {
         key = fnv(key, &grp[r]->params, sizeof(pbf_params)); key = fnv(key, &grp[r]->options, sizeof(pbf_options));
     }
     cudaStream_t st = grp[0]->stream;
-    const bool graph = b0->use_graph && !grp[0]->timing;
+    const bool graph = b0->use_graph && !grp[0]->timing && !b0->phases;
     if (graph) {
         if (!b0->graph_exec || b0->graph_key != key) {
             if (b0->graph_exec) { cudaGraphExecDestroy(b0->graph_exec); cudaGraphDestroy(b0->graph); b0->graph_exec = nullptr; b0->graph = nullptr; }
@@ -1328,6 +1341,10 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     {
         const char *g = getenv("PBF_SLAB_GRAPH");
         b->use_graph = !(g && g[0] == '0');
+        const char *ph = getenv("PBF_SLAB_PHASES");
+        b->phases = ph && ph[0] == '1';
+        if (b->phases)
+            for (int k = 0; k < 8; k++) cudaEventCreate(&b->ph_ev[k]);
     }
     cudaStreamSynchronize(s->stream);      // the mailbox flags are zero before any neighbour can see them
     s->slab = b;
@@ -1590,6 +1607,19 @@ int pbf_slab_step_host(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, ui
     PBF_CUDA(cudaMemcpyAsync(gid, s->slab->gid, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
     PBF_CUDA(cudaStreamSynchronize(s->stream));
     *n_out = m;
+    return PBF_OK;
+}
+
+// PBF_SLAB_PHASES=1: device time of the last step's phases on this rank -- [0] predict + migration out + compaction,
+// [1] arrivals + boundary + ghosts out, [2] ghosts in + sort + cells + halo index, [3] solver with its halo refreshes,
+// [4] ghost velocities + vorticity with its halo refresh
+int pbf_slab_phase_times(pbf_handle s, float ms[5]) {
+    if (!s || !s->slab || !ms) { pbf_set_error("pbf_slab_phase_times: slab not initialised"); return PBF_ERR_STATE; }
+    pbf_slab_state *b = s->slab->group ? s->slab->group[0]->slab : s->slab;
+    if (!b->phases || !b->ph_valid) { pbf_set_error("pbf_slab_phase_times: set PBF_SLAB_PHASES=1 before pbf_slab_init and step once"); return PBF_ERR_STATE; }
+    DeviceGuard guard(s->device);
+    PBF_CUDA(cudaEventSynchronize(b->ph_ev[5]));
+    for (int k = 0; k < 5; k++) PBF_CUDA(cudaEventElapsedTime(&ms[k], b->ph_ev[k], b->ph_ev[k + 1]));
     return PBF_OK;
 }
 

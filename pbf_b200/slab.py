@@ -118,6 +118,11 @@ class SlabSPH(SPH):
         _check(lib().pbf_slab_step_host(self._h, _ptr(pos), _ptr(vel), _ptr(gid), n, capacity, C.byref(m), nsteps))
         return m.value
 
+    def phase_times(self):
+        ms = (C.c_float * 5)()
+        _check(lib().pbf_slab_phase_times(self._h, ms))
+        return dict(zip(("predict_migrate", "arrivals_ghosts_out", "ghosts_in_sort_cells", "solver", "vorticity"), [float(x) for x in ms]))
+
     def stats(self):
         out = (C.c_uint64 * 8)()
         _check(lib().pbf_slab_stats(self._h, out))
@@ -251,6 +256,7 @@ def bench(args, name, cfg, scene, rank, world, local, B):
         ms = e0.elapsed_time(e1) / args.steps
     launches = s.kernel_launches - l0
     st = s.stats()
+    phases = s.phase_times() if os.environ.get("PBF_SLAB_PHASES") == "1" else None
     t = torch.tensor([ms, float(st["n_local"]), float(st["migrated"] - m0), float(st["ghosts_lo"] + st["ghosts_hi"])],
                      dtype=torch.float64, device=dev)
     tmax = t.clone()
@@ -305,7 +311,7 @@ def bench(args, name, cfg, scene, rank, world, local, B):
                        "ms_per_step_min_over_ranks": tmin[0].item(),
                        "exchanges_per_step": st["exchanges"] // max(1, args.steps + args.warmup),
                        "step_algorithmic_bytes_per_particle": step_bytes,
-                       "step_hbm_frac_of_peak": per_gpu_gbs / peak},
+                       "step_hbm_frac_of_peak": per_gpu_gbs / peak, "rank0_phase_ms_last_step": phases},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "e2e": {"value": n_total / (e2e_max[0].item() * 1e-3), "unit": B.UNIT, "h2d_bytes_per_step": int(e2e[1].item()),
                     "d2h_bytes_per_step": int(e2e[1].item()), "ms_per_step": e2e_max[0].item(),

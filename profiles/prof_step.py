@@ -14,7 +14,7 @@ import pbf_b200
 small = "--small" in sys.argv
 n3, grid = ((128, 64, 128), (256, 128, 256)) if small else ((256, 128, 256), (512, 256, 512))
 pos, vel = pbf_b200.dam_break(*n3)
-sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False, use_graph=False)      # direct launches: ncu -k sees plain kernels
 sph.SetNumSolverIterations(4)
 sph.SetVorticityConfinementEnabled(True)
 sph.upload(pos, vel)
@@ -25,5 +25,7 @@ print("tiles, tiled:", sph.tile_stats(), sph.tile_fallback_reasons)
 for _ in range(2):
     sph.calc_lambda(); sph.update_positions()
 sph.finalize(); sph.vorticity()
+sph.sync()
+sph.Run(1)                       # one whole step: the fused kernels (predict + table reset, last delta-p + update)
 sph.sync()
 print("ok")
