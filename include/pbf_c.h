@@ -280,6 +280,12 @@ int pbf_slab_step(pbf_handle h, int nsteps);
  * owns afterwards back out into the same arrays (*n_out of them; the arrays hold `capacity`) */
 int pbf_slab_step_host(pbf_handle h, float *pos4, float *vel4, uint32_t *gid, uint32_t n_in, uint32_t capacity,
                        uint32_t *n_out, int nsteps);
+/* Load balancing: this rank's particle count per GLOBAL cell layer (gz_global counters, HOST array), and new planes for
+ * this rank from the next step on.  Every rank must be given consistent planes before any of them steps; the particles that
+ * fall outside travel through the next step's migration, so move a plane by a layer or two at a time.  The handle's grid
+ * depth (pbf_config.grid[2]) bounds the window: create slab handles a few layers deeper than (z_hi - z_lo) + 2. */
+int pbf_slab_layer_counts(pbf_handle h, uint32_t *counts);
+int pbf_slab_set_planes(pbf_handle h, int z_lo, int z_hi);
 /* with PBF_SLAB_PHASES=1 in the environment (direct launches): device ms of the last step's five phases on this rank:
  * predict + migration out, arrivals + boundary + ghosts out, ghosts in + sort + cells, solver incl. halos, vorticity */
 int pbf_slab_phase_times(pbf_handle h, float ms[5]);

@@ -116,6 +116,8 @@ def lib():
         L.pbf_slab_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.pbf_slab_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.pbf_slab_download_highlight.argtypes = [C.c_void_p, C.c_void_p]
+        L.pbf_slab_layer_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.pbf_slab_set_planes.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.pbf_slab_phase_times.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.pbf_slab_step.argtypes = [C.c_void_p, C.c_int]
         L.pbf_slab_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,

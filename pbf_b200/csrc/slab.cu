@@ -630,6 +630,14 @@ k_ghost_velocity(const u32 *__restrict__ dn, const u32 *__restrict__ ghost_sorte
     }
 }
 
+// particles per global cell layer (by the positions the next predict starts from): what the host runtime balances on
+__global__ void __launch_bounds__(256)
+k_layer_counts(NRef nr, const float4 *__restrict__ pos, GridInfo g, u32 *__restrict__ counts) {
+    const u32 n = nref(nr);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&counts[min(global_layer(pos[i].z, g), g.gz_global - 1)], 1u);
+}
+
 // last kernel of a step: what the next step's table reset runs over
 __global__ void k_step_end(u32 *dn) {
     if (threadIdx.x == 0) dn[DN_PREV] = dn[DN_TOTAL];
@@ -1245,6 +1253,7 @@ int slab_step_dev(pbf_sim **grp, int ng) {
         int rc = refresh_bounds(grp[r]);
         if (rc) return rc;
         key = fnv(key, &grp[r]->n, 4); key = fnv(key, &grp[r]->slab->bound_local, 4);
+        key = fnv(key, &grp[r]->slab->z_lo, 4); key = fnv(key, &grp[r]->slab->z_hi, 4);
         key = fnv(key, &grp[r]->params, sizeof(pbf_params)); key = fnv(key, &grp[r]->options, sizeof(pbf_options));
     }
     cudaStream_t st = grp[0]->stream;
@@ -1298,8 +1307,8 @@ int sync_counts(pbf_sim *s) {
 int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_global, u32 halo_cap) {
     if (s->slab) { pbf_set_error("slab: already initialised"); return PBF_ERR_STATE; }
     if (z_hi - z_lo < 2) { pbf_set_error("slab: a slab must own at least 2 cell layers"); return PBF_ERR_INVALID; }
-    if (z_hi - z_lo + 2 != s->grid.gz) {
-        pbf_set_error("slab: the handle's grid z extent must be (z_hi - z_lo) + 2 ghost layers");
+    if (z_hi - z_lo + 2 > s->cfg.grid[2]) {
+        pbf_set_error("slab: the handle's grid z extent must be at least (z_hi - z_lo) + 2 ghost layers (more leaves room for pbf_slab_set_planes)");
         return PBF_ERR_INVALID;
     }
     if (rank < 0 || rank >= nranks || halo_cap == 0) { pbf_set_error("slab: bad rank or halo capacity"); return PBF_ERR_INVALID; }
@@ -1310,6 +1319,7 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     b->halo_cap = halo_cap;
     b->n_local = s->n;
     s->grid.zoff = z_lo - 1;
+    s->grid.gz = z_hi - z_lo + 2;           // the window in use; the tables (and the key stride gx * gz) keep the allocated depth
     s->grid.gz_global = gz_global;
     s->grid.ref_quirks = 0;     // the lowest-key-cell quirk is a single-domain artefact (findcells.glsl:39-43)
     s->grid.whi[2] = (float)gz_global - s->cfg.wall[2];
@@ -1607,6 +1617,54 @@ int pbf_slab_step_host(pbf_handle s, float *pos4, float *vel4, uint32_t *gid, ui
     PBF_CUDA(cudaMemcpyAsync(gid, s->slab->gid, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
     PBF_CUDA(cudaStreamSynchronize(s->stream));
     *n_out = m;
+    return PBF_OK;
+}
+
+// Load balancing.  pbf_slab_layer_counts: this rank's particles per global cell layer (gz_global counters, HOST array); the
+// host runtime sums them over the ranks and picks new planes.  pbf_slab_set_planes: this rank owns [z_lo, z_hi) from the
+// next step on -- every rank must be given consistent planes before any of them steps; the particles that now lie outside
+// move to the neighbours through the next step's ordinary migration, so a plane may only move by what one step's record
+// capacity can carry (a layer or two).  The window (z_hi - z_lo + 2 layers) must fit the grid depth the handle was created
+// with.
+int pbf_slab_layer_counts(pbf_handle s, uint32_t *counts) {
+    if (!s || !s->slab || !counts) { pbf_set_error("pbf_slab_layer_counts: slab not initialised or null buffer"); return PBF_ERR_STATE; }
+    DeviceGuard guard(s->device);
+    pbf_slab_state *b = s->slab;
+    const size_t bytes = (size_t)s->grid.gz_global * 4;
+    u32 *d = nullptr;
+    PBF_CUDA(cudaMalloc(&d, bytes));
+    cudaMemsetAsync(d, 0, bytes, s->stream);
+    const NRef nloc = b->devcount ? NRef{b->bound_local, s->dn + DN_LOCAL} : NRef{b->n_local, nullptr};
+    k_layer_counts<<<nb(nloc.n ? nloc.n : 1), 256, 0, s->stream>>>(nloc, s->pos, s->grid, d);
+    s->launches++;
+    cudaMemcpyAsync(counts, d, bytes, cudaMemcpyDeviceToHost, s->stream);
+    const cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { pbf_set_error(cudaGetErrorString(e)); return PBF_ERR_CUDA; }
+    return PBF_OK;
+}
+
+int pbf_slab_set_planes(pbf_handle s, int z_lo, int z_hi) {
+    if (!s || !s->slab) { pbf_set_error("pbf_slab_set_planes: slab not initialised"); return PBF_ERR_STATE; }
+    pbf_slab_state *b = s->slab;
+    if (z_hi - z_lo < 2 || z_lo < 0 || z_hi > s->grid.gz_global || z_hi - z_lo + 2 > s->cfg.grid[2]) {
+        pbf_set_error("pbf_slab_set_planes: a slab owns at least 2 layers and its window must fit the handle's grid depth");
+        return PBF_ERR_INVALID;
+    }
+    if ((!b->has[0] && z_lo != b->z_lo) || (!b->has[1] && z_hi != b->z_hi)) {
+        pbf_set_error("pbf_slab_set_planes: the outer planes of the domain cannot move");
+        return PBF_ERR_INVALID;
+    }
+    if (z_lo == b->z_lo && z_hi == b->z_hi) return PBF_OK;
+    DeviceGuard guard(s->device);
+    // the cell tables are addressed relative to the window: undo the last step's entries under the OLD window first
+    s->launches += launch_unclear_cells(s);
+    s->n_prev_sorted = 0;
+    if (b->devcount) PBF_CUDA(cudaMemsetAsync(s->dn + DN_PREV, 0, 4, s->stream));
+    b->z_lo = z_lo; b->z_hi = z_hi;
+    s->grid.zoff = z_lo - 1;
+    s->grid.gz = z_hi - z_lo + 2;
+    PBF_CUDA(cudaGetLastError());
     return PBF_OK;
 }
 

@@ -35,6 +35,28 @@ def plan_slabs(cell_z, gz_global, nranks):
     return planes
 
 
+def rebalance_planes(layer_counts, old_planes, max_shift=1, max_thickness=None):
+    """New slab planes from the particle count per global cell layer: the equal-share planes of plan_slabs, but every inner
+    plane moves at most `max_shift` layers per call (the particles that change owner travel through ONE step's migration),
+    slabs keep at least 2 layers and at most `max_thickness` (what the handles' grids were allocated for)."""
+    counts = np.asarray(layer_counts, dtype=np.int64)
+    n = len(old_planes) - 1
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    new = [int(old_planes[0])]
+    for r in range(1, n):
+        want = int(np.searchsorted(cum, cum[-1] * r / n, side="left"))
+        z = int(np.clip(want, old_planes[r] - max_shift, old_planes[r] + max_shift))
+        z = max(z, new[-1] + 2)
+        z = min(z, int(old_planes[-1]) - 2 * (n - r))
+        if max_thickness is not None:
+            z = min(z, new[-1] + max_thickness)
+        new.append(z)
+    new.append(int(old_planes[-1]))
+    if max_thickness is not None and any(b - a > max_thickness for a, b in zip(new[:-1], new[1:])):
+        return [int(z) for z in old_planes]            # cannot be satisfied with the allocated windows: keep the planes
+    return new
+
+
 def cell_layer(pos, gz_global):
     return np.clip(pos[:, 2], 0.0, float(gz_global)).astype(np.int32)
 
@@ -53,13 +75,15 @@ class SlabSPH(SPH):
     """One rank's slab: an SPH handle whose cell tables cover layers [z_lo-1, z_hi+1) of the global domain."""
 
     def __init__(self, rank, nranks, z_planes, grid_xy, gz_global, capacity, halo_capacity, wall=(16.0, 0.0, 16.0),
-                 device=-1):
+                 device=-1, extra_layers=0):
+        """extra_layers: how many layers the window may grow beyond its initial thickness (set_planes / rebalancing)."""
         self.rank, self.nranks = rank, nranks
         self.z_lo, self.z_hi = int(z_planes[rank]), int(z_planes[rank + 1])
         self.gz_global = gz_global
         self.halo_capacity = halo_capacity
+        self.max_thickness = self.z_hi - self.z_lo + int(extra_layers)
         capacity = (capacity + 511) // 512 * 512
-        super().__init__(capacity, (grid_xy[0], grid_xy[1], self.z_hi - self.z_lo + 2), wall=wall, ref_quirks=False,
+        super().__init__(capacity, (grid_xy[0], grid_xy[1], self.max_thickness + 2), wall=wall, ref_quirks=False,
                          device=device, use_graph=False, capacity=capacity)
         self.capacity = capacity
 
@@ -118,6 +142,31 @@ class SlabSPH(SPH):
         _check(lib().pbf_slab_step_host(self._h, _ptr(pos), _ptr(vel), _ptr(gid), n, capacity, C.byref(m), nsteps))
         return m.value
 
+    def layer_counts(self):
+        """This rank's particles per GLOBAL cell layer (what rebalancing sums over the ranks)."""
+        out = np.zeros(self.gz_global, np.uint32)
+        _check(lib().pbf_slab_layer_counts(self._h, _ptr(out)))
+        return out
+
+    def set_planes(self, z_lo, z_hi):
+        _check(lib().pbf_slab_set_planes(self._h, int(z_lo), int(z_hi)))
+        self.z_lo, self.z_hi = int(z_lo), int(z_hi)
+
+    def rebalance(self, dist, z_planes, max_shift=1):
+        """Real ranks: sum the layer histograms over torch.distributed, move every inner plane by at most max_shift layers
+        towards equal particle counts, adopt this rank's new planes.  Collective: every rank calls it between steps.
+        Returns the new planes (the same list on every rank)."""
+        import torch
+        t = torch.from_numpy(self.layer_counts().astype(np.int64))
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t)
+        thick = torch.tensor([self.max_thickness], dtype=torch.int64, device=t.device)
+        dist.all_reduce(thick, op=dist.ReduceOp.MIN)
+        new = rebalance_planes(t.cpu().numpy(), z_planes, max_shift, int(thick.item()))
+        self.set_planes(new[self.rank], new[self.rank + 1])
+        return new
+
     def phase_times(self):
         ms = (C.c_float * 5)()
         _check(lib().pbf_slab_phase_times(self._h, ms))
@@ -151,14 +200,16 @@ def broadcast_unique_id(dist, rank, device=None):
 class VirtualGroup:
     """nranks slabs inside ONE process on one GPU, exchanged with device copies (tests of the slab logic)."""
 
-    def __init__(self, pos, vel, nranks, grid, wall=(16.0, 0.0, 16.0), halo_capacity=1 << 16, slack=1.5, device=-1):
+    def __init__(self, pos, vel, nranks, grid, wall=(16.0, 0.0, 16.0), halo_capacity=1 << 16, slack=1.5, device=-1,
+                 extra_layers=0, z_planes=None):
         gz_global = grid[2]
-        self.z_planes = plan_slabs(cell_layer(pos, gz_global), gz_global, nranks)
+        self.z_planes = list(z_planes) if z_planes is not None else plan_slabs(cell_layer(pos, gz_global), gz_global, nranks)
         parts = split_scene(pos, vel, self.z_planes, gz_global)
         self.ranks = []
         for r, (p, v, g) in enumerate(parts):
             cap = int(max(p.shape[0], 512) * slack) + 2 * halo_capacity
-            self.ranks.append(SlabSPH(r, nranks, self.z_planes, grid[:2], gz_global, cap, halo_capacity, wall, device))
+            self.ranks.append(SlabSPH(r, nranks, self.z_planes, grid[:2], gz_global, cap, halo_capacity, wall, device,
+                                      extra_layers=extra_layers))
         hs = (C.c_void_p * nranks)(*[s._h for s in self.ranks])
         _check(lib().pbf_slab_init_group(hs, nranks, (C.c_int32 * (nranks + 1))(*self.z_planes), gz_global, halo_capacity))
         for s, (p, v, g) in zip(self.ranks, parts):
@@ -182,6 +233,15 @@ class VirtualGroup:
             seen[g] += 1
         assert np.all(seen == 1), "every particle must be owned by exactly one rank"
         return pos, vel
+
+    def rebalance(self, max_shift=1):
+        """Move the inner planes by at most max_shift layers towards equal particle counts (between steps)."""
+        counts = sum(s.layer_counts().astype(np.int64) for s in self.ranks)
+        new = rebalance_planes(counts, self.z_planes, max_shift, min(s.max_thickness for s in self.ranks))
+        for r, s in enumerate(self.ranks):
+            s.set_planes(new[r], new[r + 1])
+        self.z_planes = new
+        return new
 
     def toggle_highlight(self, gids):
         """Simulation::OnMouseDown's highlight toggle for particles given by GLOBAL id (the owner's slot is looked up)."""

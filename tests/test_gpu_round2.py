@@ -459,3 +459,33 @@ def oracle_params_of(sph):
               "tensile_instability_scale", "xsph_viscosity_c", "vorticity_epsilon"):
         setattr(P, k, getattr(p, k))
     return P
+
+
+def test_virtual_slabs_rebalancing(built_lib):
+    """slab planes follow the particles.  A block that starts inside ONE of two slabs: the inner plane moves
+    a layer per step until the shares are equal, whole layers of particles change owner through the ordinary migration, and
+    the result still matches the single-domain run."""
+    from pbf_b200 import slab
+    grid = (64, 32, 96)
+    pos, vel = oracle.dam_break(16, 16, 40, origin=(18.5, 0.5, 30.5))          # z in [30.5, 67.2]
+    single = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+    single.SetNumSolverIterations(3)
+    single.SetVorticityConfinementEnabled(True)
+    single.upload(pos, vel)
+    grp = slab.VirtualGroup(pos, vel, 2, grid, halo_capacity=8192, slack=3.0, extra_layers=16, z_planes=[0, 36, 96])
+    grp.set_params(num_solver_iterations=3, vorticity_confinement=1)
+    before = [s.stats()["n_local"] for s in grp.ranks]
+    assert before[0] < 0.25 * pos.shape[0]                                      # badly balanced to begin with
+    planes = [list(grp.z_planes)]
+    for step in range(12):
+        single.Run()
+        grp.Run()
+        planes.append(grp.rebalance(max_shift=1))
+    spos, svel = single.download()
+    gpos, gvel = grp.gather()
+    assert np.max(np.abs(spos - gpos)) < 2e-4
+    assert np.max(np.abs(svel - gvel)) < 2e-4 / 0.016
+    assert planes[-1][1] > planes[0][1] + 8                                      # the plane walked into the block
+    after = [s.stats()["n_local"] for s in grp.ranks]
+    assert sum(after) == pos.shape[0] and after[0] > 2 * before[0]
+    grp.close()

@@ -50,3 +50,20 @@ def test_slab_model_world2_gloo(built_lib):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SLAB_MODEL ok=True" in r.stdout
+
+
+def test_rebalance_planes_moves_towards_equal_shares():
+    from pbf_b200.slab import rebalance_planes
+    counts = np.zeros(64, np.int64)
+    counts[10:40] = 100                        # all the fluid in layers 10..39
+    planes = [0, 32, 64]                       # rank 0 holds 2200, rank 1 holds 800
+    for _ in range(10):
+        new = rebalance_planes(counts, planes, max_shift=1)
+        assert abs(new[1] - planes[1]) <= 1 and new[0] == 0 and new[2] == 64
+        planes = new
+    assert planes[1] == 25                     # equal shares: 1500 particles either side
+    # thickness limit: the lower slab may not grow past what its window was allocated for
+    assert rebalance_planes(counts, [0, 32, 64], max_shift=8, max_thickness=33)[1] >= 31
+    # three ranks, minimum two layers each
+    p3 = rebalance_planes(counts, [0, 2, 4, 64], max_shift=50)
+    assert all(b - a >= 2 for a, b in zip(p3[:-1], p3[1:])) and p3[0] == 0 and p3[-1] == 64
