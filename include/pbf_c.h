@@ -194,7 +194,8 @@ int pbf_get_vorticity(pbf_handle h, float *vorticity);
 int pbf_enable_timing(pbf_handle h, int on);
 int pbf_get_timings(pbf_handle h, float ms[5]);
 /* finer than the reference's queries: mean duration of one calclambda and one updatepos launch (src/SPH.cpp:304-310)
- * over the solver iterations of the last timed step -- what bench.py's roofline is computed from */
+ * over the solver iterations of the last timed step -- what bench.py's roofline is computed from (the last iteration's
+ * updatepos launch, which also carries update.glsl, is left out of its mean) */
 int pbf_get_solver_kernel_timings(pbf_handle h, float *lambda_ms, float *delta_p_ms);
 
 /* Selection.  pbf_pick_particle replaces Selection::GetParticle (src/Selection.cpp:55-85), which

@@ -89,7 +89,10 @@ def traffic(path, particles):
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     acc = collections.OrderedDict()
     for r in rows[2:]:
-        name = re.sub(r'<.*', '', short(r[idx['Kernel Name']]))
+        full_name = short(r[idx['Kernel Name']])
+        name = re.sub(r'<.*', '', full_name)
+        if name == 'k_delta_p' and not full_name.startswith('k_delta_p<0'):
+            name = 'k_delta_p_update'          # the last iteration's launch also does update.glsl: kept apart
         b = sum(float(r[idx[k]].replace(',', '')) * scale[units[idx[k]]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
         t = float(r[idx['gpu__time_duration.sum']].replace(',', ''))
         acc.setdefault(name, []).append((b, t, units[idx['gpu__time_duration.sum']]))
