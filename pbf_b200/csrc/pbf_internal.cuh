@@ -73,6 +73,16 @@ struct LeaveArgs {
     u32 cap;
 };
 
+// Which tiles one launch of a sweep kernel covers.  Slab ranks run every sweep that feeds a halo refresh in two launches:
+// first the few tiles that hold boundary particles (part 1: the list k_halo_index built), then -- while a second stream
+// already pushes those particles' values into the neighbour's mailbox -- all the others (part 2: every tile whose flag is
+// clear).  part 0: all tiles, one launch.
+struct TileSel {
+    const u32 *blist;      // tiles that hold boundary particles, in no particular order
+    const u32 *flags;      // [0] = how many, [1 + tile] = tile is in blist
+    int part;
+};
+
 struct SortPlan {
     int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
     int passes;      // onesweep passes of up to 9 bits
@@ -114,6 +124,8 @@ struct pbf_sim {
     // plan of the tiled sweeps (sweeps.cu): per 256-particle tile the nine sorted-index ranges that hold all its
     // candidates, per particle its nine neighbour runs relative to the tile's shared-memory image
     int *tile_desc; u32 *tile_runs;
+    TileSel tile_sel;                     // applies to the sweep launches that follow (slab.cu sets and clears it)
+    u32 tile_grid;                        // blocks of those launches (0: one per tile)
     bool fuse_update;                     // update.glsl in the epilogue of the last delta-p sweep (env PBF_SEPARATE_UPDATE=1: own kernel)
     bool tiled_sweeps;                    // false (env PBF_GENERAL_SWEEPS=1, debugging): every tile takes the general path
     // solver state in sorted order

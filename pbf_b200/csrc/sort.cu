@@ -183,6 +183,7 @@ k_onesweep(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32
                 __syncwarp();
                 cd = d;
                 cc = wh[d];
+                __syncwarp();          // every lane has read the count before lane 0 may overwrite it at the next digit change
             }
             rk = cc + (u32)lane;
             cc += 32u;

@@ -240,7 +240,7 @@ __device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, cons
 template <int NSRC>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
-                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_) {
+                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, u32 tile_ahead) {
     const int *dg = desc + (size_t)tile * TL_DESC;
     TileCtx c;
     c.tile = tile;
@@ -262,7 +262,7 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     // two DRAM round trips.  Warp 2 does this while the block waits for its own image anyway.
     constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the ten prefetching threads
     if (tid >= PF0 && tid < PF0 + 10) {
-        const u32 ft = tile + (u32)PBF_PREFETCH_DIST;
+        const u32 ft = tile_ahead;                    // the tile the block one wave later will work on
         if (ft < ntiles_) {
             const int *fd = desc + (size_t)ft * TL_DESC;
             const int o = tid - PF0;
@@ -458,11 +458,17 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
 // Every sweep kernel: one tile per block; the loop only turns when the grid was sized for fewer particles than there are
 // (NRef: a slab rank's count lives on the device).  Before a block reuses its image and its mbarrier for another tile
 // everybody must be done with them and the barrier object must be invalidated.
+// sel (TileSel): part 1 walks the list of boundary tiles, part 2 all tiles but those (slab ranks, see pbf_internal.cuh).
 #define TILE_LOOP_BEGIN                                                                  \
     const u32 n = nref(nr), ntl = (n + (u32)TL - 1u) / (u32)TL;                          \
-    for (u32 tile = blockIdx.x; tile < ntl; tile += gridDim.x) {
+    const u32 tcount = sel.part == 1 ? min(sel.flags[0], ntl) : ntl;                     \
+    for (u32 t_ = blockIdx.x; t_ < tcount; t_ += gridDim.x) {                            \
+        const u32 tile = sel.part == 1 ? sel.blist[t_] : t_;                             \
+        if (sel.part == 2 && sel.flags[1 + tile]) continue;                              \
+        const u32 tile_ahead = sel.part == 1 ? (t_ + (u32)PBF_PREFETCH_DIST < tcount ? sel.blist[t_ + PBF_PREFETCH_DIST] : 0xffffffffu) \
+                                             : tile + (u32)PBF_PREFETCH_DIST;
 #define TILE_LOOP_END(tc)                                                                \
-        if (tile + gridDim.x < ntl) {                                                    \
+        if (t_ + gridDim.x < tcount) {                                                   \
             __syncthreads();                                                             \
             if ((tc).mode && tid == 0)                                                   \
                 asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&mbar)) : "memory"); \
@@ -471,7 +477,7 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
     }
 
 #define TILE_ARGS const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,   \
-                  const int *__restrict__ desc, const u32 *__restrict__ runs
+                  const int *__restrict__ desc, const u32 *__restrict__ runs, const TileSel sel
 
 // ---- K8 calclambda.glsl:66-103 ------------------------------------------------------------------------------------
 // out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
@@ -483,7 +489,7 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl, tile_ahead);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
@@ -552,7 +558,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -618,7 +624,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, tile_ahead);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -662,7 +668,7 @@ k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -691,7 +697,7 @@ inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
 
 }  // namespace
 
-#define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs
+#define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->tile_sel
 
 u32 plan_tile_size(void) { return (u32)TL; }
 size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
@@ -724,8 +730,9 @@ int launch_plan(pbf_sim *s) {
 static const HaloPush NO_PUSH = {};
 #define SWEEP_LAUNCH(kern_normal, kern_full, smem, ...)                                                          \
     do {                                                                                                          \
-        if (full(s)) kern_full<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);                               \
-        else kern_normal<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);                                     \
+        const int grid_ = s->tile_grid ? (int)s->tile_grid : ntiles(s->n);                                       \
+        if (full(s)) kern_full<<<grid_, TL, smem, s->stream>>>(__VA_ARGS__);                                      \
+        else kern_normal<<<grid_, TL, smem, s->stream>>>(__VA_ARGS__);                                            \
     } while (0)
 
 int launch_lambda(pbf_sim *s, const HaloPush *push) {

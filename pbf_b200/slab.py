@@ -41,6 +41,7 @@ def rebalance_planes(layer_counts, old_planes, max_shift=1, max_thickness=None):
     slabs keep at least 2 layers and at most `max_thickness` (what the handles' grids were allocated for)."""
     counts = np.asarray(layer_counts, dtype=np.int64)
     n = len(old_planes) - 1
+    limit = None if max_thickness is None else ([int(max_thickness)] * n if np.isscalar(max_thickness) else [int(t) for t in max_thickness])
     cum = np.concatenate([[0], np.cumsum(counts)])
     new = [int(old_planes[0])]
     for r in range(1, n):
@@ -48,12 +49,12 @@ def rebalance_planes(layer_counts, old_planes, max_shift=1, max_thickness=None):
         z = int(np.clip(want, old_planes[r] - max_shift, old_planes[r] + max_shift))
         z = max(z, new[-1] + 2)
         z = min(z, int(old_planes[-1]) - 2 * (n - r))
-        if max_thickness is not None:
-            z = min(z, new[-1] + max_thickness)
+        if limit is not None:
+            z = min(z, new[-1] + limit[r - 1])                      # slab r-1 may not outgrow its window ...
         new.append(z)
     new.append(int(old_planes[-1]))
-    if max_thickness is not None and any(b - a > max_thickness for a, b in zip(new[:-1], new[1:])):
-        return [int(z) for z in old_planes]            # cannot be satisfied with the allocated windows: keep the planes
+    if limit is not None and any(b - a > t for a, b, t in zip(new[:-1], new[1:], limit)):
+        return [int(z) for z in old_planes]            # ... nor slab r: if the windows cannot hold the new cut, keep the planes
     return new
 
 
@@ -161,9 +162,10 @@ class SlabSPH(SPH):
         if dist.get_backend() == "nccl":
             t = t.cuda()
         dist.all_reduce(t)
-        thick = torch.tensor([self.max_thickness], dtype=torch.int64, device=t.device)
-        dist.all_reduce(thick, op=dist.ReduceOp.MIN)
-        new = rebalance_planes(t.cpu().numpy(), z_planes, max_shift, int(thick.item()))
+        thick = torch.zeros(self.nranks, dtype=torch.int64, device=t.device)
+        thick[self.rank] = self.max_thickness
+        dist.all_reduce(thick)
+        new = rebalance_planes(t.cpu().numpy(), z_planes, max_shift, thick.cpu().tolist())
         self.set_planes(new[self.rank], new[self.rank + 1])
         return new
 
@@ -237,7 +239,7 @@ class VirtualGroup:
     def rebalance(self, max_shift=1):
         """Move the inner planes by at most max_shift layers towards equal particle counts (between steps)."""
         counts = sum(s.layer_counts().astype(np.int64) for s in self.ranks)
-        new = rebalance_planes(counts, self.z_planes, max_shift, min(s.max_thickness for s in self.ranks))
+        new = rebalance_planes(counts, self.z_planes, max_shift, [s.max_thickness for s in self.ranks])
         for r, s in enumerate(self.ranks):
             s.set_planes(new[r], new[r + 1])
         self.z_planes = new
