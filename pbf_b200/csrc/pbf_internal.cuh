@@ -219,6 +219,8 @@ int sweeps_init(void);                   // opt-in shared-memory sizes of the sw
 size_t plan_desc_ints(u32 cap);
 size_t plan_run_words(u32 cap);
 u32 plan_tile_size(void);                // particles per tile
+int plan_desc_stride(void);              // ints per tile descriptor; word 0 = staging mode, plan_boundary_bit() marks boundary tiles
+int plan_boundary_bit(void);
 int launch_plan(pbf_sim *s);
 SimParams sim_params(const pbf_sim *s);
 // slab.cu

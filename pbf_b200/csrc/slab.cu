@@ -302,7 +302,8 @@ k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *po
 __global__ void __launch_bounds__(256)
 k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
              u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, u32 *__restrict__ push_map,
-             u32 *__restrict__ push_tiles, u32 *__restrict__ blist, u32 tile_size, GridInfo g) {
+             u32 *__restrict__ push_tiles, u32 *__restrict__ blist, int *__restrict__ desc, int desc_stride, int boundary_bit,
+             u32 tile_size, GridInfo g) {
     const u32 n = nref(nr), n_local = nref(nloc);
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u32 kraw = skey[i];
@@ -318,7 +319,10 @@ k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__rest
     if (!edge) continue;
     if (id >= n_local) { ghost_sorted[id - n_local] = i; continue; }
     if (t == 0) continue;
-    if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) blist[atomicAdd(&push_tiles[0], 1u)] = i / tile_size;   // first of its tile
+    if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) {              // first boundary particle of its tile
+        blist[atomicAdd(&push_tiles[0], 1u)] = i / tile_size;
+        if (desc) atomicOr(&desc[(size_t)(i / tile_size) * desc_stride], boundary_bit);
+    }
     if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
     else send_lo[t - 1u] = i;
     }
@@ -990,7 +994,7 @@ int slab_step(pbf_sim **grp, int ng) {
         if (b->n_ghost[0] + b->n_ghost[1] + b->n_bnd[0] + b->n_bnd[1]) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(NRef{s->n, nullptr}, NRef{b->n_local, nullptr}, s->skey, s->perm, b->btag, b->send_idx[0],
-                                                          b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles, b->blist,
+                                                          b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles, b->blist, nullptr, 0, 0,
                                                           plan_tile_size(), s->grid);
             s->launches++;
         }
@@ -1225,7 +1229,8 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(nref_total(s), NRef{b->bound_local, s->dn + DN_LOCAL}, s->skey, s->perm, b->btag,
                                                           b->send_idx[0], b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
-                                                          b->blist, plan_tile_size(), s->grid);
+                                                          b->blist, b->overlap && !s->options.full_support ? s->tile_desc : nullptr,
+                                                          plan_desc_stride(), plan_boundary_bit(), plan_tile_size(), s->grid);
             s->launches++;
         }
         s->launches += launch_highlight(s);

@@ -51,6 +51,7 @@ constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B
 constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
 constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
 constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20;
+constexpr int TILE_BOUNDARY_BIT = 0x100;   // in D_MODE, see tile_begin
 constexpr int RUN_WORDS = 5;     // packed runs of one particle: nine 16-bit fields {image index:11 | count:5}; then
                                  // bit 16 of word 4: the particle meets itself in one of its runs
 static_assert(PBF_TL_CAP + 4 <= 2048, "run fields hold an 11-bit image index");
@@ -240,12 +241,17 @@ __device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, cons
 template <int NSRC>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
-                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, u32 tile_ahead) {
+                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, u32 tile_ahead,
+                                              bool skip_boundary) {
     const int *dg = desc + (size_t)tile * TL_DESC;
     TileCtx c;
     c.tile = tile;
     c.ntiles = ntiles_;
     c.mode = __ldg(dg + D_MODE);
+    // bit 8 (set by the slab runtime after the plan): the tile holds boundary particles and was done by the launch that ran
+    // ahead of the halo push; the launch over "all the other tiles" leaves it alone -- before anything is staged for it
+    if (skip_boundary && (c.mode & TILE_BOUNDARY_BIT)) { c.mode = -1; return c; }
+    c.mode &= TILE_BOUNDARY_BIT - 1;
     c.cut = (u32)__ldg(dg + D_CUT);
     c.img = (unsigned)__cvta_generic_to_shared(dsm);
     const u32 *rp = runs + (size_t)tile * RUN_WORDS * TL + tid;
@@ -268,7 +274,7 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
             const int o = tid - PF0;
             if (o < 9) {
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
-                if (__ldg(fd + D_MODE) && no > 0) {
+                if ((__ldg(fd + D_MODE) & (TILE_BOUNDARY_BIT - 1)) && no > 0) {
                     bulk_prefetch_l2(src0 + so, 16u * (unsigned)no);
                     if (NSRC == 2) bulk_prefetch_l2(src1 + so, 16u * (unsigned)no);
                 }
@@ -464,7 +470,7 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
     const u32 tcount = sel.part == 1 ? min(sel.flags[0], ntl) : ntl;                     \
     for (u32 t_ = blockIdx.x; t_ < tcount; t_ += gridDim.x) {                            \
         const u32 tile = sel.part == 1 ? sel.blist[t_] : t_;                             \
-        if (sel.part == 2 && sel.flags[1 + tile]) continue;                              \
+        if (FULL && sel.part == 2 && sel.flags[1 + tile]) continue;   /* no plan in FULL mode: the flag array itself */ \
         const u32 tile_ahead = sel.part == 1 ? (t_ + (u32)PBF_PREFETCH_DIST < tcount ? sel.blist[t_ + PBF_PREFETCH_DIST] : 0xffffffffu) \
                                              : tile + (u32)PBF_PREFETCH_DIST;
 #define TILE_LOOP_END(tc)                                                                \
@@ -489,7 +495,8 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl, tile_ahead);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
+    if (tc.mode < 0) continue;
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
@@ -558,7 +565,8 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
+    if (tc.mode < 0) continue;
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -624,7 +632,8 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, tile_ahead);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
+    if (tc.mode < 0) continue;
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -668,7 +677,8 @@ k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
+    if (tc.mode < 0) continue;
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -700,6 +710,8 @@ inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
 #define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->tile_sel
 
 u32 plan_tile_size(void) { return (u32)TL; }
+int plan_desc_stride(void) { return TL_DESC; }
+int plan_boundary_bit(void) { return TILE_BOUNDARY_BIT; }
 size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
 size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 
