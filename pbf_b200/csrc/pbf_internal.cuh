@@ -73,16 +73,6 @@ struct LeaveArgs {
     u32 cap;
 };
 
-// Which tiles one launch of a sweep kernel covers.  Slab ranks run every sweep that feeds a halo refresh in two launches:
-// first the few tiles that hold boundary particles (part 1: the list k_halo_index built), then -- while a second stream
-// already pushes those particles' values into the neighbour's mailbox -- all the others (part 2: every tile whose flag is
-// clear).  part 0: all tiles, one launch.
-struct TileSel {
-    const u32 *blist;      // tiles that hold boundary particles, in no particular order
-    const u32 *flags;      // [0] = how many, [1 + tile] = tile is in blist
-    int part;
-};
-
 struct SortPlan {
     int bits;        // low key bits that take part in the sort = 2*ceil(numbits/2) (src/RadixSort.cpp:127)
     int passes;      // onesweep passes of up to 9 bits
@@ -124,8 +114,6 @@ struct pbf_sim {
     // plan of the tiled sweeps (sweeps.cu): per 256-particle tile the nine sorted-index ranges that hold all its
     // candidates, per particle its nine neighbour runs relative to the tile's shared-memory image
     int *tile_desc; u32 *tile_runs;
-    TileSel tile_sel;                     // applies to the sweep launches that follow (slab.cu sets and clears it)
-    u32 tile_grid;                        // blocks of those launches (0: one per tile)
     bool fuse_update;                     // update.glsl in the epilogue of the last delta-p sweep (env PBF_SEPARATE_UPDATE=1: own kernel)
     bool tiled_sweeps;                    // false (env PBF_GENERAL_SWEEPS=1, debugging): every tile takes the general path
     // solver state in sorted order
@@ -219,8 +207,6 @@ int sweeps_init(void);                   // opt-in shared-memory sizes of the sw
 size_t plan_desc_ints(u32 cap);
 size_t plan_run_words(u32 cap);
 u32 plan_tile_size(void);                // particles per tile
-int plan_desc_stride(void);              // ints per tile descriptor; word 0 = staging mode, plan_boundary_bit() marks boundary tiles
-int plan_boundary_bit(void);
 int launch_plan(pbf_sim *s);
 SimParams sim_params(const pbf_sim *s);
 // slab.cu

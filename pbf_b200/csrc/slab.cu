@@ -94,10 +94,6 @@ struct pbf_slab_state {
     uint64_t graph_key;
     u32 graph_kernels;
     bool use_graph;
-    u32 *blist;                         // sweep tiles that hold boundary particles (push_tiles[0] of them)
-    cudaStream_t xstream;               // the halo pushes run here, under the interior tiles of the producing sweep
-    cudaEvent_t x_ev[2];
-    bool overlap;                       // PBF_SLAB_OVERLAP=0: push after the whole sweep, on the main stream
     bool phases;                        // PBF_SLAB_PHASES=1: direct launches with an event at every phase boundary
     cudaEvent_t ph_ev[8];
     bool ph_valid;
@@ -302,8 +298,7 @@ k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *po
 __global__ void __launch_bounds__(256)
 k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
              u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, u32 *__restrict__ push_map,
-             u32 *__restrict__ push_tiles, u32 *__restrict__ blist, int *__restrict__ desc, int desc_stride, int boundary_bit,
-             u32 tile_size, GridInfo g) {
+             u32 *__restrict__ push_tiles, u32 tile_size, GridInfo g) {
     const u32 n = nref(nr), n_local = nref(nloc);
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u32 kraw = skey[i];
@@ -319,10 +314,7 @@ k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__rest
     if (!edge) continue;
     if (id >= n_local) { ghost_sorted[id - n_local] = i; continue; }
     if (t == 0) continue;
-    if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) {              // first boundary particle of its tile
-        blist[atomicAdd(&push_tiles[0], 1u)] = i / tile_size;
-        if (desc) atomicOr(&desc[(size_t)(i / tile_size) * desc_stride], boundary_bit);
-    }
+    if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
     if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
     else send_lo[t - 1u] = i;
     }
@@ -994,7 +986,7 @@ int slab_step(pbf_sim **grp, int ng) {
         if (b->n_ghost[0] + b->n_ghost[1] + b->n_bnd[0] + b->n_bnd[1]) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(NRef{s->n, nullptr}, NRef{b->n_local, nullptr}, s->skey, s->perm, b->btag, b->send_idx[0],
-                                                          b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles, b->blist, nullptr, 0, 0,
+                                                          b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
                                                           plan_tile_size(), s->grid);
             s->launches++;
         }
@@ -1113,37 +1105,19 @@ void halo_pull_dev(pbf_sim *s, bool wide, u32 e) {
     s->launches++;
 }
 
-// A sweep that produces a halo quantity, and the refresh of that quantity (exchange number e of the step).
-// Overlap (default): the sweep runs in two launches.  First the few tiles that hold boundary particles; as soon as they are
-// done a second stream pushes their values into the neighbours' mailboxes, while the main stream already works on all the
-// other tiles.  By the time the neighbour's pull kernel looks at its flag the values have long arrived: the NVLink
-// transfer, the push kernel and the skew between the ranks hide under the interior tiles (measured: an exchange cost
-// ~34 us per sweep before).  Without overlap: whole sweep, push, pull on one stream.
+// A sweep that produces a halo quantity, and the refresh of that quantity (exchange number e of the step): sweep, push,
+// pull.  Measured and NOT adopted (2 x 8M particles on 2 B200, splash scene): running the tiles that hold boundary particles
+// first and pushing from a second stream under the interior tiles -- 5.09-5.14 ms per step against 5.00-5.06 ms: the
+// tile-selection logic costs every sweep block ~3 % (also on a single GPU: 4.39 -> 4.49 ms), more than the ~30 us per
+// exchange the overlap hides.
 template <class Launch>
 void sweep_and_refresh(pbf_sim **grp, int ng, bool wide, u32 e, Launch launch) {
-    constexpr u32 BOUNDARY_GRID = 2048;     // blocks of the boundary launch (it loops if there are more boundary tiles)
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
         pbf_slab_state *b = s->slab;
         b->exchanges++;
-        if (!b->has[0] && !b->has[1]) { s->launches += launch(s); continue; }
-        if (!b->overlap) {
-            s->launches += launch(s);
-            halo_push_dev(s, wide, e, s->stream);
-            continue;
-        }
-        s->tile_sel = TileSel{b->blist, b->push_tiles, 1};
-        s->tile_grid = BOUNDARY_GRID;
         s->launches += launch(s);
-        cudaEventRecord(b->x_ev[0], s->stream);
-        cudaStreamWaitEvent(b->xstream, b->x_ev[0], 0);
-        halo_push_dev(s, wide, e, b->xstream);
-        cudaEventRecord(b->x_ev[1], b->xstream);
-        s->tile_sel = TileSel{b->blist, b->push_tiles, 2};
-        s->tile_grid = 0;
-        s->launches += launch(s);
-        s->tile_sel = TileSel{nullptr, nullptr, 0};
-        cudaStreamWaitEvent(s->stream, b->x_ev[1], 0);      // joins the push back (the next push reuses its counter)
+        if (b->has[0] || b->has[1]) halo_push_dev(s, wide, e, s->stream);
     }
     for (int r = 0; r < ng; r++)            // all pushes are enqueued before any pull (virtual ranks share one stream)
         if (grp[r]->slab->has[0] || grp[r]->slab->has[1]) halo_pull_dev(grp[r], wide, e);
@@ -1229,8 +1203,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(nref_total(s), NRef{b->bound_local, s->dn + DN_LOCAL}, s->skey, s->perm, b->btag,
                                                           b->send_idx[0], b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
-                                                          b->blist, b->overlap && !s->options.full_support ? s->tile_desc : nullptr,
-                                                          plan_desc_stride(), plan_boundary_bit(), plan_tile_size(), s->grid);
+                                                          plan_tile_size(), s->grid);
             s->launches++;
         }
         s->launches += launch_highlight(s);
@@ -1373,7 +1346,6 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     A((void **)&b->mbox, mbox_bytes(b)); A((void **)&b->push_done, 16); A((void **)&b->push_map, (size_t)s->cap * 4);
     b->max_tiles = (s->cap + plan_tile_size() - 1) / plan_tile_size();
     A((void **)&b->push_tiles, (size_t)(1 + b->max_tiles) * 4);
-    A((void **)&b->blist, (size_t)b->max_tiles * 4);
     A((void **)&b->rec_done, 16);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_counters, 16 * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_ring, (size_t)RING * DN_WORDS * 4);
@@ -1387,10 +1359,6 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     {
         const char *g = getenv("PBF_SLAB_GRAPH");
         b->use_graph = !(g && g[0] == '0');
-        const char *ov = getenv("PBF_SLAB_OVERLAP");
-        b->overlap = !(ov && ov[0] == '0');
-        if (cudaStreamCreateWithFlags(&b->xstream, cudaStreamNonBlocking) != cudaSuccess) b->overlap = false;
-        for (int k = 0; k < 2; k++) cudaEventCreateWithFlags(&b->x_ev[k], cudaEventDisableTiming);
         const char *ph = getenv("PBF_SLAB_PHASES");
         b->phases = ph && ph[0] == '1';
         if (b->phases)
@@ -1441,10 +1409,6 @@ void slab_free(pbf_sim *s) {
     if (b->push_map) cudaFree(b->push_map);
     if (b->push_tiles) cudaFree(b->push_tiles);
     if (b->rec_done) cudaFree(b->rec_done);
-    if (b->blist) cudaFree(b->blist);
-    if (b->xstream) cudaStreamDestroy(b->xstream);
-    for (int k = 0; k < 2; k++)
-        if (b->x_ev[k]) cudaEventDestroy(b->x_ev[k]);
     if (b->h_ring) cudaFreeHost(b->h_ring);
     for (int k = 0; k < RING; k++)
         if (b->ring_ev[k]) cudaEventDestroy(b->ring_ev[k]);

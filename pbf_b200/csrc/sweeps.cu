@@ -51,7 +51,6 @@ constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B
 constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
 constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
 constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20;
-constexpr int TILE_BOUNDARY_BIT = 0x100;   // in D_MODE, see tile_begin
 constexpr int RUN_WORDS = 5;     // packed runs of one particle: nine 16-bit fields {image index:11 | count:5}; then
                                  // bit 16 of word 4: the particle meets itself in one of its runs
 static_assert(PBF_TL_CAP + 4 <= 2048, "run fields hold an 11-bit image index");
@@ -61,6 +60,7 @@ constexpr size_t TL_SMEM1 = TL_IMG;                                // PBF_TL_CTA
 constexpr size_t TL_SMEM2 = 2 * TL_IMG;                            // two arrays: half as many
 
 // ---- the plan: one block per tile ---------------------------------------------------------------------------------------
+template <bool LOOP>
 __global__ void __launch_bounds__(TL)
 k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
        int *__restrict__ desc, u32 *__restrict__ runs, GridInfo g, int allow) {
@@ -69,9 +69,9 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
     __shared__ int sS[9], sN[9], sBase[9];         // per tile: range start, length, (image offset of the range) - start
     __shared__ int sMeta[4];                       // phases, records, cuts, "every range fits one image"
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 n = nref(nr);
-    // one tile per block; the loop only turns when the grid was sized for fewer particles than there are (NRef)
-    for (u32 tile = blockIdx.x; tile * (u32)TL < n; tile += gridDim.x) {
+    const u32 n = LOOP ? nref(nr) : nr.n;
+    // one tile per block; the loop only turns when the grid was sized for fewer particles than there are (NRef, LOOP)
+    for (u32 tile = blockIdx.x; tile * (u32)TL < n; tile += LOOP ? gridDim.x : 0x1000000u) {
     const u32 i = tile * (u32)TL + tid;
     int2 r[9];
 #pragma unroll
@@ -171,7 +171,7 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
     int *d = desc + (size_t)tile * TL_DESC;
     if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = sMeta[1]; d[D_CUT] = sMeta[2]; }
     if (tid < 9) { d[D_S + tid] = sS[tid]; d[D_N + tid] = sN[tid]; }
-    __syncthreads();                               // the shared tables are free for the next tile
+    if (LOOP) __syncthreads();                     // the shared tables are free for the next tile
     }
 }
 
@@ -241,17 +241,12 @@ __device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, cons
 template <int NSRC>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
-                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, u32 tile_ahead,
-                                              bool skip_boundary) {
+                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_) {
     const int *dg = desc + (size_t)tile * TL_DESC;
     TileCtx c;
     c.tile = tile;
     c.ntiles = ntiles_;
     c.mode = __ldg(dg + D_MODE);
-    // bit 8 (set by the slab runtime after the plan): the tile holds boundary particles and was done by the launch that ran
-    // ahead of the halo push; the launch over "all the other tiles" leaves it alone -- before anything is staged for it
-    if (skip_boundary && (c.mode & TILE_BOUNDARY_BIT)) { c.mode = -1; return c; }
-    c.mode &= TILE_BOUNDARY_BIT - 1;
     c.cut = (u32)__ldg(dg + D_CUT);
     c.img = (unsigned)__cvta_generic_to_shared(dsm);
     const u32 *rp = runs + (size_t)tile * RUN_WORDS * TL + tid;
@@ -268,13 +263,13 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     // two DRAM round trips.  Warp 2 does this while the block waits for its own image anyway.
     constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the ten prefetching threads
     if (tid >= PF0 && tid < PF0 + 10) {
-        const u32 ft = tile_ahead;                    // the tile the block one wave later will work on
+        const u32 ft = tile + (u32)PBF_PREFETCH_DIST;
         if (ft < ntiles_) {
             const int *fd = desc + (size_t)ft * TL_DESC;
             const int o = tid - PF0;
             if (o < 9) {
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
-                if ((__ldg(fd + D_MODE) & (TILE_BOUNDARY_BIT - 1)) && no > 0) {
+                if (__ldg(fd + D_MODE) && no > 0) {
                     bulk_prefetch_l2(src0 + so, 16u * (unsigned)no);
                     if (NSRC == 2) bulk_prefetch_l2(src1 + so, 16u * (unsigned)no);
                 }
@@ -464,17 +459,12 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
 // Every sweep kernel: one tile per block; the loop only turns when the grid was sized for fewer particles than there are
 // (NRef: a slab rank's count lives on the device).  Before a block reuses its image and its mbarrier for another tile
 // everybody must be done with them and the barrier object must be invalidated.
-// sel (TileSel): part 1 walks the list of boundary tiles, part 2 all tiles but those (slab ranks, see pbf_internal.cuh).
+// LOOP = false (count known on the host, grid = tiles): the loop folds into `if (blockIdx.x < tiles)`, the original kernel.
 #define TILE_LOOP_BEGIN                                                                  \
-    const u32 n = nref(nr), ntl = (n + (u32)TL - 1u) / (u32)TL;                          \
-    const u32 tcount = sel.part == 1 ? min(sel.flags[0], ntl) : ntl;                     \
-    for (u32 t_ = blockIdx.x; t_ < tcount; t_ += gridDim.x) {                            \
-        const u32 tile = sel.part == 1 ? sel.blist[t_] : t_;                             \
-        if (FULL && sel.part == 2 && sel.flags[1 + tile]) continue;   /* no plan in FULL mode: the flag array itself */ \
-        const u32 tile_ahead = sel.part == 1 ? (t_ + (u32)PBF_PREFETCH_DIST < tcount ? sel.blist[t_ + PBF_PREFETCH_DIST] : 0xffffffffu) \
-                                             : tile + (u32)PBF_PREFETCH_DIST;
+    const u32 n = LOOP ? nref(nr) : nr.n, ntl = (n + (u32)TL - 1u) / (u32)TL;            \
+    for (u32 tile = blockIdx.x; tile < ntl; tile += LOOP ? gridDim.x : 0x40000000u) {
 #define TILE_LOOP_END(tc)                                                                \
-        if (t_ + gridDim.x < tcount) {                                                   \
+        if (LOOP && tile + gridDim.x < ntl) {                                            \
             __syncthreads();                                                             \
             if ((tc).mode && tid == 0)                                                   \
                 asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(&mbar)) : "memory"); \
@@ -483,11 +473,11 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
     }
 
 #define TILE_ARGS const u32 *__restrict__ home, const int2 *__restrict__ runs3, const int2 *__restrict__ cells,   \
-                  const int *__restrict__ desc, const u32 *__restrict__ runs, const TileSel sel
+                  const int *__restrict__ desc, const u32 *__restrict__ runs
 
 // ---- K8 calclambda.glsl:66-103 ------------------------------------------------------------------------------------
 // out {x,y,z,lambda}.  rho (self excluded), S = sum |g_j|^2 + |sum g_j|^2, lambda = -C/(S+eps).
-template <bool DIAG, bool FULL>
+template <bool DIAG, bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag,
          const HaloPush hp) {
@@ -495,8 +485,7 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
-    if (tc.mode < 0) continue;
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
@@ -557,7 +546,7 @@ struct UpdateArgs {
                              // position) must survive for k_ghost_velocity; null on a single domain
 };
 
-template <int FINAL, bool FULL>
+template <int FINAL, bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp,
           const UpdateArgs up) {
@@ -565,8 +554,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
-    if (tc.mode < 0) continue;
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -624,7 +612,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
 
 // ---- K11 vorticity.glsl:34-60 (first sweep): XSPH + vorticity ------------------------------------------------------------
 // out: vprime = v + c*sum v_ij W, omega = sum v_ij x gradW, B = {p, |omega|}
-template <bool FULL>
+template <bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL)
 k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
               float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P, const HaloPush hp) {
@@ -632,8 +620,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
-    if (tc.mode < 0) continue;
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -669,7 +656,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
 }
 
 // ---- K11 vorticity.glsl:65-85 (second sweep): confinement force, velocity[id] written once -------------------------------
-template <bool FULL>
+template <bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
               const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P) {
@@ -677,8 +664,7 @@ k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ 
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, tile_ahead, sel.part == 2);
-    if (tc.mode < 0) continue;
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -707,11 +693,9 @@ inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
 
 }  // namespace
 
-#define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->tile_sel
+#define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs
 
 u32 plan_tile_size(void) { return (u32)TL; }
-int plan_desc_stride(void) { return TL_DESC; }
-int plan_boundary_bit(void) { return TILE_BOUNDARY_BIT; }
 size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
 size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 
@@ -720,12 +704,16 @@ int sweeps_init(void) {
     auto opt = [&](const void *f, size_t bytes) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     };
-    opt((const void *)k_lambda<false, false>, TL_SMEM1); opt((const void *)k_lambda<true, false>, TL_SMEM1);
-    opt((const void *)k_lambda<false, true>, TL_SMEM1); opt((const void *)k_lambda<true, true>, TL_SMEM1);
-    opt((const void *)k_delta_p<0, false>, TL_SMEM1); opt((const void *)k_delta_p<1, false>, TL_SMEM1); opt((const void *)k_delta_p<2, false>, TL_SMEM1);
-    opt((const void *)k_delta_p<0, true>, TL_SMEM1); opt((const void *)k_delta_p<1, true>, TL_SMEM1); opt((const void *)k_delta_p<2, true>, TL_SMEM1);
-    opt((const void *)k_vorticity_b<false>, TL_SMEM1); opt((const void *)k_vorticity_b<true>, TL_SMEM1);
-    opt((const void *)k_vorticity_a<false>, TL_SMEM2); opt((const void *)k_vorticity_a<true>, TL_SMEM2);
+#define OPT_ALL(kern, smem, ...)                                                                      \
+    opt((const void *)kern<__VA_ARGS__, false, false>, smem); opt((const void *)kern<__VA_ARGS__, false, true>, smem); \
+    opt((const void *)kern<__VA_ARGS__, true, false>, smem); opt((const void *)kern<__VA_ARGS__, true, true>, smem);
+    OPT_ALL(k_lambda, TL_SMEM1, false) OPT_ALL(k_lambda, TL_SMEM1, true)
+    OPT_ALL(k_delta_p, TL_SMEM1, 0) OPT_ALL(k_delta_p, TL_SMEM1, 1) OPT_ALL(k_delta_p, TL_SMEM1, 2)
+#undef OPT_ALL
+    opt((const void *)k_vorticity_b<false, false>, TL_SMEM1); opt((const void *)k_vorticity_b<false, true>, TL_SMEM1);
+    opt((const void *)k_vorticity_b<true, false>, TL_SMEM1); opt((const void *)k_vorticity_b<true, true>, TL_SMEM1);
+    opt((const void *)k_vorticity_a<false, false>, TL_SMEM2); opt((const void *)k_vorticity_a<false, true>, TL_SMEM2);
+    opt((const void *)k_vorticity_a<true, false>, TL_SMEM2); opt((const void *)k_vorticity_a<true, true>, TL_SMEM2);
     return e == cudaSuccess ? 0 : -1;
 }
 
@@ -734,27 +722,41 @@ static inline bool full(const pbf_sim *s) { return s->options.full_support != 0;
 
 int launch_plan(pbf_sim *s) {
     if (full(s)) return 0;
-    k_plan<<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
-                                               s->tiled_sweeps ? 1 : 0);
+    if (s->n_dev)
+        k_plan<true><<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
+                                                         s->tiled_sweeps ? 1 : 0);
+    else
+        k_plan<false><<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
+                                                          s->tiled_sweeps ? 1 : 0);
     return 1;
 }
 
 static const HaloPush NO_PUSH = {};
-#define SWEEP_LAUNCH(kern_normal, kern_full, smem, ...)                                                          \
+// kernel<..., FULL, LOOP>: FULL = 5 x 5 x 5 search, LOOP = the count lives on the device (slab rank)
+#define SWEEP_LAUNCH(K, smem, ...)                                                                                \
     do {                                                                                                          \
-        const int grid_ = s->tile_grid ? (int)s->tile_grid : ntiles(s->n);                                       \
-        if (full(s)) kern_full<<<grid_, TL, smem, s->stream>>>(__VA_ARGS__);                                      \
-        else kern_normal<<<grid_, TL, smem, s->stream>>>(__VA_ARGS__);                                            \
+        const bool loop_ = s->n_dev != nullptr;                                                                   \
+        if (full(s)) { if (loop_) K(true, true)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);              \
+                       else K(true, false)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__); }                 \
+        else { if (loop_) K(false, true)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);                     \
+               else K(false, false)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__); }                        \
     } while (0)
+#define KL_LAMBDA(F, L) k_lambda<false, F, L>
+#define KL_DIAG(F, L) k_lambda<true, F, L>
+#define KL_DP0(F, L) k_delta_p<0, F, L>
+#define KL_DP1(F, L) k_delta_p<1, F, L>
+#define KL_DP2(F, L) k_delta_p<2, F, L>
+#define KL_VA(F, L) k_vorticity_a<F, L>
+#define KL_VB(F, L) k_vorticity_b<F, L>
 
 int launch_lambda(pbf_sim *s, const HaloPush *push) {
-    SWEEP_LAUNCH((k_lambda<false, false>), (k_lambda<false, true>), TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
+    SWEEP_LAUNCH(KL_LAMBDA, TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
                  sim_params(s), nullptr, push ? *push : NO_PUSH);
     return 1;
 }
 
 int launch_delta_p(pbf_sim *s, const HaloPush *push) {
-    SWEEP_LAUNCH((k_delta_p<0, false>), (k_delta_p<0, true>), TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
+    SWEEP_LAUNCH(KL_DP0, TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
                  sim_params(s), push ? *push : NO_PUSH, UpdateArgs{});
     return 1;
 }
@@ -763,22 +765,22 @@ int launch_delta_p(pbf_sim *s, const HaloPush *push) {
 int launch_delta_p_update(pbf_sim *s) {
     const UpdateArgs up = {s->perm, s->pos, s->vel, s->svel, s->n_dev ? s->dn + DN_LOCAL : nullptr};
     if (s->params.vorticity_confinement)
-        SWEEP_LAUNCH((k_delta_p<2, false>), (k_delta_p<2, true>), TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
+        SWEEP_LAUNCH(KL_DP2, TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
                      sim_params(s), NO_PUSH, up);
     else
-        SWEEP_LAUNCH((k_delta_p<1, false>), (k_delta_p<1, true>), TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
+        SWEEP_LAUNCH(KL_DP1, TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
                      sim_params(s), NO_PUSH, up);
     return 1;
 }
 
 int launch_vorticity_a(pbf_sim *s, const HaloPush *push) {
-    SWEEP_LAUNCH((k_vorticity_a<false>), (k_vorticity_a<true>), TL_SMEM2, nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
+    SWEEP_LAUNCH(KL_VA, TL_SMEM2, nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
                  s->omega, s->grid, sim_params(s), push ? *push : NO_PUSH);
     return 1;
 }
 
 int launch_vorticity_b(pbf_sim *s) {
-    SWEEP_LAUNCH((k_vorticity_b<false>), (k_vorticity_b<true>), TL_SMEM1, nref_total(s), s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
+    SWEEP_LAUNCH(KL_VB, TL_SMEM1, nref_total(s), s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
                  s->vel, s->grid, sim_params(s));
     return 1;
 }
@@ -786,7 +788,7 @@ int launch_vorticity_b(pbf_sim *s) {
 int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s, nullptr) + launch_vorticity_b(s); }
 
 int launch_density_diag(pbf_sim *s) {
-    SWEEP_LAUNCH((k_lambda<true, false>), (k_lambda<true, true>), TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
+    SWEEP_LAUNCH(KL_DIAG, TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
                  sim_params(s), s->diag, NO_PUSH);
     return 1;
 }
