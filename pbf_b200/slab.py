@@ -364,14 +364,16 @@ def bench(args, name, cfg, scene, rank, world, local, B):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": B.static_config(name, cfg, world, scene),
-            "detail": {"halo_transport": ("peer-memory stores + flags over NVLink (lambda, positions, |omega|)%s; NCCL send/recv for migration and ghost records"
-                                          % (", pushed by the producing sweep's epilogue" if os.environ.get("PBF_SLAB_FUSED") == "1" else ", push kernel + pull kernel")) if p2p else "NCCL send/recv",
+            "detail": {"halo_transport": (("peer-memory stores + release flags over NVLink for everything (migration and ghost records into the neighbour's inbox; lambda, positions, |omega| into its mailbox); counts stay on the device, the step is one CUDA graph"
+                                           if os.environ.get("PBF_SLAB_DEVCOUNT", "1") != "0" and os.environ.get("PBF_SLAB_FUSED") != "1" else
+                                           "peer-memory stores + flags for lambda, positions, |omega|; NCCL send/recv for migration and ghost records, counts read back twice per step")
+                                          if p2p else "NCCL send/recv"),
                        "particles_total": int(n_total), "particles_per_rank_min_max": [int(tmin[1].item()), int(tmax[1].item())],
                        "migrated_particles_in_timed_steps": int(tsum[2].item()),
                        "migrated_fraction_per_step": tsum[2].item() / max(1.0, n_total * args.steps),
                        "ghost_particles_total": int(tsum[3].item()),
                        "ms_per_step_min_over_ranks": tmin[0].item(),
-                       "exchanges_per_step": st["exchanges"] // max(1, args.steps + args.warmup),
+                       "exchanges_per_step": 2 + 2 * cfg["iters"] + (1 if cfg["vort"] else 0),
                        "step_algorithmic_bytes_per_particle": step_bytes,
                        "step_hbm_frac_of_peak": per_gpu_gbs / peak, "rank0_phase_ms_last_step": phases},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
