@@ -9,4 +9,4 @@ compute-sanitizer --tool memcheck --error-exitcode 77 --print-limit 20 python -m
 echo "memcheck exit code: $?" >> gpurun_out/${1:-r02}_memcheck.log
 compute-sanitizer --tool racecheck --error-exitcode 77 --print-limit 20 python -m pytest tests -m gpu -q -x -k "$SEL_RACE" > gpurun_out/${1:-r02}_racecheck.log 2>&1
 echo "racecheck exit code: $?" >> gpurun_out/${1:-r02}_racecheck.log
-tail -4 gpurun_out/${1:-r02}_memcheck.log gpurun_out/${1:-r02}_racecheck.log
+tail -n 4 gpurun_out/${1:-r02}_memcheck.log; tail -n 4 gpurun_out/${1:-r02}_racecheck.log
