@@ -241,7 +241,9 @@ __device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, cons
 template <int NSRC>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
-                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_) {
+                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, int ptid = -1) {
+    // ptid: the thread's particle within the tile when it differs from tid (two threads per particle, k_vorticity_a)
+    if (ptid < 0) ptid = tid;
     const int *dg = desc + (size_t)tile * TL_DESC;
     TileCtx c;
     c.tile = tile;
@@ -249,7 +251,7 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     c.mode = __ldg(dg + D_MODE);
     c.cut = (u32)__ldg(dg + D_CUT);
     c.img = (unsigned)__cvta_generic_to_shared(dsm);
-    const u32 *rp = runs + (size_t)tile * RUN_WORDS * TL + tid;
+    const u32 *rp = runs + (size_t)tile * RUN_WORDS * TL + ptid;
     u32 w[RUN_WORDS];
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) w[k] = __ldg(rp + k * TL);   // in flight while the bulk copies land
@@ -354,16 +356,19 @@ __device__ __forceinline__ void walk_run(unsigned a, const unsigned end, F &body
     }
 }
 
+// split (two threads per particle): 0 = this thread walks all nine runs; 1 / 2 = in a one-image tile the even / odd run
+// slots (the runs are sorted by length, so the halves weigh about the same), in a tile staged in phases all / none.
 template <int NSRC, class F>
 __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsigned long long *mbar,
                                            const float4 *__restrict__ src0, const float4 *__restrict__ src1,
-                                           const int *__restrict__ desc, int tid, F body) {
+                                           const int *__restrict__ desc, int tid, F body, int split = 0) {
     const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
     __syncthreads();                                       // the barrier is initialised
     if (c.mode == 1) {                                     // all nine ranges in one image (all but a handful of tiles):
         mbar_wait(mb, 0u);                                 // no per-run phase test
 #pragma unroll
         for (int o = 0; o < 9; o++) {
+            if (split && ((o & 1) + 1) != split) continue;
             const unsigned a = c.img + 16u * (c.run[o] & 0x7ffu);
             walk_run<NSRC>(a, a + 16u * (c.run[o] >> 11), body);
         }
@@ -379,7 +384,7 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
         }
         mbar_wait(mb, (unsigned)(ph & 1));
 #pragma unroll 1
-        for (int o = lo; o < hi; o++) {                    // rare path: rolled, the runs come from a switch
+        for (int o = lo; o < (split == 2 ? lo : hi); o++) {   // rare path: rolled, the runs come from a switch
             u32 r = 0;
 #pragma unroll
             for (int k = 0; k < 9; k++) r = (o == k) ? c.run[k] : r;
@@ -412,11 +417,13 @@ template <int NSRC, bool FULL, class F>
 __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                      const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                      const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
-                                     const int *__restrict__ desc, const GridInfo &g, u32 i, bool live, int tid, F body) {
+                                     const int *__restrict__ desc, const GridInfo &g, u32 i, bool live, int tid, F body,
+                                     int split = 0) {
+    if (split == 2 && (FULL || c.mode == 0)) return;       // the second thread of a particle has no share in the general walk
     if (FULL) {                                            // full-support search: 25 rows of five cells from global memory
         if (live) general_walk<NSRC, 2>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
     } else if (c.mode) {
-        tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body);
+        tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body, split);
     } else if (live) {
         general_walk<NSRC, 1>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
     }
@@ -612,16 +619,22 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
 
 // ---- K11 vorticity.glsl:34-60 (first sweep): XSPH + vorticity ------------------------------------------------------------
 // out: vprime = v + c*sum v_ij W, omega = sum v_ij x gradW, B = {p, |omega|}
+// TWO THREADS PER PARTICLE: this kernel stages two images (positions and velocities, 52 KB), so only four blocks fit an SM;
+// with one thread per particle that is 16 warps per SM, and the kernel spent 45 % of its issue slots waiting (ncu r02h).
+// Blocks of 2 x TL threads give it the 32 warps the other sweeps have: thread t and thread t + TL share particle t, the
+// first walks the even run slots, the second the odd ones (the plan sorts a particle's runs by length, so the halves weigh
+// about the same), and the partial sums meet in shared memory.
 template <bool FULL, bool LOOP>
-__global__ void __launch_bounds__(TL)
+__global__ void __launch_bounds__(2 * TL, 4)
 k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ svel, TILE_ARGS, float4 *__restrict__ B,
               float4 *__restrict__ vprime, float4 *__restrict__ omega, GridInfo g, SimParams P, const HaloPush hp) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
-    const int tid = threadIdx.x;
+    float (*part)[TL] = reinterpret_cast<float (*)[TL]>(dsm);   // 3 KB of the image area, once everybody is done walking it
+    const int tid = threadIdx.x, ptid = tid & (TL - 1), second = tid >= TL ? 1 : 0;
     TILE_LOOP_BEGIN
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl);
-    const u32 i = tile * TL + tid;
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, ptid);
+    const u32 i = tile * TL + ptid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -642,16 +655,28 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
         wx = __ffma2_rn(uy, gz, __ffma2_rn(__fmul2_rn(gy, uz), neg1, wx));
         wy = __ffma2_rn(uz, gx, __ffma2_rn(__fmul2_rn(gz, ux), neg1, wy));
         wz = __ffma2_rn(ux, gy, __ffma2_rn(__fmul2_rn(gx, uy), neg1, wz));
-    });
-    const float cw = -P.xsph_c * POLY6;
-    const float ox = SPIKY_GRAD * (wx.x + wx.y), oy = SPIKY_GRAD * (wy.x + wy.y), oz = SPIKY_GRAD * (wz.x + wz.y);
-    const float4 out = make_float4(pi.x, pi.y, pi.z, sqrtf(ox * ox + oy * oy + oz * oz));   // vorticity.glsl:60
-    if (live) {
-        vprime[i] = make_float4(vi.x + cw * (vx.x + vx.y), vi.y + cw * (vy.x + vy.y), vi.z + cw * (vz.x + vz.y), 0.0f);
+    }, 1 + second);
+    // the second thread hands its share over (zeros where it had none: general path, tiles staged in phases)
+    __syncthreads();
+    if (second) {
+        part[0][ptid] = vx.x + vx.y; part[1][ptid] = vy.x + vy.y; part[2][ptid] = vz.x + vz.y;
+        part[3][ptid] = wx.x + wx.y; part[4][ptid] = wy.x + wy.y; part[5][ptid] = wz.x + wz.y;
+    }
+    __syncthreads();
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool mine = live && !second;
+    if (mine) {
+        const float sx = (vx.x + vx.y) + part[0][ptid], sy = (vy.x + vy.y) + part[1][ptid], sz = (vz.x + vz.y) + part[2][ptid];
+        const float cw = -P.xsph_c * POLY6;
+        const float ox = SPIKY_GRAD * ((wx.x + wx.y) + part[3][ptid]), oy = SPIKY_GRAD * ((wy.x + wy.y) + part[4][ptid]),
+                    oz = SPIKY_GRAD * ((wz.x + wz.y) + part[5][ptid]);
+        out = make_float4(pi.x, pi.y, pi.z, sqrtf(ox * ox + oy * oy + oz * oz));   // vorticity.glsl:60
+        vprime[i] = make_float4(vi.x + cw * sx, vi.y + cw * sy, vi.z + cw * sz, 0.0f);
         omega[i] = make_float4(ox, oy, oz, 0.0f);
         B[i] = out;
     }
-    halo_push(hp, i, live, out, false, tid);
+    halo_push(hp, i, mine, out, false, tid);
+    if (LOOP) __syncthreads();                             // part[] is free for the next tile
     TILE_LOOP_END(tc)
 }
 
@@ -733,14 +758,15 @@ int launch_plan(pbf_sim *s) {
 
 static const HaloPush NO_PUSH = {};
 // kernel<..., FULL, LOOP>: FULL = 5 x 5 x 5 search, LOOP = the count lives on the device (slab rank)
-#define SWEEP_LAUNCH(K, smem, ...)                                                                                \
+#define SWEEP_LAUNCH_T(K, threads, smem, ...)                                                                     \
     do {                                                                                                          \
         const bool loop_ = s->n_dev != nullptr;                                                                   \
-        if (full(s)) { if (loop_) K(true, true)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);              \
-                       else K(true, false)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__); }                 \
-        else { if (loop_) K(false, true)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__);                     \
-               else K(false, false)<<<ntiles(s->n), TL, smem, s->stream>>>(__VA_ARGS__); }                        \
+        if (full(s)) { if (loop_) K(true, true)<<<ntiles(s->n), threads, smem, s->stream>>>(__VA_ARGS__);         \
+                       else K(true, false)<<<ntiles(s->n), threads, smem, s->stream>>>(__VA_ARGS__); }            \
+        else { if (loop_) K(false, true)<<<ntiles(s->n), threads, smem, s->stream>>>(__VA_ARGS__);                \
+               else K(false, false)<<<ntiles(s->n), threads, smem, s->stream>>>(__VA_ARGS__); }                   \
     } while (0)
+#define SWEEP_LAUNCH(K, smem, ...) SWEEP_LAUNCH_T(K, TL, smem, __VA_ARGS__)
 #define KL_LAMBDA(F, L) k_lambda<false, F, L>
 #define KL_DIAG(F, L) k_lambda<true, F, L>
 #define KL_DP0(F, L) k_delta_p<0, F, L>
@@ -774,7 +800,7 @@ int launch_delta_p_update(pbf_sim *s) {
 }
 
 int launch_vorticity_a(pbf_sim *s, const HaloPush *push) {
-    SWEEP_LAUNCH(KL_VA, TL_SMEM2, nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
+    SWEEP_LAUNCH_T(KL_VA, 2 * TL, TL_SMEM2, nref_total(s), s->bufA, s->svel, TILE_PASS, s->bufB, s->vprime,
                  s->omega, s->grid, sim_params(s), push ? *push : NO_PUSH);
     return 1;
 }
