@@ -69,8 +69,9 @@ enum { DN_TOTAL = 0, DN_LOCAL = 1, DN_PREV = 2, DN_STAY = 3, DN_LEAVE = 4 /* lo,
 struct LeaveArgs {
     int z_lo, z_hi;
     bool has_lo, has_hi;
-    u32 *btag, *leave_lo, *leave_hi, *cnt;
+    u32 *btag, *leave_lo, *leave_hi, *cnt;     // cnt[0..1] leavers lo / hi, cnt[2..3] boundary-layer particles lo / hi
     u32 cap;
+    u32 *bnd_lo, *bnd_hi;                      // non-null: also list the particles of the boundary layers z_lo and z_hi - 1
 };
 
 struct SortPlan {

@@ -89,6 +89,12 @@ k_predict(u32 first, NRef nr, const float4 *__restrict__ pos, const float4 *__re
                 const u32 k = atomicAdd(&la.cnt[1], 1u);
                 if (k < la.cap) la.leave_hi[k] = i;
                 tag = 0xffffffffu;
+            } else if (la.bnd_lo && la.has_lo && cz == la.z_lo) {          // the neighbours' ghosts-to-be (k_mark_boundary)
+                const u32 k = atomicAdd(&la.cnt[2], 1u);
+                if (k < la.cap) { la.bnd_lo[k] = i; tag = k + 1u; }
+            } else if (la.bnd_hi && la.has_hi && cz == la.z_hi - 1) {
+                const u32 k = atomicAdd(&la.cnt[3], 1u);
+                if (k < la.cap) { la.bnd_hi[k] = i; tag = 0x80000000u | (k + 1u); }
             }
             la.btag[i] = tag;
         }

@@ -480,11 +480,17 @@ k_find_holes_dev(const u32 *__restrict__ dn, int side, const u32 *__restrict__ l
 }
 __global__ void __launch_bounds__(256)
 k_fill_holes_dev(const u32 *__restrict__ cnt, const u32 *__restrict__ holes, const u32 *__restrict__ movers, float4 *pos,
-                 float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys) {
+                 float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys, u32 *btag, u32 *bnd_lo, u32 *bnd_hi) {
     const u32 count = cnt[5];
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
         const u32 d = holes[k], s = movers[k];
         pos[d] = pos[s]; vel[d] = vel[s]; gid[d] = gid[s]; hl[d] = hl[s]; keys[d] = keys[s];
+        const u32 tag = btag[s];                       // a boundary-layer particle keeps its place in the list k_predict made
+        btag[d] = tag;
+        if (tag) {
+            if (tag & 0x80000000u) bnd_hi[(tag & 0x7fffffffu) - 1u] = d;
+            else bnd_lo[tag - 1u] = d;
+        }
         float4 p = pred[s];
         p.w = __int_as_float((int)d);
         pred[d] = p;
@@ -494,7 +500,8 @@ k_fill_holes_dev(const u32 *__restrict__ cnt, const u32 *__restrict__ holes, con
 // wait for both neighbours' migrants of this step and append them after the stayers (lo first, then hi)
 __global__ void __launch_bounds__(256)
 k_pull_migrants(const u32 *__restrict__ dn, char *my_area_lo0, char *my_area_hi0, size_t area_bytes, u32 cap, u32 part_cap,
-                bool has_lo, bool has_hi, float4 *pos, float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys, GridInfo g) {
+                bool has_lo, bool has_hi, float4 *pos, float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys, GridInfo g,
+                int z_lo, int z_hi, u32 *btag, u32 *bnd_lo, u32 *bnd_hi, u32 *cnt) {
     const u32 step = dn[DN_STEP];
     char *alo = my_area_lo0 + (size_t)(step & 1u) * area_bytes, *ahi = my_area_hi0 + (size_t)(step & 1u) * area_bytes;
     if (threadIdx.x == 0) {
@@ -519,6 +526,17 @@ k_pull_migrants(const u32 *__restrict__ dn, char *my_area_lo0, char *my_area_hi0
         r.pred.w = __int_as_float((int)s);
         pred[s] = r.pred;
         keys[s] = window_key(r.pred.x, r.pred.y, r.pred.z, g);
+        // an arrival that landed in one of my boundary layers is a ghost-to-be of the neighbour on that side
+        const int cz = global_layer(r.pred.z, g);
+        u32 tag = 0;
+        if (has_lo && cz == z_lo) {
+            const u32 q2 = atomicAdd(&cnt[2], 1u);
+            if (q2 < cap) { bnd_lo[q2] = s; tag = q2 + 1u; }
+        } else if (has_hi && cz == z_hi - 1) {
+            const u32 q2 = atomicAdd(&cnt[3], 1u);
+            if (q2 < cap) { bnd_hi[q2] = s; tag = 0x80000000u | (q2 + 1u); }
+        }
+        btag[s] = tag;
     }
 }
 
@@ -1139,7 +1157,8 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         cudaMemsetAsync(b->counters, 0, 16 * sizeof(u32), s->stream);
         k_step_begin<<<1, 32, 0, s->stream>>>(s->dn);
         // one pass over the local particles: predict, reset of the previous step's table entries, who leaves
-        const LeaveArgs la = {b->z_lo, b->z_hi, b->has[0], b->has[1], b->btag, b->list[0], b->list[1], b->counters, b->halo_cap};
+        const LeaveArgs la = {b->z_lo, b->z_hi, b->has[0], b->has[1], b->btag, b->list[0], b->list[1], b->counters, b->halo_cap,
+                              b->list[2], b->list[3]};
         s->launches += 1 + launch_predict_slab(s, nloc, la);
         k_counts_leave<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
         s->launches += 1;
@@ -1154,7 +1173,8 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
             k_find_movers_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, b->btag, b->movers, b->counters);
             for (int side = 0; side < 2; side++)
                 if (b->has[side]) { k_find_holes_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[side], b->holes, b->counters); s->launches++; }
-            k_fill_holes_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(b->counters, b->holes, b->movers, s->pos, s->vel, s->pred, b->gid, s->hl, s->keys);
+            k_fill_holes_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(b->counters, b->holes, b->movers, s->pos, s->vel, s->pred, b->gid, s->hl, s->keys,
+                                                                b->btag, b->list[2], b->list[3]);
             s->launches += 2;
         }
     }
@@ -1167,14 +1187,15 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         char *alo = inbox_area(b->mbox, b, 0), *ahi = inbox_area(b->mbox, b, 1);
         if (b->has[0] || b->has[1]) {
             k_pull_migrants<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1],
-                                                               s->pos, s->vel, s->pred, b->gid, s->hl, s->keys, s->grid);
+                                                               s->pos, s->vel, s->pred, b->gid, s->hl, s->keys, s->grid,
+                                                               b->z_lo, b->z_hi, b->btag, b->list[2], b->list[3], b->counters);
             s->launches++;
         }
+        // the boundary-layer lists were made on the way: by k_predict for the particles that stayed (slots patched by the
+        // compaction), by k_pull_migrants for the arrivals -- no pass of its own over the local particles
         k_counts_arrive<<<1, 32, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1]);
-        k_mark_boundary<<<nb(b->bound_local), 256, 0, s->stream>>>(nloc, s->pred, s->grid, b->z_lo, b->z_hi, b->has[0], b->has[1], b->btag,
-                                                                   b->list[2], b->list[3], b->counters, b->halo_cap);
         k_counts_boundary<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
-        s->launches += 3;
+        s->launches += 2;
         for (int side = 0; side < 2; side++)
             if (b->has[side]) {
                 k_push_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[2 + side], s->pred, s->pos, s->hl, b->peer_inbox[side],
