@@ -310,6 +310,7 @@ k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__rest
     const bool edge = (kraw & PBF_KEY_NOCELL) != 0u || !(cz > 1 && cz < g.gz - 2);
     const u32 id = edge ? perm[i] : 0u;
     if (edge && id < n_local) t = btag[id];
+    if (t == LEAVER) t = 0;        // only after a capacity overflow (a leaver that could not be sent): reported by the host
     push_map[i] = t;
     if (!edge) continue;
     if (id >= n_local) { ghost_sorted[id - n_local] = i; continue; }
@@ -481,7 +482,9 @@ k_find_holes_dev(const u32 *__restrict__ dn, int side, const u32 *__restrict__ l
 __global__ void __launch_bounds__(256)
 k_fill_holes_dev(const u32 *__restrict__ cnt, const u32 *__restrict__ holes, const u32 *__restrict__ movers, float4 *pos,
                  float4 *vel, float4 *pred, u32 *gid, u32 *hl, u32 *keys, u32 *btag, u32 *bnd_lo, u32 *bnd_hi) {
-    const u32 count = cnt[5];
+    // holes and movers pair up one to one -- except after a capacity overflow (leavers that could not be listed), which the
+    // host reports; until then nothing may be read or written out of bounds
+    const u32 count = min(cnt[5], cnt[4]);
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
         const u32 d = holes[k], s = movers[k];
         pos[d] = pos[s]; vel[d] = vel[s]; gid[d] = gid[s]; hl[d] = hl[s]; keys[d] = keys[s];
