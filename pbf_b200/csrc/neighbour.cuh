@@ -123,6 +123,15 @@ __device__ __forceinline__ Pair ldg_pair(const float4 *p) {   // one 256-bit rea
     return r;
 }
 
+// the same through L2 only: for arrays that other blocks of the SAME kernel write (ghost slots, fused halo pull)
+__device__ __forceinline__ Pair ldcg_pair(const float4 *p) {
+    Pair r;
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.x.x), "=f"(r.y.x), "=f"(r.z.x), "=f"(r.w.x), "=f"(r.x.y), "=f"(r.y.y), "=f"(r.z.y), "=f"(r.w.y)
+                 : "l"(p) : "memory");
+    return r;
+}
+
 __device__ __forceinline__ float rsqrt_ftz(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -46,6 +46,30 @@ struct HaloPush {
     u32 *done;                       // counter of the blocks that have pushed
     const u32 *expect;               // how many blocks (tiles) hold boundary particles at all: the last of them publishes
     u32 count[2];                    // boundary particles per face (a flag is only published for a non-empty face)
+    // device-side counts (slab.cu, one graph per step): the sequence number is 256 * dn[DN_STEP] + e and the per-face counts
+    // are dn[DN_HALO_N], dn[DN_HALO_N + 1]; seq and count[] above are then unused.  tile_flags: per tile, bit 0 = holds
+    // boundary particles -- only those tiles look at `map` at all
+    const u32 *dn;
+    const u32 *tile_flags;
+    u32 e;
+};
+
+// Fused halo pull (slab ranks with device-side counts): the sweep that CONSUMES a halo quantity fetches it itself.  Its
+// first blocks wait for the neighbours' refresh number e, copy the values of the ghost particles from this rank's mailbox
+// into the sweep's input array and publish `ready`; tiles that touch the halo layers (tile_flags bit 1) wait for `ready`
+// before they stage anything, every other tile -- 98 % of them -- starts at once.  The exchange costs no kernel of its own and
+// the interior tiles hide its latency and the skew between the ranks.  e = 0: this sweep pulls nothing.
+#define PBF_PULL_BLOCKS 32
+struct HaloPull {
+    u32 *dn;                         // DN_STEP, DN_HALO_N + 2 / + 3 = ghosts from z- / z+; DN_OVERFLOW bit 4 = a wait timed out
+    const u32 *tile_flags;           // per tile: bit 1 = holds particles of the ghost or boundary layers
+    const char *data[2];             // this rank's mailbox slot of refresh e: from z- / from z+
+    const unsigned long long *flag[2];
+    const u32 *ghost_sorted;         // sorted slot of every ghost, z- ghosts first
+    float4 *buf;                     // the sweep's input array
+    unsigned long long *ready;       // PBF_PULL_BLOCKS local flags
+    u32 e;
+    int wide;                        // 16-byte records (positions) or 4-byte values into .w (lambda, |omega|)
 };
 
 // A particle count as kernels take it.  Single-domain handles know their count on the host: p is null and n is the value.
@@ -190,13 +214,13 @@ int launch_predict_slab(pbf_sim *s, NRef n_local, const LeaveArgs &la);   // pre
 int launch_keys_only(pbf_sim *s, u32 first, u32 count);
 int launch_reorder_cells(pbf_sim *s);
 int launch_highlight(pbf_sim *s);
-int launch_lambda(pbf_sim *s, const HaloPush *push = nullptr);
-int launch_delta_p(pbf_sim *s, const HaloPush *push = nullptr);
-int launch_delta_p_update(pbf_sim *s);   // sweeps.cu: last iteration, K10 fused into the epilogue
+int launch_lambda(pbf_sim *s, const HaloPush *push = nullptr, const HaloPull *pull = nullptr);
+int launch_delta_p(pbf_sim *s, const HaloPush *push = nullptr, const HaloPull *pull = nullptr);
+int launch_delta_p_update(pbf_sim *s, const HaloPush *push = nullptr, const HaloPull *pull = nullptr);   // sweeps.cu: last iteration, K10 fused into the epilogue
 int launch_update(pbf_sim *s);
 int launch_vorticity(pbf_sim *s);
 int launch_vorticity_a(pbf_sim *s, const HaloPush *push = nullptr);
-int launch_vorticity_b(pbf_sim *s);
+int launch_vorticity_b(pbf_sim *s, const HaloPull *pull = nullptr);
 int launch_density_diag(pbf_sim *s);
 int launch_kinetic_diag(pbf_sim *s);
 int launch_compose_records(pbf_sim *s, float4 *out);

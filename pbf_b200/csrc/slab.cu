@@ -74,7 +74,7 @@ struct pbf_slab_state {
     unsigned long long *peer_flag[2];
     void *ipc_base[2];                  // opened IPC mappings (null for virtual ranks)
     u32 *push_done;                     // last-block counter of k_halo_push / of the fused push
-    u32 *push_tiles;                    // [0] sweep tiles that hold boundary particles, [1..] per-tile "seen" flags
+    u32 *push_tiles;                    // [0] sweep tiles that hold boundary particles, [1..] per-tile flags (k_halo_index)
     u32 max_tiles;
     u32 *push_map;                      // per sorted slot: which boundary particle of which face (HaloPush::map)
     bool pushed;                        // the sweep just launched has pushed refresh number xseq already
@@ -94,6 +94,9 @@ struct pbf_slab_state {
     uint64_t graph_key;
     u32 graph_kernels;
     bool use_graph;
+    bool overlap;                       // halo refreshes inside the sweeps (fused push + fused pull, sweeps.cu); PBF_SLAB_OVERLAP=0:
+                                        // a push and a pull kernel per refresh
+    unsigned long long *pull_ready;     // PBF_PULL_BLOCKS flags of the fused pull (HaloPull::ready)
     bool phases;                        // PBF_SLAB_PHASES=1: direct launches with an event at every phase boundary
     cudaEvent_t ph_ev[8];
     bool ph_valid;
@@ -313,9 +316,13 @@ k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__rest
     if (t == LEAVER) t = 0;        // only after a capacity overflow (a leaver that could not be sent): reported by the host
     push_map[i] = t;
     if (!edge) continue;
+    // per-tile flags of the sweeps: bit 1 = the tile holds particles of the ghost or boundary layers, i.e. its candidates
+    // may be ghosts (it has to wait for the fused pull); bit 0 = it holds boundary particles (it pushes)
+    u32 *tf = &push_tiles[1 + i / tile_size];
+    if ((*tf & 2u) == 0u) atomicOr(tf, 2u);
     if (id >= n_local) { ghost_sorted[id - n_local] = i; continue; }
     if (t == 0) continue;
-    if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
+    if ((atomicOr(tf, 1u) & 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
     if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
     else send_lo[t - 1u] = i;
     }
@@ -1078,7 +1085,7 @@ int refresh_bounds(pbf_sim *s) {
     if (best < 0) return PBF_OK;
     const u32 *h = b->h_ring + (size_t)best * DN_WORDS;
     if (h[DN_OVERFLOW]) {
-        pbf_set_error("slab: capacity exceeded on the device (bit 0: leavers, 1: arrivals, 2: boundary layer, 3: ghosts > capacity): " +
+        pbf_set_error("slab: capacity exceeded on the device (bit 0: leavers, 1: arrivals, 2: boundary layer, 3: ghosts > capacity; bit 4: a halo refresh never arrived): " +
                       std::to_string(h[DN_OVERFLOW]) + "; raise the particle / halo capacity");
         return PBF_ERR_CAPACITY;
     }
@@ -1124,6 +1131,40 @@ void halo_pull_dev(pbf_sim *s, bool wide, u32 e) {
     }
     k_halo_pull_dev<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side[0], side[1], b->ghost_sorted, wide ? s->bufA : s->bufB, wide ? 1 : 0, e);
     s->launches++;
+}
+
+// Parameter blocks of the refreshes that run inside the sweeps (device-side counts): refresh number e of the step
+void fused_push(pbf_sim *s, u32 e, HaloPush *hp) {
+    pbf_slab_state *b = s->slab;
+    const size_t slot = e % MB_SLOTS;
+    memset(hp, 0, sizeof(*hp));
+    for (int k = 0; k < 2; k++) {
+        hp->data[k] = b->peer_data[k] ? b->peer_data[k] + slot * mbox_slot_bytes(b) : nullptr;
+        hp->flag[k] = b->peer_flag[k] ? b->peer_flag[k] + slot : nullptr;
+    }
+    hp->map = b->push_map;
+    hp->done = b->push_done;
+    hp->expect = b->push_tiles;
+    hp->dn = s->dn;
+    hp->tile_flags = b->push_tiles + 1;
+    hp->e = e;
+}
+
+void fused_pull(pbf_sim *s, u32 e, bool wide, float4 *buf, HaloPull *pl) {
+    pbf_slab_state *b = s->slab;
+    const size_t slot = e % MB_SLOTS;
+    memset(pl, 0, sizeof(*pl));
+    for (int k = 0; k < 2; k++) {
+        pl->data[k] = b->mbox + ((size_t)k * MB_SLOTS + slot) * mbox_slot_bytes(b);
+        pl->flag[k] = reinterpret_cast<unsigned long long *>(b->mbox + mbox_flags_offset(b)) + k * MB_SLOTS + slot;
+    }
+    pl->dn = s->dn;
+    pl->tile_flags = b->push_tiles + 1;
+    pl->ghost_sorted = b->ghost_sorted;
+    pl->buf = buf;
+    pl->ready = b->pull_ready;
+    pl->e = e;
+    pl->wide = wide ? 1 : 0;
 }
 
 // A sweep that produces a halo quantity, and the refresh of that quantity (exchange number e of the step): sweep, push,
@@ -1240,6 +1281,64 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
     // meaningless (half its neighbourhood is missing) and is replaced by its owner's position right after; with vorticity
     // on, its sorted velocity -- which the neighbours' vorticity sweeps read -- is then derived again from that position.
     const bool vort = grp[0]->params.vorticity_confinement != 0;
+    if (grp[0]->slab->overlap && grp[0]->fuse_update) {
+        // Refreshes inside the sweeps: the sweep that produces a halo quantity pushes it from its boundary tiles, the sweep that
+        // consumes it pulls it with its first blocks while every tile that does not touch the halo layers is already running
+        // (HaloPush / HaloPull, sweeps.cu).  Only the positions after the LAST delta-p are pulled by a kernel of their own:
+        // the ghosts' sorted velocities are derived from them before the vorticity sweep starts.
+        auto neighbours = [](pbf_sim *s) { return s->slab->has[0] || s->slab->has[1]; };
+        for (int it = 0; it < K; it++) {
+            ++e;
+            for (int r = 0; r < ng; r++) {
+                pbf_sim *s = grp[r];
+                HaloPush hp; HaloPull pl;
+                const bool nb_ = neighbours(s);
+                if (nb_) { fused_push(s, e, &hp); s->slab->exchanges++; }
+                if (nb_ && it > 0) fused_pull(s, e - 1, true, s->bufA, &pl);
+                s->launches += launch_lambda(s, nb_ ? &hp : nullptr, nb_ && it > 0 ? &pl : nullptr);
+            }
+            ++e;
+            const bool last = it == K - 1;
+            for (int r = 0; r < ng; r++) {
+                pbf_sim *s = grp[r];
+                HaloPush hp; HaloPull pl;
+                const bool nb_ = neighbours(s), push_ = nb_ && (!last || vort);     // nobody reads the last positions without vorticity
+                if (push_) { fused_push(s, e, &hp); s->slab->exchanges++; }
+                if (nb_) fused_pull(s, e - 1, false, s->bufB, &pl);
+                s->launches += last ? launch_delta_p_update(s, push_ ? &hp : nullptr, nb_ ? &pl : nullptr)
+                                    : launch_delta_p(s, push_ ? &hp : nullptr, nb_ ? &pl : nullptr);
+            }
+        }
+        mark(4);
+        if (vort) {
+            for (int r = 0; r < ng; r++) {
+                pbf_sim *s = grp[r];
+                pbf_slab_state *b = s->slab;
+                if (!neighbours(s)) continue;
+                if (K > 0) {
+                    halo_pull_dev(s, true, e);
+                    k_ghost_velocity<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, b->ghost_sorted, s->bufA, s->perm, s->pos, s->svel,
+                                                                        sim_params(s).timestep);
+                    s->launches++;
+                }
+            }
+            ++e;
+            for (int r = 0; r < ng; r++) {
+                pbf_sim *s = grp[r];
+                HaloPush hp;
+                const bool nb_ = neighbours(s);
+                if (nb_) { fused_push(s, e, &hp); s->slab->exchanges++; }
+                s->launches += launch_vorticity_a(s, nb_ ? &hp : nullptr);
+            }
+            for (int r = 0; r < ng; r++) {
+                pbf_sim *s = grp[r];
+                HaloPull pl;
+                const bool nb_ = neighbours(s);
+                if (nb_) fused_pull(s, e, false, s->bufB, &pl);
+                s->launches += launch_vorticity_b(s, nb_ ? &pl : nullptr);
+            }
+        }
+    } else {
     for (int it = 0; it < K; it++) {
         sweep_and_refresh(grp, ng, false, ++e, [](pbf_sim *s) { return launch_lambda(s, nullptr); });
         const bool last = it == K - 1 && grp[0]->fuse_update;
@@ -1262,6 +1361,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
     if (grp[0]->params.vorticity_confinement) {
         sweep_and_refresh(grp, ng, false, ++e, [](pbf_sim *s) { return launch_vorticity_a(s, nullptr); });
         for (int r = 0; r < ng; r++) grp[r]->launches += launch_vorticity_b(grp[r]);
+    }
     }
     for (int r = 0; r < ng; r++) {
         k_step_end<<<1, 32, 0, grp[r]->stream>>>(grp[r]->dn);
@@ -1371,6 +1471,7 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     b->max_tiles = (s->cap + plan_tile_size() - 1) / plan_tile_size();
     A((void **)&b->push_tiles, (size_t)(1 + b->max_tiles) * 4);
     A((void **)&b->rec_done, 16);
+    A((void **)&b->pull_ready, PBF_PULL_BLOCKS * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_counters, 16 * 4);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&b->h_ring, (size_t)RING * DN_WORDS * 4);
     for (int k = 0; k < RING && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&b->ring_ev[k], cudaEventDisableTiming);
@@ -1379,10 +1480,13 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
     cudaMemsetAsync(b->mbox, 0, mbox_bytes(b), s->stream);
     cudaMemsetAsync(b->push_done, 0, 16, s->stream);
     cudaMemsetAsync(b->rec_done, 0, 16, s->stream);
+    if (b->pull_ready) cudaMemsetAsync(b->pull_ready, 0, PBF_PULL_BLOCKS * sizeof(unsigned long long), s->stream);
     cudaMemsetAsync(s->dn, 0, DN_WORDS * sizeof(u32), s->stream);
     {
         const char *g = getenv("PBF_SLAB_GRAPH");
         b->use_graph = !(g && g[0] == '0');
+        const char *ov = getenv("PBF_SLAB_OVERLAP");
+        b->overlap = !(ov && ov[0] == '0');
         const char *ph = getenv("PBF_SLAB_PHASES");
         b->phases = ph && ph[0] == '1';
         if (b->phases)
@@ -1433,6 +1537,7 @@ void slab_free(pbf_sim *s) {
     if (b->push_map) cudaFree(b->push_map);
     if (b->push_tiles) cudaFree(b->push_tiles);
     if (b->rec_done) cudaFree(b->rec_done);
+    if (b->pull_ready) cudaFree(b->pull_ready);
     if (b->h_ring) cudaFreeHost(b->h_ring);
     for (int k = 0; k < RING; k++)
         if (b->ring_ev[k]) cudaEventDestroy(b->ring_ev[k]);

@@ -396,7 +396,8 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
 }
 
 // General walk of one particle: its nine merged runs from global memory (aligned pairs, masked edges).
-template <int NSRC, int RAD, class F>
+// CG: candidate loads through L2 only (kernels whose first blocks overwrite ghost slots of the array they sweep)
+template <int NSRC, int RAD, bool CG, class F>
 __device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, const float4 *__restrict__ src0,
                                              const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                              const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
@@ -406,14 +407,14 @@ __device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, con
     int slots_;
     load_runs<TL, RAD>(home[i], i, g, runs3, cells, srun, tid, &slots_, &c.self_in);
     for_each_pair<TL>(srun, tid, slots_, [&](int m, bool v0, bool v1) {
-        const Pair p = ldg_pair(src0 + 2 * (size_t)m);
-        if (NSRC == 2) body(p, ldg_pair(src1 + 2 * (size_t)m), v0, v1);
+        const Pair p = CG ? ldcg_pair(src0 + 2 * (size_t)m) : ldg_pair(src0 + 2 * (size_t)m);
+        if (NSRC == 2) body(p, CG ? ldcg_pair(src1 + 2 * (size_t)m) : ldg_pair(src1 + 2 * (size_t)m), v0, v1);
         else body(p, p, v0, v1);
     });
 }
 
 // both paths; every thread of the block calls this (the tiled path synchronises the block), `live` = has a particle
-template <int NSRC, bool FULL, class F>
+template <int NSRC, bool FULL, bool CG, class F>
 __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                      const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                      const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
@@ -421,11 +422,11 @@ __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned lo
                                      int split = 0) {
     if (split == 2 && (FULL || c.mode == 0)) return;       // the second thread of a particle has no share in the general walk
     if (FULL) {                                            // full-support search: 25 rows of five cells from global memory
-        if (live) general_walk<NSRC, 2>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+        if (live) general_walk<NSRC, 2, CG>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
     } else if (c.mode) {
         tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body, split);
     } else if (live) {
-        general_walk<NSRC, 1>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+        general_walk<NSRC, 1, CG>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
     }
 }
 
@@ -458,9 +459,80 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
     if (tid == 0 && atomicAdd(hp.done, 1u) + 1u == *hp.expect) {
         *hp.done = 0u;
         __threadfence_system();
-        if (hp.count[0]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hp.flag[0]), "l"(hp.seq) : "memory");
-        if (hp.count[1]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hp.flag[1]), "l"(hp.seq) : "memory");
+        // counts on the device (one graph per step): the refresh number comes from the step counter
+        const unsigned long long seq = hp.dn ? 256ull * hp.dn[DN_STEP] + hp.e : hp.seq;
+        const u32 c0 = hp.dn ? hp.dn[DN_HALO_N] : hp.count[0], c1 = hp.dn ? hp.dn[DN_HALO_N + 1] : hp.count[1];
+        if (c0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hp.flag[0]), "l"(seq) : "memory");
+        if (c1) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(hp.flag[1]), "l"(seq) : "memory");
     }
+}
+
+// Fused halo pull (HaloPull, pbf_internal.cuh).  halo_tile_begin is called by every thread at the start of every tile of a
+// kernel that runs on a device-side count; it returns the tile's flags (bit 0: holds boundary particles -> push, bit 1:
+// touches the halo layers -> had to wait).
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p, bool sys) {
+    unsigned long long v;
+    if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Wait until *p >= seq.  A neighbour that never delivers (a bug, or a rank that died) must not hang the GPU: after 20 s the
+// wait gives up for good and sets bit 4 of dn[DN_OVERFLOW], which the host reports with the next call.
+__device__ __forceinline__ void halo_spin(const unsigned long long *p, unsigned long long seq, bool sys, u32 *dn, unsigned ns) {
+    unsigned long long t0 = 0;
+    u32 it = 0;
+    while (ld_acquire_u64(p, sys) < seq) {
+        __nanosleep(ns);
+        if ((++it & 255u) == 0u) {
+            if (*reinterpret_cast<volatile u32 *>(dn + DN_OVERFLOW) & 16u) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) { atomicOr(dn + DN_OVERFLOW, 16u); break; }
+        }
+    }
+}
+
+// the first blocks of the grid, before their first tile (they are resident before any block that waits for them)
+__device__ __forceinline__ void halo_pull_run(const HaloPull &pl, int tid, int nthreads) {
+    if (pl.e == 0u || blockIdx.x >= (unsigned)PBF_PULL_BLOCKS) return;      // uniform
+    const u32 nlo = pl.dn[DN_HALO_N + 2], nhi = pl.dn[DN_HALO_N + 3];
+    const unsigned long long seq = 256ull * pl.dn[DN_STEP] + pl.e;
+    if (tid == 0) {
+        if (nlo) halo_spin(pl.flag[0], seq, true, pl.dn, 64);
+        if (nhi) halo_spin(pl.flag[1], seq, true, pl.dn, 64);
+    }
+    __syncthreads();
+    const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
+    for (u32 k = blockIdx.x * (u32)nthreads + (u32)tid; k < nlo + nhi; k += nblk * (u32)nthreads) {
+        const u32 i = pl.ghost_sorted[k];
+        const char *src = k < nlo ? pl.data[0] : pl.data[1];
+        const u32 j = k < nlo ? k : k - nlo;
+        if (pl.wide) {
+            const uint4 q = __ldcv(reinterpret_cast<const uint4 *>(src) + j);
+            pl.buf[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+        } else {
+            pl.buf[i].w = __ldcv(reinterpret_cast<const float *>(src) + j);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(pl.ready + blockIdx.x), "l"(seq) : "memory");
+}
+
+__device__ __forceinline__ u32 halo_tile_begin(const HaloPull &pl, const HaloPush &hp, u32 tile, int tid) {
+    const u32 *tf = pl.tile_flags ? pl.tile_flags : hp.tile_flags;
+    if (tf == nullptr) return 0u;                            // uniform: no neighbour, or the exchanges run as kernels of their own
+    const u32 f = __ldg(tf + tile);
+    if (pl.e && (f & 2u)) {
+        const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
+        const unsigned long long seq = 256ull * pl.dn[DN_STEP] + pl.e;
+        if ((u32)tid < nblk) halo_spin(pl.ready + tid, seq, false, pl.dn, 32);
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copies below read what generic stores just wrote
+    }
+    return f;
 }
 
 // Every sweep kernel: one tile per block; the loop only turns when the grid was sized for fewer particles than there are
@@ -487,19 +559,21 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
 template <bool DIAG, bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ B, GridInfo g, SimParams P, double *diag,
-         const HaloPush hp) {
+         const HaloPush hp, const HaloPull pl) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
+    if (LOOP) halo_pull_run(pl, tid, TL);
     TILE_LOOP_BEGIN
+    const u32 tflag = LOOP ? halo_tile_begin(pl, hp, tile, tid) : 1u;
     TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 pi = live ? (LOOP ? __ldcg(A + i) : A[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
-    walk<1, FULL>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL, LOOP>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 tt = __fmul2_rn(q.t2, q.t2);                         // (h-l)^2
@@ -523,7 +597,7 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
         if (DIAG) err = fabsf(C);
         else B[i] = out = make_float4(pi.x, pi.y, pi.z, -C / (Ssum + P.epsilon));
     }
-    if (!DIAG) halo_push(hp, i, live, out, false, tid);
+    if (!DIAG && (tflag & 1u)) halo_push(hp, i, live, out, false, tid);
     if (DIAG) {
         __shared__ float red[TL / 32];
 #pragma unroll
@@ -556,15 +630,17 @@ struct UpdateArgs {
 template <int FINAL, bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__ A, GridInfo g, SimParams P, const HaloPush hp,
-          const UpdateArgs up) {
+          const UpdateArgs up, const HaloPull pl) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
+    if (LOOP) halo_pull_run(pl, tid, TL);
     TILE_LOOP_BEGIN
+    const u32 tflag = LOOP ? halo_tile_begin(pl, hp, tile, tid) : 1u;
     TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
-    const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 pi = live ? (LOOP ? __ldcg(B + i) : B[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     u32 id = 0;
     float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
     if (FINAL && live) {                                    // in flight while the sweep runs
@@ -578,7 +654,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     sc4 *= sc4;
     const float nk = -P.tensile_k * sc4;
     const float2 nk2 = make_float2(nk, nk), li2 = make_float2(pi.w, pi.w);
-    walk<1, FULL>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL, LOOP>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         float2 t3 = __fmul2_rn(__fmul2_rn(q.t, q.t), q.t);
         t3 = __fmul2_rn(t3, t3);
@@ -613,7 +689,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
         }
         if (FINAL == 2) up.svel[i] = v;
     }
-    halo_push(hp, i, live, out, true, tid);
+    if (tflag & 1u) halo_push(hp, i, live, out, true, tid);
     TILE_LOOP_END(tc)
 }
 
@@ -633,6 +709,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     float (*part)[TL] = reinterpret_cast<float (*)[TL]>(dsm);   // 3 KB of the image area, once everybody is done walking it
     const int tid = threadIdx.x, ptid = tid & (TL - 1), second = tid >= TL ? 1 : 0;
     TILE_LOOP_BEGIN
+    const u32 tflag = LOOP && hp.tile_flags ? __ldg(hp.tile_flags + tile) : 1u;
     TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, ptid);
     const u32 i = tile * TL + ptid;
     const bool live = i < n;
@@ -640,7 +717,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
     const float2 neg1 = make_float2(-1.0f, -1.0f);
-    walk<2, FULL>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
+    walk<2, FULL, LOOP>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
         const float2 uy = make_float2(u.y.x - vi.y, u.y.y - vi.y);
@@ -675,7 +752,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
         omega[i] = make_float4(ox, oy, oz, 0.0f);
         B[i] = out;
     }
-    halo_push(hp, i, mine, out, false, tid);
+    if (tflag & 1u) halo_push(hp, i, mine, out, false, tid);
     if (LOOP) __syncthreads();                             // part[] is free for the next tile
     TILE_LOOP_END(tc)
 }
@@ -684,17 +761,19 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
 template <bool FULL, bool LOOP>
 __global__ void __launch_bounds__(TL, PBF_TL_CTAS)
 k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ vprime, const float4 *__restrict__ omega,
-              const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P) {
+              const u32 *__restrict__ perm, TILE_ARGS, float4 *__restrict__ vel, GridInfo g, SimParams P, const HaloPull pl) {
     extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ __align__(8) unsigned long long mbar;
     const int tid = threadIdx.x;
+    if (LOOP) halo_pull_run(pl, tid, TL);
     TILE_LOOP_BEGIN
+    if (LOOP) halo_tile_begin(pl, HaloPush{}, tile, tid);
     TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
-    const float4 pi = live ? B[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 pi = live ? (LOOP ? __ldcg(B + i) : B[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
-    walk<1, FULL>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL, LOOP>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 cc = __fmul2_rn(c.w, __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il));   // |omega_j| * grad factor
         ex = __ffma2_rn(cc, q.dx, ex);
@@ -757,6 +836,7 @@ int launch_plan(pbf_sim *s) {
 }
 
 static const HaloPush NO_PUSH = {};
+static const HaloPull NO_PULL = {};
 // kernel<..., FULL, LOOP>: FULL = 5 x 5 x 5 search, LOOP = the count lives on the device (slab rank)
 #define SWEEP_LAUNCH_T(K, threads, smem, ...)                                                                     \
     do {                                                                                                          \
@@ -775,27 +855,29 @@ static const HaloPush NO_PUSH = {};
 #define KL_VA(F, L) k_vorticity_a<F, L>
 #define KL_VB(F, L) k_vorticity_b<F, L>
 
-int launch_lambda(pbf_sim *s, const HaloPush *push) {
+// push: the sweep stores its boundary particles' results into the neighbours' mailboxes; pull: its first blocks fetch the
+// ghost particles' inputs from this rank's mailbox (slab ranks only, slab.cu)
+int launch_lambda(pbf_sim *s, const HaloPush *push, const HaloPull *pull) {
     SWEEP_LAUNCH(KL_LAMBDA, TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
-                 sim_params(s), nullptr, push ? *push : NO_PUSH);
+                 sim_params(s), nullptr, push ? *push : NO_PUSH, pull ? *pull : NO_PULL);
     return 1;
 }
 
-int launch_delta_p(pbf_sim *s, const HaloPush *push) {
+int launch_delta_p(pbf_sim *s, const HaloPush *push, const HaloPull *pull) {
     SWEEP_LAUNCH(KL_DP0, TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
-                 sim_params(s), push ? *push : NO_PUSH, UpdateArgs{});
+                 sim_params(s), push ? *push : NO_PUSH, UpdateArgs{}, pull ? *pull : NO_PULL);
     return 1;
 }
 
 // the last solver iteration of a step: delta-p with update.glsl in its epilogue (replaces launch_delta_p + launch_update)
-int launch_delta_p_update(pbf_sim *s) {
+int launch_delta_p_update(pbf_sim *s, const HaloPush *push, const HaloPull *pull) {
     const UpdateArgs up = {s->perm, s->pos, s->vel, s->svel, s->n_dev ? s->dn + DN_LOCAL : nullptr};
     if (s->params.vorticity_confinement)
         SWEEP_LAUNCH(KL_DP2, TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
-                     sim_params(s), NO_PUSH, up);
+                     sim_params(s), push ? *push : NO_PUSH, up, pull ? *pull : NO_PULL);
     else
         SWEEP_LAUNCH(KL_DP1, TL_SMEM1, nref_total(s), s->bufB, TILE_PASS, s->bufA, s->grid,
-                     sim_params(s), NO_PUSH, up);
+                     sim_params(s), push ? *push : NO_PUSH, up, pull ? *pull : NO_PULL);
     return 1;
 }
 
@@ -805,9 +887,9 @@ int launch_vorticity_a(pbf_sim *s, const HaloPush *push) {
     return 1;
 }
 
-int launch_vorticity_b(pbf_sim *s) {
+int launch_vorticity_b(pbf_sim *s, const HaloPull *pull) {
     SWEEP_LAUNCH(KL_VB, TL_SMEM1, nref_total(s), s->bufB, s->vprime, s->omega, s->perm, TILE_PASS,
-                 s->vel, s->grid, sim_params(s));
+                 s->vel, s->grid, sim_params(s), pull ? *pull : NO_PULL);
     return 1;
 }
 
@@ -815,6 +897,6 @@ int launch_vorticity(pbf_sim *s) { return launch_vorticity_a(s, nullptr) + launc
 
 int launch_density_diag(pbf_sim *s) {
     SWEEP_LAUNCH(KL_DIAG, TL_SMEM1, nref_total(s), s->bufA, TILE_PASS, s->bufB, s->grid,
-                 sim_params(s), s->diag, NO_PUSH);
+                 sim_params(s), s->diag, NO_PUSH, NO_PULL);
     return 1;
 }

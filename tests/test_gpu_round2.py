@@ -325,16 +325,18 @@ def test_cuda_against_reference_shaders_live(built_lib):
             sph.upload(rp, rv)                    # continue from identical states: the comparison stays a one-step one
 
 
-@pytest.mark.parametrize("mode", ["graph", "direct", "starved", "readback"])
+@pytest.mark.parametrize("mode", ["graph", "direct", "starved", "kernels", "kernels-starved", "readback"])
 def test_virtual_slabs_device_side_counts(built_lib, mode, monkeypatch):
-    """The slab step without host round trips (device-side counts, records through the neighbour's inbox, one CUDA graph
-    per step) against the single-domain run, on the splash scene (whole layers change owner): as a replayed graph, as
-    direct launches, with grid bounds a third of the particle count (every kernel loops over its device-side count), and
-    the older step that reads its counts back twice per step."""
+    """The slab step without host round trips (device-side counts, records through the neighbour's inbox, halo refreshes
+    inside the sweeps, one CUDA graph per step) against the single-domain run, on the splash scene (whole layers change
+    owner): as a replayed graph, as direct launches, with grid bounds a third of the particle count (every kernel loops over
+    its device-side count), with a push and a pull kernel per refresh instead of the fused ones, and the older step that
+    reads its counts back twice per step."""
     import scenes
     from pbf_b200 import slab
     monkeypatch.setenv("PBF_SLAB_GRAPH", "0" if mode == "direct" else "1")
-    monkeypatch.setenv("PBF_SLAB_STARVE_BOUNDS", "1" if mode == "starved" else "0")
+    monkeypatch.setenv("PBF_SLAB_STARVE_BOUNDS", "1" if mode.endswith("starved") else "0")
+    monkeypatch.setenv("PBF_SLAB_OVERLAP", "0" if mode.startswith("kernels") else "1")
     monkeypatch.setenv("PBF_SLAB_DEVCOUNT", "0" if mode == "readback" else "1")
     grid = (128, 64, 128)
     pos, vel = scenes.splash()
