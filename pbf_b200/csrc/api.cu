@@ -789,10 +789,11 @@ int pbf_get_tile_stats(pbf_handle s, uint32_t *tiles, uint32_t *tiled, uint32_t 
     uint32_t a = 0, b = 0;
     if (why) memset(why, 0, 8 * sizeof(uint32_t));
     for (size_t t = 0; t < nt; t += stride) {
+        const int mode = tmp[t] & 0xff;          // a slab rank's descriptors carry PBF_TILE_* flags above the mode
         a++;
-        b += tmp[t] != 0;
+        b += mode != 0;
         if (why) {
-            why[tmp[t] != 0 ? 0 : 1]++;
+            why[mode != 0 ? 0 : 1]++;
             // staged records of the tile (desc[1]) per particle of a full tile, in six classes: <= 9, 10, 11, 12, 13, more
             const int per = (tmp[t + 1] + (int)plan_tile_size() - 1) / (int)plan_tile_size();
             why[2 + (per <= 9 ? 0 : (per > 13 ? 5 : per - 9))]++;

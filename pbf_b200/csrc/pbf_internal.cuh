@@ -47,22 +47,23 @@ struct HaloPush {
     const u32 *expect;               // how many blocks (tiles) hold boundary particles at all: the last of them publishes
     u32 count[2];                    // boundary particles per face (a flag is only published for a non-empty face)
     // device-side counts (slab.cu, one graph per step): the sequence number is 256 * dn[DN_STEP] + e and the per-face counts
-    // are dn[DN_HALO_N], dn[DN_HALO_N + 1]; seq and count[] above are then unused.  tile_flags: per tile, bit 0 = holds
-    // boundary particles -- only those tiles look at `map` at all
+    // are dn[DN_HALO_N], dn[DN_HALO_N + 1]; seq and count[] above are then unused, and only the tiles whose descriptor carries
+    // PBF_TILE_PUSH look at `map` at all
     const u32 *dn;
-    const u32 *tile_flags;
     u32 e;
 };
 
 // Fused halo pull (slab ranks with device-side counts): the sweep that CONSUMES a halo quantity fetches it itself.  Its
 // first blocks wait for the neighbours' refresh number e, copy the values of the ghost particles from this rank's mailbox
-// into the sweep's input array and publish `ready`; tiles that touch the halo layers (tile_flags bit 1) wait for `ready`
-// before they stage anything, every other tile -- 98 % of them -- starts at once.  The exchange costs no kernel of its own and
+// into the sweep's input array and publish `ready`; tiles that touch the halo layers (PBF_TILE_WAIT in their descriptor) wait
+// for `ready` before they stage anything, every other tile -- 98 % of them -- starts at once.  The exchange costs no kernel of its own and
 // the interior tiles hide its latency and the skew between the ranks.  e = 0: this sweep pulls nothing.
 #define PBF_PULL_BLOCKS 32
+// flags k_halo_index (slab.cu) ORs into the mode word of a tile descriptor after k_plan wrote it (sweeps.cu, TileCtx::flags)
+#define PBF_TILE_PUSH 0x100u         // the tile holds boundary particles
+#define PBF_TILE_WAIT 0x200u         // the tile holds particles of the ghost or boundary layers: its candidates may be ghosts
 struct HaloPull {
     u32 *dn;                         // DN_STEP, DN_HALO_N + 2 / + 3 = ghosts from z- / z+; DN_OVERFLOW bit 4 = a wait timed out
-    const u32 *tile_flags;           // per tile: bit 1 = holds particles of the ghost or boundary layers
     const char *data[2];             // this rank's mailbox slot of refresh e: from z- / from z+
     const unsigned long long *flag[2];
     const u32 *ghost_sorted;         // sorted slot of every ghost, z- ghosts first
@@ -231,7 +232,8 @@ int launch_toggle_highlight(pbf_sim *s, u32 id);
 int sweeps_init(void);                   // opt-in shared-memory sizes of the sweep kernels (once per device)
 size_t plan_desc_ints(u32 cap);
 size_t plan_run_words(u32 cap);
-u32 plan_tile_size(void);                // particles per tile
+u32 plan_tile_size(void);
+u32 plan_desc_stride(void);      // ints per tile descriptor; the mode word is the first                // particles per tile
 int launch_plan(pbf_sim *s);
 SimParams sim_params(const pbf_sim *s);
 // slab.cu

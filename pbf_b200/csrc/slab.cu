@@ -74,7 +74,7 @@ struct pbf_slab_state {
     unsigned long long *peer_flag[2];
     void *ipc_base[2];                  // opened IPC mappings (null for virtual ranks)
     u32 *push_done;                     // last-block counter of k_halo_push / of the fused push
-    u32 *push_tiles;                    // [0] sweep tiles that hold boundary particles, [1..] per-tile flags (k_halo_index)
+    u32 *push_tiles;                    // [0] sweep tiles that hold boundary particles, [1..] per-tile "seen" flags
     u32 max_tiles;
     u32 *push_map;                      // per sorted slot: which boundary particle of which face (HaloPush::map)
     bool pushed;                        // the sweep just launched has pushed refresh number xseq already
@@ -100,6 +100,12 @@ struct pbf_slab_state {
     bool phases;                        // PBF_SLAB_PHASES=1: direct launches with an event at every phase boundary
     cudaEvent_t ph_ev[8];
     bool ph_valid;
+    // PBF_SLAB_TRACE=1 (with PBF_SLAB_PHASES=1, debugging): an event after every sweep / refresh of the solver and vorticity
+    // phases of rank 0; the intervals of the last step are printed to stderr by pbf_slab_phase_times
+    bool trace;
+    cudaEvent_t tr_ev[96];
+    const char *tr_label[96];
+    int tr_n;
 };
 
 constexpr int MB_SLOTS = 4;   // 2 would do: a rank pushes refresh e+2 only after it received e+1, which its neighbour
@@ -301,7 +307,7 @@ k_unpack_ghosts(u32 count, u32 base, const GhostRec *__restrict__ in, float4 *po
 __global__ void __launch_bounds__(256)
 k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ btag,
              u32 *__restrict__ send_lo, u32 *__restrict__ send_hi, u32 *__restrict__ ghost_sorted, u32 *__restrict__ push_map,
-             u32 *__restrict__ push_tiles, u32 tile_size, GridInfo g) {
+             u32 *__restrict__ push_tiles, u32 tile_size, GridInfo g, int *__restrict__ desc, u32 desc_stride) {
     const u32 n = nref(nr), n_local = nref(nloc);
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const u32 kraw = skey[i];
@@ -316,13 +322,15 @@ k_halo_index(NRef nr, NRef nloc, const u32 *__restrict__ skey, const u32 *__rest
     if (t == LEAVER) t = 0;        // only after a capacity overflow (a leaver that could not be sent): reported by the host
     push_map[i] = t;
     if (!edge) continue;
-    // per-tile flags of the sweeps: bit 1 = the tile holds particles of the ghost or boundary layers, i.e. its candidates
-    // may be ghosts (it has to wait for the fused pull); bit 0 = it holds boundary particles (it pushes)
-    u32 *tf = &push_tiles[1 + i / tile_size];
-    if ((*tf & 2u) == 0u) atomicOr(tf, 2u);
+    // desc (refreshes inside the sweeps): flags in the mode word of the tile's descriptor, which every sweep block loads first
+    // anyway -- PBF_TILE_WAIT: the tile holds particles of the ghost or boundary layers, so its candidates may be ghosts and it
+    // has to wait for the fused pull; PBF_TILE_PUSH: it holds boundary particles and pushes them
+    int *tf = desc ? desc + (size_t)(i / tile_size) * desc_stride : nullptr;
+    if (tf && ((u32)*tf & PBF_TILE_WAIT) == 0u) atomicOr(tf, (int)PBF_TILE_WAIT);
     if (id >= n_local) { ghost_sorted[id - n_local] = i; continue; }
     if (t == 0) continue;
-    if ((atomicOr(tf, 1u) & 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
+    if (tf) { if (((u32)atomicOr(tf, (int)PBF_TILE_PUSH) & PBF_TILE_PUSH) == 0u) atomicAdd(&push_tiles[0], 1u); }
+    else if (atomicExch(&push_tiles[1 + i / tile_size], 1u) == 0u) atomicAdd(&push_tiles[0], 1u);   // first of its tile
     if (t & 0x80000000u) send_hi[(t & 0x7fffffffu) - 1u] = i;
     else send_lo[t - 1u] = i;
     }
@@ -1015,7 +1023,7 @@ int slab_step(pbf_sim **grp, int ng) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(NRef{s->n, nullptr}, NRef{b->n_local, nullptr}, s->skey, s->perm, b->btag, b->send_idx[0],
                                                           b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
-                                                          plan_tile_size(), s->grid);
+                                                          plan_tile_size(), s->grid, nullptr, 0u);
             s->launches++;
         }
         s->launches += launch_highlight(s);
@@ -1133,6 +1141,9 @@ void halo_pull_dev(pbf_sim *s, bool wide, u32 e) {
     s->launches++;
 }
 
+// Refreshes inside the sweeps need the plan's tile descriptors (no full-support search) and update.glsl in the last delta-p
+bool overlap_on(const pbf_sim *s) { return s->slab->overlap && s->fuse_update && !s->options.full_support; }
+
 // Parameter blocks of the refreshes that run inside the sweeps (device-side counts): refresh number e of the step
 void fused_push(pbf_sim *s, u32 e, HaloPush *hp) {
     pbf_slab_state *b = s->slab;
@@ -1146,7 +1157,6 @@ void fused_push(pbf_sim *s, u32 e, HaloPush *hp) {
     hp->done = b->push_done;
     hp->expect = b->push_tiles;
     hp->dn = s->dn;
-    hp->tile_flags = b->push_tiles + 1;
     hp->e = e;
 }
 
@@ -1159,7 +1169,6 @@ void fused_pull(pbf_sim *s, u32 e, bool wide, float4 *buf, HaloPull *pl) {
         pl->flag[k] = reinterpret_cast<unsigned long long *>(b->mbox + mbox_flags_offset(b)) + k * MB_SLOTS + slot;
     }
     pl->dn = s->dn;
-    pl->tile_flags = b->push_tiles + 1;
     pl->ghost_sorted = b->ghost_sorted;
     pl->buf = buf;
     pl->ready = b->pull_ready;
@@ -1172,17 +1181,20 @@ void fused_pull(pbf_sim *s, u32 e, bool wide, float4 *buf, HaloPull *pl) {
 // first and pushing from a second stream under the interior tiles -- 5.09-5.14 ms per step against 5.00-5.06 ms: the
 // tile-selection logic costs every sweep block ~3 % (also on a single GPU: 4.39 -> 4.49 ms), more than the ~30 us per
 // exchange the overlap hides.
-template <class Launch>
-void sweep_and_refresh(pbf_sim **grp, int ng, bool wide, u32 e, Launch launch) {
+template <class Launch, class Mark>
+void sweep_and_refresh(pbf_sim **grp, int ng, bool wide, u32 e, Launch launch, Mark tmark, const char *name) {
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
         pbf_slab_state *b = s->slab;
         b->exchanges++;
         s->launches += launch(s);
+        if (ng == 1) tmark(name);
         if (b->has[0] || b->has[1]) halo_push_dev(s, wide, e, s->stream);
     }
+    tmark(ng == 1 ? "push" : name);
     for (int r = 0; r < ng; r++)            // all pushes are enqueued before any pull (virtual ranks share one stream)
         if (grp[r]->slab->has[0] || grp[r]->slab->has[1]) halo_pull_dev(grp[r], wide, e);
+    tmark("pull");
 }
 
 // One step of every rank of `grp`, enqueued without touching the host-side state the device decides (capturable).
@@ -1191,7 +1203,13 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         pbf_slab_state *b = grp[0]->slab;
         if (b->phases) { cudaEventRecord(b->ph_ev[k], grp[0]->stream); b->ph_valid = true; }
     };
+    auto tmark = [&](const char *label) {
+        pbf_slab_state *b = grp[0]->slab;
+        if (b->phases && b->trace && b->tr_n < 96) { b->tr_label[b->tr_n] = label; cudaEventRecord(b->tr_ev[b->tr_n++], grp[0]->stream); }
+    };
+    grp[0]->slab->tr_n = 0;
     mark(0);
+    tmark("t0");
     // ---- predict, who leaves, leavers into the neighbours' inboxes, compaction ------------------------------------------
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -1204,6 +1222,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         const LeaveArgs la = {b->z_lo, b->z_hi, b->has[0], b->has[1], b->btag, b->list[0], b->list[1], b->counters, b->halo_cap,
                               b->list[2], b->list[3]};
         s->launches += 1 + launch_predict_slab(s, nloc, la);
+        if (ng == 1) tmark("predict");
         k_counts_leave<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
         s->launches += 1;
         for (int side = 0; side < 2; side++)
@@ -1223,6 +1242,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         }
     }
     mark(1);
+    tmark("migrate_out");
     // ---- arrivals, boundary layers, ghosts into the neighbours' inboxes --------------------------------------------------
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -1240,6 +1260,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         k_counts_arrive<<<1, 32, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1]);
         k_counts_boundary<<<1, 32, 0, s->stream>>>(s->dn, b->counters, b->halo_cap, b->has[0], b->has[1]);
         s->launches += 2;
+        if (ng == 1) tmark("arrivals");
         for (int side = 0; side < 2; side++)
             if (b->has[side]) {
                 k_push_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[2 + side], s->pred, s->pos, s->hl, b->peer_inbox[side],
@@ -1248,6 +1269,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
             }
     }
     mark(2);
+    tmark("ghosts_out");
     // ---- ghosts in, sort + cells over local + ghost particles --------------------------------------------------------------
     for (int r = 0; r < ng; r++) {
         pbf_sim *s = grp[r];
@@ -1260,20 +1282,25 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         }
         k_counts_ghosts<<<1, 32, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1]);
         s->launches++;
+        if (ng == 1) tmark("ghosts_in");
         s->launches += launch_sort_hist(s, s->keys, nref_total(s));
         s->launches += launch_sort_scan(s);
         s->launches += launch_sort_passes(s);
+        if (ng == 1) tmark("sort");
         s->launches += launch_reorder_cells(s);
+        if (ng == 1) tmark("cells");
         if (b->has[0] || b->has[1]) {
             cudaMemsetAsync(b->push_tiles, 0, (size_t)(1 + b->max_tiles) * 4, s->stream);
             k_halo_index<<<nb(s->n), 256, 0, s->stream>>>(nref_total(s), NRef{b->bound_local, s->dn + DN_LOCAL}, s->skey, s->perm, b->btag,
                                                           b->send_idx[0], b->send_idx[1], b->ghost_sorted, b->push_map, b->push_tiles,
-                                                          plan_tile_size(), s->grid);
+                                                          plan_tile_size(), s->grid, overlap_on(s) ? s->tile_desc : nullptr, plan_desc_stride());
             s->launches++;
         }
+        if (ng == 1) tmark("halo_index");
         s->launches += launch_highlight(s);
     }
     mark(3);
+    tmark("highlight");
     // ---- solver, update, vorticity ------------------------------------------------------------------------------------------
     const int K = grp[0]->params.num_solver_iterations;
     u32 e = 0;
@@ -1281,7 +1308,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
     // meaningless (half its neighbourhood is missing) and is replaced by its owner's position right after; with vorticity
     // on, its sorted velocity -- which the neighbours' vorticity sweeps read -- is then derived again from that position.
     const bool vort = grp[0]->params.vorticity_confinement != 0;
-    if (grp[0]->slab->overlap && grp[0]->fuse_update) {
+    if (overlap_on(grp[0])) {
         // Refreshes inside the sweeps: the sweep that produces a halo quantity pushes it from its boundary tiles, the sweep that
         // consumes it pulls it with its first blocks while every tile that does not touch the halo layers is already running
         // (HaloPush / HaloPull, sweeps.cu).  Only the positions after the LAST delta-p are pulled by a kernel of their own:
@@ -1297,6 +1324,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
                 if (nb_ && it > 0) fused_pull(s, e - 1, true, s->bufA, &pl);
                 s->launches += launch_lambda(s, nb_ ? &hp : nullptr, nb_ && it > 0 ? &pl : nullptr);
             }
+            tmark("lambda");
             ++e;
             const bool last = it == K - 1;
             for (int r = 0; r < ng; r++) {
@@ -1308,8 +1336,10 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
                 s->launches += last ? launch_delta_p_update(s, push_ ? &hp : nullptr, nb_ ? &pl : nullptr)
                                     : launch_delta_p(s, push_ ? &hp : nullptr, nb_ ? &pl : nullptr);
             }
+            tmark(last ? "delta_p_update" : "delta_p");
         }
         mark(4);
+        tmark("-");
         if (vort) {
             for (int r = 0; r < ng; r++) {
                 pbf_sim *s = grp[r];
@@ -1322,6 +1352,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
                     s->launches++;
                 }
             }
+            tmark("pull+ghost_velocity");
             ++e;
             for (int r = 0; r < ng; r++) {
                 pbf_sim *s = grp[r];
@@ -1330,6 +1361,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
                 if (nb_) { fused_push(s, e, &hp); s->slab->exchanges++; }
                 s->launches += launch_vorticity_a(s, nb_ ? &hp : nullptr);
             }
+            tmark("vorticity_a");
             for (int r = 0; r < ng; r++) {
                 pbf_sim *s = grp[r];
                 HaloPull pl;
@@ -1337,14 +1369,17 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
                 if (nb_) fused_pull(s, e, false, s->bufB, &pl);
                 s->launches += launch_vorticity_b(s, nb_ ? &pl : nullptr);
             }
+            tmark("vorticity_b");
         }
     } else {
     for (int it = 0; it < K; it++) {
-        sweep_and_refresh(grp, ng, false, ++e, [](pbf_sim *s) { return launch_lambda(s, nullptr); });
+        sweep_and_refresh(grp, ng, false, ++e, [](pbf_sim *s) { return launch_lambda(s, nullptr); }, tmark, "lambda");
         const bool last = it == K - 1 && grp[0]->fuse_update;
-        sweep_and_refresh(grp, ng, true, ++e, [last](pbf_sim *s) { return last ? launch_delta_p_update(s) : launch_delta_p(s, nullptr); });
+        sweep_and_refresh(grp, ng, true, ++e, [last](pbf_sim *s) { return last ? launch_delta_p_update(s) : launch_delta_p(s, nullptr); },
+                          tmark, last ? "delta_p_update" : "delta_p");
     }
     mark(4);
+    tmark("-");
     if (K > 0 && grp[0]->fuse_update) {
         for (int r = 0; r < ng; r++) {
             pbf_sim *s = grp[r];
@@ -1359,8 +1394,9 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         for (int r = 0; r < ng; r++) grp[r]->launches += launch_update(grp[r]);
     }
     if (grp[0]->params.vorticity_confinement) {
-        sweep_and_refresh(grp, ng, false, ++e, [](pbf_sim *s) { return launch_vorticity_a(s, nullptr); });
+        sweep_and_refresh(grp, ng, false, ++e, [](pbf_sim *s) { return launch_vorticity_a(s, nullptr); }, tmark, "vorticity_a");
         for (int r = 0; r < ng; r++) grp[r]->launches += launch_vorticity_b(grp[r]);
+        tmark("vorticity_b");
     }
     }
     for (int r = 0; r < ng; r++) {
@@ -1491,6 +1527,10 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
         b->phases = ph && ph[0] == '1';
         if (b->phases)
             for (int k = 0; k < 8; k++) cudaEventCreate(&b->ph_ev[k]);
+        const char *tr = getenv("PBF_SLAB_TRACE");
+        b->trace = b->phases && tr && tr[0] == '1';
+        if (b->trace)
+            for (int k = 0; k < 96; k++) cudaEventCreate(&b->tr_ev[k]);
     }
     cudaStreamSynchronize(s->stream);      // the mailbox flags are zero before any neighbour can see them
     s->slab = b;
@@ -1815,6 +1855,17 @@ int pbf_slab_phase_times(pbf_handle s, float ms[5]) {
     DeviceGuard guard(s->device);
     PBF_CUDA(cudaEventSynchronize(b->ph_ev[5]));
     for (int k = 0; k < 5; k++) PBF_CUDA(cudaEventElapsedTime(&ms[k], b->ph_ev[k], b->ph_ev[k + 1]));
+    if (b->trace && b->tr_n > 1) {
+        std::string line = "PBF_SLAB_TRACE rank " + std::to_string(b->rank) + ":";
+        for (int k = 1; k < b->tr_n; k++) {
+            float t = 0.0f;
+            cudaEventElapsedTime(&t, b->tr_ev[k - 1], b->tr_ev[k]);
+            char buf[64];
+            snprintf(buf, sizeof(buf), " %s=%.3f", b->tr_label[k], t);
+            line += buf;
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+    }
     return PBF_OK;
 }
 

@@ -175,11 +175,74 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
     }
 }
 
+// Fused halo pull (HaloPull, pbf_internal.cuh): halo_pull_run by the first blocks of the grid before their first tile,
+// halo_pull_wait by every tile whose descriptor says that it touches the halo layers.
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p, bool sys) {
+    unsigned long long v;
+    if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Wait until *p >= seq.  A neighbour that never delivers (a bug, or a rank that died) must not hang the GPU: after 20 s the
+// wait gives up for good and sets bit 4 of dn[DN_OVERFLOW], which the host reports with the next call.
+__device__ __forceinline__ void halo_spin(const unsigned long long *p, unsigned long long seq, bool sys, u32 *dn, unsigned ns) {
+    unsigned long long t0 = 0;
+    u32 it = 0;
+    while (ld_acquire_u64(p, sys) < seq) {
+        __nanosleep(ns);
+        if ((++it & 255u) == 0u) {
+            if (*reinterpret_cast<volatile u32 *>(dn + DN_OVERFLOW) & 16u) break;
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 20000000000ull) { atomicOr(dn + DN_OVERFLOW, 16u); break; }
+        }
+    }
+}
+
+// the first blocks of the grid, before their first tile (they are resident before any block that waits for them)
+__device__ __forceinline__ void halo_pull_run(const HaloPull &pl, int tid, int nthreads) {
+    if (pl.e == 0u || blockIdx.x >= (unsigned)PBF_PULL_BLOCKS) return;      // uniform
+    const u32 nlo = pl.dn[DN_HALO_N + 2], nhi = pl.dn[DN_HALO_N + 3];
+    const unsigned long long seq = 256ull * pl.dn[DN_STEP] + pl.e;
+    if (tid == 0) {
+        if (nlo) halo_spin(pl.flag[0], seq, true, pl.dn, 64);
+        if (nhi) halo_spin(pl.flag[1], seq, true, pl.dn, 64);
+    }
+    __syncthreads();
+    const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
+    for (u32 k = blockIdx.x * (u32)nthreads + (u32)tid; k < nlo + nhi; k += nblk * (u32)nthreads) {
+        const u32 i = pl.ghost_sorted[k];
+        const char *src = k < nlo ? pl.data[0] : pl.data[1];
+        const u32 j = k < nlo ? k : k - nlo;
+        if (pl.wide) {
+            const uint4 q = __ldcv(reinterpret_cast<const uint4 *>(src) + j);
+            pl.buf[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
+        } else {
+            pl.buf[i].w = __ldcv(reinterpret_cast<const float *>(src) + j);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(pl.ready + blockIdx.x), "l"(seq) : "memory");
+}
+
+__device__ __forceinline__ void halo_pull_wait(const HaloPull &pl, int tid) {
+    const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
+    const unsigned long long seq = 256ull * pl.dn[DN_STEP] + pl.e;
+    if ((u32)tid < nblk) halo_spin(pl.ready + tid, seq, false, pl.dn, 32);
+    __syncthreads();
+    asm volatile("fence.proxy.async;" ::: "memory");         // the bulk copies that follow read what generic stores just wrote
+}
+
 // ---- tile frame of the sweeps -------------------------------------------------------------------------------------------
 struct TileCtx {
     u32 tile;            // this block's tile (normally blockIdx.x) and the number of tiles of the launch's particle count
     u32 ntiles;
     int mode;            // staging phases of the tiled path (1 for almost every tile), 0 = general path
+    u32 flags;           // slab rank: PBF_TILE_PUSH / PBF_TILE_WAIT >> 8 (bits 8.. of the descriptor's mode word, set by k_halo_index
+                         // after the plan)
     u32 cut;             // first range of every phase, 4 bits each, closed by 9
     bool self_in;        // FOR_EACH_NEIGHBOUR would have met (and skipped) the particle itself
     unsigned img;        // shared-window address of image 0 (image 1 follows at + TL_IMG)
@@ -238,10 +301,11 @@ __device__ __forceinline__ void tile_stage(unsigned char *dsm, unsigned mb, cons
 
 // All threads of the block call this.  Thread 0 initialises the mbarrier and stages the first phase; meanwhile the
 // others fetch their runs (the caller overlaps its own loads before tile_sweep).
-template <int NSRC>
+template <int NSRC, bool LOOP>
 __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                               const float4 *__restrict__ src1, const int *__restrict__ desc,
-                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, int ptid = -1) {
+                                              const u32 *__restrict__ runs, int tid, u32 tile, u32 ntiles_, const HaloPull &pl,
+                                              int ptid = -1) {
     // ptid: the thread's particle within the tile when it differs from tid (two threads per particle, k_vorticity_a)
     if (ptid < 0) ptid = tid;
     const int *dg = desc + (size_t)tile * TL_DESC;
@@ -249,6 +313,12 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     c.tile = tile;
     c.ntiles = ntiles_;
     c.mode = __ldg(dg + D_MODE);
+    c.flags = 0u;
+    if (LOOP) {                      // only a slab rank's descriptors carry flags (and only its kernels are LOOP kernels)
+        c.flags = (u32)c.mode >> 8;
+        c.mode &= 0xff;
+        if (pl.e && (c.flags & 2u)) halo_pull_wait(pl, tid);     // block-uniform
+    }
     c.cut = (u32)__ldg(dg + D_CUT);
     c.img = (unsigned)__cvta_generic_to_shared(dsm);
     const u32 *rp = runs + (size_t)tile * RUN_WORDS * TL + ptid;
@@ -433,7 +503,7 @@ __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned lo
 // tile frame of a FULL kernel: no plan, no image
 __device__ __forceinline__ TileCtx tile_none(u32 tile, u32 ntiles_) {
     TileCtx c;
-    c.tile = tile; c.ntiles = ntiles_; c.mode = 0; c.cut = 0; c.self_in = false; c.img = 0;
+    c.tile = tile; c.ntiles = ntiles_; c.mode = 0; c.flags = 0u; c.cut = 0; c.self_in = false; c.img = 0;
     return c;
 }
 
@@ -467,74 +537,6 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
     }
 }
 
-// Fused halo pull (HaloPull, pbf_internal.cuh).  halo_tile_begin is called by every thread at the start of every tile of a
-// kernel that runs on a device-side count; it returns the tile's flags (bit 0: holds boundary particles -> push, bit 1:
-// touches the halo layers -> had to wait).
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p, bool sys) {
-    unsigned long long v;
-    if (sys) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    else asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Wait until *p >= seq.  A neighbour that never delivers (a bug, or a rank that died) must not hang the GPU: after 20 s the
-// wait gives up for good and sets bit 4 of dn[DN_OVERFLOW], which the host reports with the next call.
-__device__ __forceinline__ void halo_spin(const unsigned long long *p, unsigned long long seq, bool sys, u32 *dn, unsigned ns) {
-    unsigned long long t0 = 0;
-    u32 it = 0;
-    while (ld_acquire_u64(p, sys) < seq) {
-        __nanosleep(ns);
-        if ((++it & 255u) == 0u) {
-            if (*reinterpret_cast<volatile u32 *>(dn + DN_OVERFLOW) & 16u) break;
-            unsigned long long t;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > 20000000000ull) { atomicOr(dn + DN_OVERFLOW, 16u); break; }
-        }
-    }
-}
-
-// the first blocks of the grid, before their first tile (they are resident before any block that waits for them)
-__device__ __forceinline__ void halo_pull_run(const HaloPull &pl, int tid, int nthreads) {
-    if (pl.e == 0u || blockIdx.x >= (unsigned)PBF_PULL_BLOCKS) return;      // uniform
-    const u32 nlo = pl.dn[DN_HALO_N + 2], nhi = pl.dn[DN_HALO_N + 3];
-    const unsigned long long seq = 256ull * pl.dn[DN_STEP] + pl.e;
-    if (tid == 0) {
-        if (nlo) halo_spin(pl.flag[0], seq, true, pl.dn, 64);
-        if (nhi) halo_spin(pl.flag[1], seq, true, pl.dn, 64);
-    }
-    __syncthreads();
-    const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
-    for (u32 k = blockIdx.x * (u32)nthreads + (u32)tid; k < nlo + nhi; k += nblk * (u32)nthreads) {
-        const u32 i = pl.ghost_sorted[k];
-        const char *src = k < nlo ? pl.data[0] : pl.data[1];
-        const u32 j = k < nlo ? k : k - nlo;
-        if (pl.wide) {
-            const uint4 q = __ldcv(reinterpret_cast<const uint4 *>(src) + j);
-            pl.buf[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
-        } else {
-            pl.buf[i].w = __ldcv(reinterpret_cast<const float *>(src) + j);
-        }
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(pl.ready + blockIdx.x), "l"(seq) : "memory");
-}
-
-__device__ __forceinline__ u32 halo_tile_begin(const HaloPull &pl, const HaloPush &hp, u32 tile, int tid) {
-    const u32 *tf = pl.tile_flags ? pl.tile_flags : hp.tile_flags;
-    if (tf == nullptr) return 0u;                            // uniform: no neighbour, or the exchanges run as kernels of their own
-    const u32 f = __ldg(tf + tile);
-    if (pl.e && (f & 2u)) {
-        const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
-        const unsigned long long seq = 256ull * pl.dn[DN_STEP] + pl.e;
-        if ((u32)tid < nblk) halo_spin(pl.ready + tid, seq, false, pl.dn, 32);
-        __syncthreads();
-        asm volatile("fence.proxy.async;" ::: "memory");     // the bulk copies below read what generic stores just wrote
-    }
-    return f;
-}
-
 // Every sweep kernel: one tile per block; the loop only turns when the grid was sized for fewer particles than there are
 // (NRef: a slab rank's count lives on the device).  Before a block reuses its image and its mbarrier for another tile
 // everybody must be done with them and the barrier object must be invalidated.
@@ -565,8 +567,8 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
     const int tid = threadIdx.x;
     if (LOOP) halo_pull_run(pl, tid, TL);
     TILE_LOOP_BEGIN
-    const u32 tflag = LOOP ? halo_tile_begin(pl, hp, tile, tid) : 1u;
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1, LOOP>(dsm, &mbar, A, A, desc, runs, tid, tile, ntl, pl);
+    const u32 tflag = LOOP ? tc.flags : 1u;
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     float err = 0.0f;
@@ -636,8 +638,8 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     const int tid = threadIdx.x;
     if (LOOP) halo_pull_run(pl, tid, TL);
     TILE_LOOP_BEGIN
-    const u32 tflag = LOOP ? halo_tile_begin(pl, hp, tile, tid) : 1u;
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1, LOOP>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, pl);
+    const u32 tflag = LOOP ? tc.flags : 1u;
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? (LOOP ? __ldcg(B + i) : B[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -709,8 +711,8 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     float (*part)[TL] = reinterpret_cast<float (*)[TL]>(dsm);   // 3 KB of the image area, once everybody is done walking it
     const int tid = threadIdx.x, ptid = tid & (TL - 1), second = tid >= TL ? 1 : 0;
     TILE_LOOP_BEGIN
-    const u32 tflag = LOOP && hp.tile_flags ? __ldg(hp.tile_flags + tile) : 1u;
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, ptid);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<2, LOOP>(dsm, &mbar, A, svel, desc, runs, tid, tile, ntl, HaloPull{}, ptid);
+    const u32 tflag = LOOP ? tc.flags : 1u;
     const u32 i = tile * TL + ptid;
     const bool live = i < n;
     const float4 pi = live ? A[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -767,8 +769,7 @@ k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ 
     const int tid = threadIdx.x;
     if (LOOP) halo_pull_run(pl, tid, TL);
     TILE_LOOP_BEGIN
-    if (LOOP) halo_tile_begin(pl, HaloPush{}, tile, tid);
-    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl);
+    TileCtx tc = FULL ? tile_none(tile, ntl) : tile_begin<1, LOOP>(dsm, &mbar, B, B, desc, runs, tid, tile, ntl, pl);
     const u32 i = tile * TL + tid;
     const bool live = i < n;
     const float4 pi = live ? (LOOP ? __ldcg(B + i) : B[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -800,6 +801,7 @@ inline int ntiles(u32 n) { return (int)((n + TL - 1) / TL); }
 #define TILE_PASS s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs
 
 u32 plan_tile_size(void) { return (u32)TL; }
+u32 plan_desc_stride(void) { return (u32)TL_DESC; }
 size_t plan_desc_ints(u32 cap) { return (size_t)ntiles(cap) * TL_DESC; }
 size_t plan_run_words(u32 cap) { return (size_t)ntiles(cap) * RUN_WORDS * TL; }
 
