@@ -118,7 +118,20 @@ int pbf_sort_bits(const int32_t grid[3]) {   // src/RadixSort.cpp:44, :127
     return 2 * ((numbits + 1) >> 1);
 }
 
-int pbf_sort_passes(const int32_t grid[3]) { return make_sort_plan(pbf_sort_bits(grid)).passes; }
+// Key bits the simulation's own sort has to look at.  The reference sorts on pbf_sort_bits low bits of the hash (an even
+// number, it sorts two bits per pass).  The hash of a clamped cell never exceeds ncell + gx*gz + gx (a cell on the x = gx,
+// y = gy or z = gz plane), so every masked key is below 2^live and the bits from `live` up are zero: leaving them
+// out gives the same stable permutation.  512 x 256 x 514 (a slab rank's window): 28 -> 27 bits = three 9-bit passes, not four.
+static int live_sort_bits(const int32_t grid[3]) {
+    const int bits = pbf_sort_bits(grid);
+    const uint64_t ncell = (uint64_t)grid[0] * (uint64_t)grid[1] * (uint64_t)grid[2];
+    const uint64_t kmax = ncell + (uint64_t)grid[0] * (uint64_t)grid[2] + (uint64_t)grid[0];
+    const uint64_t top = (1ull << bits) - 1;
+    const int live = bitlength(kmax < top ? kmax : top);
+    return live < bits ? live : bits;
+}
+
+int pbf_sort_passes(const int32_t grid[3]) { return make_sort_plan(live_sort_bits(grid)).passes; }
 
 int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     if (!cfg || !out) return fail(PBF_ERR_INVALID, "pbf_create: null argument");
@@ -167,7 +180,7 @@ int pbf_create(const pbf_config *cfg, pbf_handle *out) {
     s->grid.ref_quirks = cfg->ref_quirks;
     s->grid.bx = bx; s->grid.bz = bz;
     s->grid.zoff = 0; s->grid.gz_global = cfg->grid[2];
-    s->plan = make_sort_plan(sortbits);
+    s->plan = make_sort_plan(live_sort_bits(cfg->grid));
     const char *su = getenv("PBF_SEPARATE_UPDATE");
     s->fuse_update = !(su && su[0] == '1');
     const char *gs = getenv("PBF_GENERAL_SWEEPS");

@@ -94,6 +94,7 @@ struct pbf_slab_state {
     uint64_t graph_key;
     u32 graph_kernels;
     bool use_graph;
+    bool ov_push, ov_pull;              // PBF_SLAB_OVERLAP=2 / 3 (experiments): only the push / only the pull inside the sweeps
     bool overlap;                       // halo refreshes inside the sweeps (fused push + fused pull, sweeps.cu); PBF_SLAB_OVERLAP=0:
                                         // a push and a pull kernel per refresh
     unsigned long long *pull_ready;     // PBF_PULL_BLOCKS flags of the fused pull (HaloPull::ready)
@@ -1314,29 +1315,44 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         // (HaloPush / HaloPull, sweeps.cu).  Only the positions after the LAST delta-p are pulled by a kernel of their own:
         // the ghosts' sorted velocities are derived from them before the vorticity sweep starts.
         auto neighbours = [](pbf_sim *s) { return s->slab->has[0] || s->slab->has[1]; };
+        // PBF_SLAB_OVERLAP=2 / 3 (experiments): only the push / only the pull runs inside the sweeps, the other as a kernel
+        const bool fpush = grp[0]->slab->ov_push, fpull = grp[0]->slab->ov_pull;
+        // One sweep of every rank.  kind 0 lambda, 1 delta-p, 2 delta-p + update, 3 vorticity A, 4 vorticity B;  pull_in: it
+        // consumes refresh e_in (wide_in: positions into bufA, else values into bufB.w); push_: it produces refresh e_out
+        auto sweep = [&](int kind, bool pull_in, u32 e_in, bool wide_in, bool push_, u32 e_out, bool pull_kernel_after, const char *name) {
+            for (int r = 0; r < ng; r++) {
+                pbf_sim *s = grp[r];
+                HaloPush hp; HaloPull pl;
+                const bool nb_ = neighbours(s), dopush = nb_ && push_, dopull = nb_ && pull_in && fpull;
+                if (dopush) { fused_push(s, e_out, &hp); s->slab->exchanges++; }
+                if (dopull) fused_pull(s, e_in, wide_in, wide_in ? s->bufA : s->bufB, &pl);
+                const HaloPush *php = dopush && fpush ? &hp : nullptr;
+                const HaloPull *ppl = dopull ? &pl : nullptr;
+                switch (kind) {
+                case 0: s->launches += launch_lambda(s, php, ppl); break;
+                case 1: s->launches += launch_delta_p(s, php, ppl); break;
+                case 2: s->launches += launch_delta_p_update(s, php, ppl); break;
+                case 3: s->launches += launch_vorticity_a(s, php); break;
+                default: s->launches += launch_vorticity_b(s, ppl); break;
+                }
+                if (ng == 1) tmark(name);
+                if (dopush && !fpush) halo_push_dev(s, kind == 1 || kind == 2, e_out, s->stream);
+            }
+            tmark(ng == 1 ? "push" : name);
+            if (push_ && pull_kernel_after) {
+                for (int r = 0; r < ng; r++)
+                    if (neighbours(grp[r])) halo_pull_dev(grp[r], kind == 1 || kind == 2, e_out);
+                tmark("pull");
+            }
+        };
         for (int it = 0; it < K; it++) {
             ++e;
-            for (int r = 0; r < ng; r++) {
-                pbf_sim *s = grp[r];
-                HaloPush hp; HaloPull pl;
-                const bool nb_ = neighbours(s);
-                if (nb_) { fused_push(s, e, &hp); s->slab->exchanges++; }
-                if (nb_ && it > 0) fused_pull(s, e - 1, true, s->bufA, &pl);
-                s->launches += launch_lambda(s, nb_ ? &hp : nullptr, nb_ && it > 0 ? &pl : nullptr);
-            }
-            tmark("lambda");
+            sweep(0, it > 0, e - 1, true, true, e, !fpull, "lambda");
             ++e;
             const bool last = it == K - 1;
-            for (int r = 0; r < ng; r++) {
-                pbf_sim *s = grp[r];
-                HaloPush hp; HaloPull pl;
-                const bool nb_ = neighbours(s), push_ = nb_ && (!last || vort);     // nobody reads the last positions without vorticity
-                if (push_) { fused_push(s, e, &hp); s->slab->exchanges++; }
-                if (nb_) fused_pull(s, e - 1, false, s->bufB, &pl);
-                s->launches += last ? launch_delta_p_update(s, push_ ? &hp : nullptr, nb_ ? &pl : nullptr)
-                                    : launch_delta_p(s, push_ ? &hp : nullptr, nb_ ? &pl : nullptr);
-            }
-            tmark(last ? "delta_p_update" : "delta_p");
+            // the positions of the last iteration are only read by the vorticity sweeps, and pulled by a kernel (below)
+            if (last) sweep(2, true, e - 1, false, vort, e, false, "delta_p_update");
+            else sweep(1, true, e - 1, false, true, e, !fpull, "delta_p");
         }
         mark(4);
         tmark("-");
@@ -1354,22 +1370,8 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
             }
             tmark("pull+ghost_velocity");
             ++e;
-            for (int r = 0; r < ng; r++) {
-                pbf_sim *s = grp[r];
-                HaloPush hp;
-                const bool nb_ = neighbours(s);
-                if (nb_) { fused_push(s, e, &hp); s->slab->exchanges++; }
-                s->launches += launch_vorticity_a(s, nb_ ? &hp : nullptr);
-            }
-            tmark("vorticity_a");
-            for (int r = 0; r < ng; r++) {
-                pbf_sim *s = grp[r];
-                HaloPull pl;
-                const bool nb_ = neighbours(s);
-                if (nb_) fused_pull(s, e, false, s->bufB, &pl);
-                s->launches += launch_vorticity_b(s, nb_ ? &pl : nullptr);
-            }
-            tmark("vorticity_b");
+            sweep(3, false, 0, false, true, e, !fpull, "vorticity_a");
+            sweep(4, true, e, false, false, 0, false, "vorticity_b");
         }
     } else {
     for (int it = 0; it < K; it++) {
@@ -1523,6 +1525,8 @@ int slab_alloc(pbf_sim *s, int rank, int nranks, int z_lo, int z_hi, int gz_glob
         b->use_graph = !(g && g[0] == '0');
         const char *ov = getenv("PBF_SLAB_OVERLAP");
         b->overlap = !(ov && ov[0] == '0');
+        b->ov_push = !(ov && ov[0] == '3');
+        b->ov_pull = !(ov && ov[0] == '2');
         const char *ph = getenv("PBF_SLAB_PHASES");
         b->phases = ph && ph[0] == '1';
         if (b->phases)

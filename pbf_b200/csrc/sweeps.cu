@@ -212,15 +212,28 @@ __device__ __forceinline__ void halo_pull_run(const HaloPull &pl, int tid, int n
     }
     __syncthreads();
     const u32 nblk = min(gridDim.x, (unsigned)PBF_PULL_BLOCKS);
-    for (u32 k = blockIdx.x * (u32)nthreads + (u32)tid; k < nlo + nhi; k += nblk * (u32)nthreads) {
-        const u32 i = pl.ghost_sorted[k];
-        const char *src = k < nlo ? pl.data[0] : pl.data[1];
-        const u32 j = k < nlo ? k : k - nlo;
-        if (pl.wide) {
-            const uint4 q = __ldcv(reinterpret_cast<const uint4 *>(src) + j);
-            pl.buf[i] = make_float4(__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w));
-        } else {
-            pl.buf[i].w = __ldcv(reinterpret_cast<const float *>(src) + j);
+    // four records per thread and trip: the chains (slot index -> mailbox value -> store) are latency bound
+    const u32 stride = nblk * (u32)nthreads, ntot = nlo + nhi;
+    for (u32 k0 = blockIdx.x * (u32)nthreads + (u32)tid; k0 < ntot; k0 += 4u * stride) {
+        u32 idx[4];
+        uint4 q[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const u32 k = k0 + (u32)u * stride;
+            idx[u] = k < ntot ? pl.ghost_sorted[k] : 0u;
+            const char *src = k < nlo ? pl.data[0] : pl.data[1];
+            const u32 j = k < nlo ? k : k - nlo;
+            q[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (k < ntot) {
+                if (pl.wide) q[u] = __ldcv(reinterpret_cast<const uint4 *>(src) + j);
+                else q[u].w = __ldcv(reinterpret_cast<const u32 *>(src) + j);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (k0 + (u32)u * stride >= ntot) continue;
+            if (pl.wide) pl.buf[idx[u]] = make_float4(__uint_as_float(q[u].x), __uint_as_float(q[u].y), __uint_as_float(q[u].z), __uint_as_float(q[u].w));
+            else pl.buf[idx[u]].w = __uint_as_float(q[u].w);
         }
     }
     __threadfence();
@@ -523,9 +536,10 @@ __device__ __forceinline__ void halo_push(const HaloPush &hp, u32 i, bool live, 
         }
     }
     // Only tiles with boundary particles (about 2 % of them) pay for the system-scope fence and the counter; their number
-    // is known from the halo index of this step.
-    if (wrote) __threadfence_system();
+    // is known from the halo index of this step.  ONE fence per tile: the block barrier orders every thread's stores before
+    // thread 0's fence, and fences are cumulative (with a fence per storing thread a sweep took 4 us longer).
     if (!__syncthreads_or(wrote)) return;
+    if (tid == 0) __threadfence_system();
     if (tid == 0 && atomicAdd(hp.done, 1u) + 1u == *hp.expect) {
         *hp.done = 0u;
         __threadfence_system();
