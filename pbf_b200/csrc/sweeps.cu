@@ -50,7 +50,7 @@ constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B
                                      // TL 128 / 1920 / 7 4.83 ms, TL 64 / 832 / 16 4.78 ms
 constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
 constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
-constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20;
+constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20, D_AT = 21;   // D_AT: image offset of every range (one-image tiles)
 constexpr int RUN_WORDS = 5;     // packed runs of one particle: nine 16-bit fields {image index:11 | count:5}; then
                                  // bit 16 of word 4: the particle meets itself in one of its runs
 static_assert(PBF_TL_CAP + 4 <= 2048, "run fields hold an 11-bit image index");
@@ -66,7 +66,7 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
        int *__restrict__ desc, u32 *__restrict__ runs, GridInfo g, int allow) {
     constexpr int NW = TL / 32;
     __shared__ int wS[NW][9], wE[NW][9];          // per warp: first / one-past-last sorted slot its runs of row o touch
-    __shared__ int sS[9], sN[9], sBase[9];         // per tile: range start, length, (image offset of the range) - start
+    __shared__ int sS[9], sN[9], sBase[9], sAt[9];  // per tile: range start, length, (image offset of the range) - start, image offset
     __shared__ int sMeta[4];                       // phases, records, cuts, "every range fits one image"
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 n = LOOP ? nref(nr) : nr.n;
@@ -104,6 +104,7 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
                 const int no = sN[o];
                 if (fill + no > TL_CAP) { if (nph < 7) cut |= (u32)o << (4 * nph); nph++; fill = 0; }
                 sBase[o] = fill - sS[o];
+                sAt[o] = fill;
                 ok = ok && no <= TL_CAP;
                 fill += no;
                 total += no;
@@ -170,7 +171,7 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
     fits = __syncthreads_and(fits) && sMeta[3] && nph <= TL_PHASES && allow;
     int *d = desc + (size_t)tile * TL_DESC;
     if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = sMeta[1]; d[D_CUT] = sMeta[2]; }
-    if (tid < 9) { d[D_S + tid] = sS[tid]; d[D_N + tid] = sN[tid]; }
+    if (tid < 9) { d[D_S + tid] = sS[tid]; d[D_N + tid] = sN[tid]; d[D_AT + tid] = sAt[tid]; }
     if (LOOP) __syncthreads();                     // the shared tables are free for the next tile
     }
 }
@@ -325,6 +326,13 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     TileCtx c;
     c.tile = tile;
     c.ntiles = ntiles_;
+    // The nine range lengths and starts of the one-image path are fetched TOGETHER with the mode word, not after it is known:
+    // the descriptor spans three 32-byte sectors, and a second dependent round trip to L2 would sit on the critical path of
+    // every tile (descriptor -> bulk copies -> image), during which the whole block idles.
+    const int no_spec = tid < 9 ? __ldg(dg + D_N + tid) : 0;
+    const int so_spec = tid < 9 ? __ldg(dg + D_S + tid) : 0;
+    const int at_spec = tid < 9 ? __ldg(dg + D_AT + tid) : 0;      // image offsets laid out by k_plan: no scan here
+    const int total_spec = tid == 0 ? __ldg(dg + D_TOTAL) : 0;
     c.mode = __ldg(dg + D_MODE);
     c.flags = 0u;
     if (LOOP) {                      // only a slab rank's descriptors carry flags (and only its kernels are LOOP kernels)
@@ -354,7 +362,8 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
             const int o = tid - PF0;
             if (o < 9) {
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
-                if (__ldg(fd + D_MODE) && no > 0) {
+                const int at = __ldg(fd + D_AT + o);                 // only to have the descriptor's last sector in L2 as well
+                if (__ldg(fd + D_MODE) && (no > 0) && at >= 0) {
                     bulk_prefetch_l2(src0 + so, 16u * (unsigned)no);
                     if (NSRC == 2) bulk_prefetch_l2(src1 + so, 16u * (unsigned)no);
                 }
@@ -365,26 +374,19 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     }
 #endif
     if (c.mode == 1 && tid < 32) {
-        // One image (all but a few per cent of the tiles): lanes 0..8 of warp 0 issue one bulk copy each -- nine range
-        // lengths in one coalesced load, their image offsets by a warp scan -- instead of one thread issuing nine in a row
+        // One image (all but a few per cent of the tiles): lanes 0..8 of warp 0 issue one bulk copy each -- range start,
+        // length and image offset come straight from the descriptor -- instead of one thread issuing nine in a row
         // (~300 instructions on the block's critical path).
         const unsigned mb = (unsigned)__cvta_generic_to_shared(mbar);
-        const int no = tid < 9 ? __ldg(dg + D_N + tid) : 0;
-        const int so = tid < 9 ? __ldg(dg + D_S + tid) : 0;
+        const int no = no_spec, so = so_spec;
         if (tid == 0) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        int incl = no;
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (tid >= d) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 8);
         float4 *sm0 = reinterpret_cast<float4 *>(dsm);
         float4 *sm1 = sm0 + (TL_CAP + TL_PAD);
         if (tid == 0) {
+            const int total = total_spec;
 #pragma unroll
             for (int k = 0; k < TL_PAD; k++) {              // see tile_stage
                 sm0[total + k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -394,7 +396,7 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
         }
         __syncwarp();
         if (no > 0) {
-            const int at = incl - no;
+            const int at = at_spec;
             bulk_g2s((unsigned)__cvta_generic_to_shared(sm0) + 16u * at, src0 + so, 16u * no, mb);
             if (NSRC == 2) bulk_g2s((unsigned)__cvta_generic_to_shared(sm1) + 16u * at, src1 + so, 16u * no, mb);
         }
