@@ -113,6 +113,12 @@ typedef struct {
 } pbf_options;
 int pbf_set_options(pbf_handle h, const pbf_options *o);
 int pbf_get_options(pbf_handle h, pbf_options *o);
+/* Verification mode, off by default: one order of every floating-point sum on every code path (runs walked in row order,
+ * pairs counted from a run's first candidate, the particles of a cell in ascending global id order on a slab rank), so that a
+ * slab decomposition (pbf_slab_*, peer-memory transport) reproduces the single-domain run BIT FOR BIT when both sides
+ * switch it on -- the reference's "stable sort from id order" carried across GPU counts.  Results stay within
+ * the parity tolerances of the default mode; a few per cent slower on disordered scenes. */
+int pbf_set_canonical_order(pbf_handle h, int on);
 
 /* Simulation::ResetParticleBuffer's upload (src/Simulation.cpp:249-272): HOST arrays of N float4 by id.
  * vel may be NULL (zero), highlight is cleared.  pbf_download_state copies back (any pointer may be NULL). */

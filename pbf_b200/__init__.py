@@ -73,6 +73,7 @@ def lib():
         L.pbf_step.argtypes = [C.c_void_p, C.c_int]
         L.pbf_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.pbf_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        L.pbf_set_canonical_order.argtypes = [C.c_void_p, C.c_int]
         L.pbf_get_options.argtypes = [C.c_void_p, C.POINTER(Options)]
         L.pbf_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
         L.pbf_get_params.argtypes = [C.c_void_p, C.POINTER(Params)]
@@ -251,6 +252,10 @@ class SPH:
         if full_support is not None:
             o.full_support = int(bool(full_support))
         _check(lib().pbf_set_options(self._h, C.byref(o)))
+
+    def set_canonical_order(self, on=True):
+        """Verification mode: one summation order on every code path, so that slab runs equal the single-domain run bit for bit."""
+        _check(lib().pbf_set_canonical_order(self._h, int(bool(on))))
 
     def get_options(self):
         o = Options()

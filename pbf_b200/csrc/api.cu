@@ -300,6 +300,21 @@ int pbf_set_options(pbf_handle s, const pbf_options *o) {
     return PBF_OK;
 }
 
+// Verification mode: one order of every floating-point sum on every code path, so that a slab decomposition reproduces the
+// single-domain run bit for bit (SURVEY.md 8e "bit-exactness across GPU counts"): a particle's nine runs are walked in row
+// order on the tiled and on the general path alike (the plan does not sort them by length), pairs are counted from a run's
+// first candidate, one thread per particle in the first vorticity sweep, and a slab rank orders the particles of every cell
+// by global id after its sort (slab.cu, k_cell_order; needs the device-count step).  Costs a few per cent on a disordered
+// scene; results stay within the parity tolerances of the default mode.
+int pbf_set_canonical_order(pbf_handle s, int on) {
+    if (check_handle(s)) return PBF_ERR_INVALID;
+    if (s->canonical != (on != 0)) {
+        s->canonical = on != 0;
+        invalidate_graph(s);
+    }
+    return PBF_OK;
+}
+
 int pbf_get_options(pbf_handle s, pbf_options *o) {
     if (check_handle(s)) return PBF_ERR_INVALID;
     if (!o) return fail(PBF_ERR_INVALID, "pbf_get_options: null");

@@ -71,9 +71,11 @@ __device__ __forceinline__ int2 merge_row(const int2 *__restrict__ cells, int ba
 // The thread's non-empty runs {start,end} into shared memory.  Returns their number; *slots = number of aligned
 // candidate pairs over all runs; *self_in = whether the particle's own slot lies in one of its runs, i.e. whether
 // FOR_EACH_NEIGHBOUR would have skipped `self`.
+// rel (canonical order, pbf_set_canonical_order): pairs are counted from the run's first candidate, not from even indices
 template <int BLOCK, int RAD = 1>
 __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const GridInfo &g, const int2 *__restrict__ runs3,
-                                         const int2 *__restrict__ cells, int2 *srun, int tid, int *slots, bool *self_in) {
+                                         const int2 *__restrict__ cells, int2 *srun, int tid, int *slots, bool *self_in,
+                                         bool rel = false) {
     int cnt = 0, tot = 0;
     bool self = false;
     if (RAD == 1) {
@@ -86,7 +88,7 @@ __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const Grid
                 const int s = r[o].x, e = r[o].x + r[o].y;
                 srun[cnt * BLOCK + tid] = make_int2(s, e);
                 cnt++;
-                tot += ((e + 1) >> 1) - (s >> 1);
+                tot += rel ? (e - s + 1) >> 1 : ((e + 1) >> 1) - (s >> 1);
             }
         }
     } else {
@@ -102,7 +104,7 @@ __device__ __forceinline__ int load_runs(const u32 home, const u32 i, const Grid
             if (r.y > 0) {
                 srun[cnt * BLOCK + tid] = make_int2(r.x, r.x + r.y);
                 cnt++;
-                tot += ((r.x + r.y + 1) >> 1) - (r.x >> 1);
+                tot += rel ? (r.y + 1) >> 1 : ((r.x + r.y + 1) >> 1) - (r.x >> 1);
             }
         }
     }
@@ -172,21 +174,25 @@ __device__ __forceinline__ PairGeom pair_geom(const float4 &p, const Pair &c, bo
     return q;
 }
 
-// flattened walk over the aligned candidate pairs of all runs; body(pair index m, valid0, valid1)
+// flattened walk over the candidate pairs of all runs; body(index of the pair's first candidate, valid0, valid1).
+// Default: ALIGNED pairs (candidates 2m, 2m+1: one 256-bit load each), members outside the run masked.  rel: pairs counted
+// from the run's first candidate, like the tiled path of sweeps.cu walks its shared-memory image -- the order of a
+// particle's floating-point sums is then the same on both paths (canonical order).
 template <int BLOCK, class F>
-__device__ __forceinline__ void for_each_pair(const int2 *srun, int tid, int slots, F body) {
+__device__ __forceinline__ void for_each_pair(const int2 *srun, int tid, int slots, bool rel, F body) {
     const int2 *sp = srun + tid;
-    int m = 0, mend = 0, s = 0, e = 0;
+    int c = 0, cend = 0, s = 0, e = 0;
 #pragma unroll 1
     for (int k = 0; k < slots; k++) {
-        if (m >= mend) {
+        if (c >= cend) {
             const int2 r = *sp;
             sp += BLOCK;
             s = r.x; e = r.y;
-            m = s >> 1; mend = (e + 1) >> 1;
+            c = rel ? s : s & ~1;
+            cend = e;
         }
-        body(m, 2 * m >= s, 2 * m + 1 < e);
-        m++;
+        body(c, c >= s, c + 1 < e);
+        c += 2;
     }
 }
 

@@ -33,6 +33,7 @@ struct SimParams {
     int extforce;
     int self_term;          // pbf_options: rho_i includes W(0)
     float restitution;      // pbf_options: < 0 off
+    int canonical;          // pbf_set_canonical_order: one order of every floating-point sum on every code path
 };
 
 // Fused halo push of the slab runtime (slab.cu): the sweep that produces a halo quantity (lambda, new position, |omega|)
@@ -140,6 +141,7 @@ struct pbf_sim {
     // plan of the tiled sweeps (sweeps.cu): per 256-particle tile the nine sorted-index ranges that hold all its
     // candidates, per particle its nine neighbour runs relative to the tile's shared-memory image
     int *tile_desc; u32 *tile_runs;
+    bool canonical;                       // pbf_set_canonical_order (verification mode)
     bool fuse_update;                     // update.glsl in the epilogue of the last delta-p sweep (env PBF_SEPARATE_UPDATE=1: own kernel)
     bool tiled_sweeps;                    // false (env PBF_GENERAL_SWEEPS=1, debugging): every tile takes the general path
     // solver state in sorted order

@@ -335,6 +335,7 @@ SimParams sim_params(const pbf_sim *s) {
     P.extforce = s->params.external_force;
     P.self_term = s->options.density_self_term;
     P.restitution = s->options.wall_restitution;
+    P.canonical = s->canonical ? 1 : 0;
     return P;
 }
 

@@ -583,7 +583,8 @@ __global__ void k_counts_boundary(u32 *dn, const u32 *__restrict__ cnt, u32 cap,
 
 __global__ void __launch_bounds__(256)
 k_push_ghosts(const u32 *__restrict__ dn, int side, const u32 *__restrict__ list, const float4 *__restrict__ pred,
-              const float4 *__restrict__ pos, const u32 *__restrict__ hl, char *peer_area0, size_t area_bytes, u32 cap, u32 *done) {
+              const float4 *__restrict__ pos, const u32 *__restrict__ hl, const u32 *__restrict__ gid, char *peer_area0,
+              size_t area_bytes, u32 cap, u32 *done) {
     const u32 step = dn[DN_STEP], count = dn[DN_BND + side];
     char *area = peer_area0 + (size_t)(step & 1u) * area_bytes;
     GhostRec *out = inbox_ghost(area, cap);
@@ -591,7 +592,8 @@ k_push_ghosts(const u32 *__restrict__ dn, int side, const u32 *__restrict__ list
         const u32 s = list[k];
         GhostRec r;
         r.pred = pred[s];
-        r.old = pos[s];
+        r.pred.w = __uint_as_float(gid[s]);              // the receiver files the ghost under its own slot; it keeps the global id
+        r.old = pos[s];                                  // for the canonical order of a cell's particles (k_cell_order)
         r.old.w = __uint_as_float(hl[s] & 1u);           // the selection bit travels with the ghost (see k_pack_ghosts)
         out[k] = r;
     }
@@ -608,7 +610,8 @@ k_push_ghosts(const u32 *__restrict__ dn, int side, const u32 *__restrict__ list
 
 __global__ void __launch_bounds__(256)
 k_pull_ghosts(const u32 *__restrict__ dn, char *my_area_lo0, char *my_area_hi0, size_t area_bytes, u32 cap, u32 part_cap,
-              bool has_lo, bool has_hi, float4 *pos, float4 *vel, float4 *pred, u32 *hl, u32 *keys, u32 *flags, GridInfo g) {
+              bool has_lo, bool has_hi, float4 *pos, float4 *vel, float4 *pred, u32 *hl, u32 *keys, u32 *flags, u32 *gid,
+              GridInfo g) {
     const u32 step = dn[DN_STEP];
     char *alo = my_area_lo0 + (size_t)(step & 1u) * area_bytes, *ahi = my_area_hi0 + (size_t)(step & 1u) * area_bytes;
     if (threadIdx.x == 0) {
@@ -632,9 +635,26 @@ k_pull_ghosts(const u32 *__restrict__ dn, char *my_area_lo0, char *my_area_hi0, 
         vel[s] = make_float4(0.f, 0.f, 0.f, 0.f);
         hl[s] = selected;
         if (selected) flags[0] = 1u;
+        gid[s] = __float_as_uint(prd.w);
         prd.w = __int_as_float((int)s);
         pred[s] = prd;
         keys[s] = window_key(prd.x, prd.y, prd.z, g);
+    }
+}
+
+// Canonical order (pbf_set_canonical_order): the reference orders the particles of a cell by ascending id (a stable sort
+// from id order).  A rank's slots are not in id order -- migrants fill holes, ghosts sit at the end -- so after the sort every
+// cell's members are put in ascending GLOBAL id order: the order a single-domain run has.  One thread per sorted slot: its
+// cell's segment is found by looking left and right (a cell holds a handful of particles), its place by counting smaller ids.
+__global__ void __launch_bounds__(256)
+k_cell_order(NRef nr, const u32 *__restrict__ skey, const u32 *__restrict__ perm, const u32 *__restrict__ gid, u32 *__restrict__ out) {
+    const u32 n = nref(nr);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 k = skey[i], id = perm[i], g = gid[id];
+        u32 lo = i, hi = i + 1, less = 0;
+        while (lo > 0 && skey[lo - 1] == k) { lo--; less += gid[perm[lo]] < g ? 1u : 0u; }
+        while (hi < n && skey[hi] == k) { less += gid[perm[hi]] < g ? 1u : 0u; hi++; }
+        out[lo + less] = id;
     }
 }
 
@@ -1264,7 +1284,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         if (ng == 1) tmark("arrivals");
         for (int side = 0; side < 2; side++)
             if (b->has[side]) {
-                k_push_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[2 + side], s->pred, s->pos, s->hl, b->peer_inbox[side],
+                k_push_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, side, b->list[2 + side], s->pred, s->pos, s->hl, b->gid, b->peer_inbox[side],
                                                                  inbox_area_bytes(b), b->halo_cap, b->rec_done + 2 + side);
                 s->launches++;
             }
@@ -1278,7 +1298,7 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         char *alo = inbox_area(b->mbox, b, 0), *ahi = inbox_area(b->mbox, b, 1);
         if (b->has[0] || b->has[1]) {
             k_pull_ghosts<<<REC_BLOCKS, 256, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1],
-                                                             s->pos, s->vel, s->pred, s->hl, s->keys, s->flags, s->grid);
+                                                             s->pos, s->vel, s->pred, s->hl, s->keys, s->flags, b->gid, s->grid);
             s->launches++;
         }
         k_counts_ghosts<<<1, 32, 0, s->stream>>>(s->dn, alo, ahi, inbox_area_bytes(b), b->halo_cap, s->cap, b->has[0], b->has[1]);
@@ -1287,6 +1307,11 @@ int enqueue_slab_step_dev(pbf_sim **grp, int ng) {
         s->launches += launch_sort_hist(s, s->keys, nref_total(s));
         s->launches += launch_sort_scan(s);
         s->launches += launch_sort_passes(s);
+        if (s->canonical) {                 // cells in ascending global id order (scratch: the sort's ping-pong buffer is free)
+            k_cell_order<<<nb(s->n), 256, 0, s->stream>>>(nref_total(s), s->skey, s->perm, b->gid, s->vtmp[0]);
+            cudaMemcpyAsync(s->perm, s->vtmp[0], (size_t)s->n * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream);
+            s->launches++;
+        }
         if (ng == 1) tmark("sort");
         s->launches += launch_reorder_cells(s);
         if (ng == 1) tmark("cells");
@@ -1425,6 +1450,7 @@ int slab_step_dev(pbf_sim **grp, int ng) {
         key = fnv(key, &grp[r]->n, 4); key = fnv(key, &grp[r]->slab->bound_local, 4);
         key = fnv(key, &grp[r]->slab->z_lo, 4); key = fnv(key, &grp[r]->slab->z_hi, 4);
         key = fnv(key, &grp[r]->params, sizeof(pbf_params)); key = fnv(key, &grp[r]->options, sizeof(pbf_options));
+        key = fnv(key, &grp[r]->canonical, sizeof(bool));
     }
     cudaStream_t st = grp[0]->stream;
     const bool graph = b0->use_graph && !grp[0]->timing && !b0->phases;

@@ -133,7 +133,7 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
     // longest first puts runs of similar length into the same slot (DESIGN.md section 4 has the numbers: -17 % slots on
     // a disordered scene, nothing on a regular lattice).  Only the order of a particle's floating-point sums changes.
     // Tiles staged in phases keep the row order: there a run belongs to the phase of its range.
-    if (nph == 1) {
+    if (nph == 1 && !(allow & 2)) {                   // allow bit 1: canonical order, the runs stay in row order
         // sort key {pair iterations = ceil(count / 2):5 | 8 - row:4 | descriptor:16}: what a slot costs is its number of
         // iterations, and runs that cost the same keep the row order -- on a regular lattice hardly anything moves, so
         // neighbouring lanes keep reading neighbouring records of the same row (no extra bank conflicts), and the order of
@@ -168,7 +168,7 @@ k_plan(NRef nr, const u32 *__restrict__ home, const int2 *__restrict__ runs3, co
     u32 *out = runs + (size_t)tile * RUN_WORDS * TL + tid;
 #pragma unroll
     for (int k = 0; k < RUN_WORDS; k++) out[k * TL] = w[k];
-    fits = __syncthreads_and(fits) && sMeta[3] && nph <= TL_PHASES && allow;
+    fits = __syncthreads_and(fits) && sMeta[3] && nph <= TL_PHASES && (allow & 1);
     int *d = desc + (size_t)tile * TL_DESC;
     if (tid == 0) { d[D_MODE] = fits ? nph : 0; d[D_TOTAL] = sMeta[1]; d[D_CUT] = sMeta[2]; }
     if (tid < 9) { d[D_S + tid] = sS[tid]; d[D_N + tid] = sN[tid]; d[D_AT + tid] = sAt[tid]; }
@@ -442,7 +442,8 @@ __device__ __forceinline__ void walk_run(unsigned a, const unsigned end, F &body
 }
 
 // split (two threads per particle): 0 = this thread walks all nine runs; 1 / 2 = in a one-image tile the even / odd run
-// slots (the runs are sorted by length, so the halves weigh about the same), in a tile staged in phases all / none.
+// slots (the runs are sorted by length, so the halves weigh about the same), in a tile staged in phases all / none; 3 = none
+// (canonical order: the first thread walks everything in row order).
 template <int NSRC, class F>
 __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsigned long long *mbar,
                                            const float4 *__restrict__ src0, const float4 *__restrict__ src1,
@@ -469,7 +470,7 @@ __device__ __forceinline__ void tile_sweep(TileCtx &c, unsigned char *dsm, unsig
         }
         mbar_wait(mb, (unsigned)(ph & 1));
 #pragma unroll 1
-        for (int o = lo; o < (split == 2 ? lo : hi); o++) {   // rare path: rolled, the runs come from a switch
+        for (int o = lo; o < (split >= 2 ? lo : hi); o++) {   // rare path: rolled, the runs come from a switch
             u32 r = 0;
 #pragma unroll
             for (int k = 0; k < 9; k++) r = (o == k) ? c.run[k] : r;
@@ -486,14 +487,23 @@ template <int NSRC, int RAD, bool CG, class F>
 __device__ __forceinline__ void general_walk(TileCtx &c, unsigned char *dsm, const float4 *__restrict__ src0,
                                              const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                              const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
-                                             const GridInfo &g, u32 i, int tid, F body) {
+                                             const GridInfo &g, u32 i, int tid, bool rel, F body) {
     int2 *srun = reinterpret_cast<int2 *>(dsm);            // 9 (25 with full support) x TL run descriptors
     static_assert((size_t)(2 * RAD + 1) * (2 * RAD + 1) * TL * sizeof(int2) <= TL_SMEM1, "run descriptors fit the image area");
     int slots_;
-    load_runs<TL, RAD>(home[i], i, g, runs3, cells, srun, tid, &slots_, &c.self_in);
-    for_each_pair<TL>(srun, tid, slots_, [&](int m, bool v0, bool v1) {
-        const Pair p = CG ? ldcg_pair(src0 + 2 * (size_t)m) : ldg_pair(src0 + 2 * (size_t)m);
-        if (NSRC == 2) body(p, CG ? ldcg_pair(src1 + 2 * (size_t)m) : ldg_pair(src1 + 2 * (size_t)m), v0, v1);
+    load_runs<TL, RAD>(home[i], i, g, runs3, cells, srun, tid, &slots_, &c.self_in, rel);
+    for_each_pair<TL>(srun, tid, slots_, rel, [&](int c0, bool v0, bool v1) {
+        if (rel) {
+            // canonical order: the pair starts at the run's first candidate (any parity): two 16-byte loads, the second only
+            // if it belongs to the run (it may lie past the end of the array)
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const Pair p = make_pair(__ldcg(src0 + c0), v1 ? __ldcg(src0 + c0 + 1) : z4);
+            if (NSRC == 2) body(p, make_pair(__ldcg(src1 + c0), v1 ? __ldcg(src1 + c0 + 1) : z4), v0, v1);
+            else body(p, p, v0, v1);
+            return;
+        }
+        const Pair p = CG ? ldcg_pair(src0 + c0) : ldg_pair(src0 + c0);
+        if (NSRC == 2) body(p, CG ? ldcg_pair(src1 + c0) : ldg_pair(src1 + c0), v0, v1);
         else body(p, p, v0, v1);
     });
 }
@@ -503,15 +513,16 @@ template <int NSRC, bool FULL, bool CG, class F>
 __device__ __forceinline__ void walk(TileCtx &c, unsigned char *dsm, unsigned long long *mbar, const float4 *__restrict__ src0,
                                      const float4 *__restrict__ src1, const u32 *__restrict__ home,
                                      const int2 *__restrict__ runs3, const int2 *__restrict__ cells,
-                                     const int *__restrict__ desc, const GridInfo &g, u32 i, bool live, int tid, F body,
+                                     const int *__restrict__ desc, const GridInfo &g, u32 i, bool live, int tid, bool rel, F body,
                                      int split = 0) {
-    if (split == 2 && (FULL || c.mode == 0)) return;       // the second thread of a particle has no share in the general walk
+    // split >= 2: a particle's second thread (3: it has no share at all, canonical order) -- none in the general walk
+    if (split >= 2 && (FULL || c.mode == 0)) return;
     if (FULL) {                                            // full-support search: 25 rows of five cells from global memory
-        if (live) general_walk<NSRC, 2, CG>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+        if (live) general_walk<NSRC, 2, CG>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, rel, body);
     } else if (c.mode) {
         tile_sweep<NSRC>(c, dsm, mbar, src0, src1, desc, tid, body, split);
     } else if (live) {
-        general_walk<NSRC, 1, CG>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, body);
+        general_walk<NSRC, 1, CG>(c, dsm, src0, src1, home, runs3, cells, g, i, tid, rel, body);
     }
 }
 
@@ -591,7 +602,7 @@ k_lambda(NRef nr, const float4 *__restrict__ A, TILE_ARGS, float4 *__restrict__ 
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 pi = live ? (LOOP ? __ldcg(A + i) : A[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 rho = make_float2(0.f, 0.f), S = rho, gx = rho, gy = rho, gz = rho;
-    walk<1, FULL, LOOP>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL, LOOP>(tc, dsm, &mbar, A, A, home, runs3, cells, desc, g, i, live, tid, P.canonical != 0, [&](const Pair &c, const Pair &, bool v0, bool v1) {
             const PairGeom q = pair_geom(pi, c, v0, v1);
             rho = __ffma2_rn(__fmul2_rn(q.t, q.t), q.t, rho);                 // -sum (h^2-r^2)^3 (q.t is negated)
             const float2 tt = __fmul2_rn(q.t2, q.t2);                         // (h-l)^2
@@ -672,7 +683,7 @@ k_delta_p(NRef nr, const float4 *__restrict__ B, TILE_ARGS, float4 *__restrict__
     sc4 *= sc4;
     const float nk = -P.tensile_k * sc4;
     const float2 nk2 = make_float2(nk, nk), li2 = make_float2(pi.w, pi.w);
-    walk<1, FULL, LOOP>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL, LOOP>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, P.canonical != 0, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         float2 t3 = __fmul2_rn(__fmul2_rn(q.t, q.t), q.t);
         t3 = __fmul2_rn(t3, t3);
@@ -735,7 +746,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
     const float4 vi = live ? svel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 vx = make_float2(0.f, 0.f), vy = vx, vz = vx, wx = vx, wy = vx, wz = vx;
     const float2 neg1 = make_float2(-1.0f, -1.0f);
-    walk<2, FULL, LOOP>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
+    walk<2, FULL, LOOP>(tc, dsm, &mbar, A, svel, home, runs3, cells, desc, g, i, live, tid, P.canonical != 0, [&](const Pair &c, const Pair &u, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 ux = make_float2(u.x.x - vi.x, u.x.y - vi.x);           // v_ij = v_j - v_i
         const float2 uy = make_float2(u.y.x - vi.y, u.y.y - vi.y);
@@ -750,7 +761,7 @@ k_vorticity_a(NRef nr, const float4 *__restrict__ A, const float4 *__restrict__ 
         wx = __ffma2_rn(uy, gz, __ffma2_rn(__fmul2_rn(gy, uz), neg1, wx));
         wy = __ffma2_rn(uz, gx, __ffma2_rn(__fmul2_rn(gz, ux), neg1, wy));
         wz = __ffma2_rn(ux, gy, __ffma2_rn(__fmul2_rn(gx, uy), neg1, wz));
-    }, 1 + second);
+    }, P.canonical ? (second ? 3 : 0) : 1 + second);
     // the second thread hands its share over (zeros where it had none: general path, tiles staged in phases)
     __syncthreads();
     if (second) {
@@ -790,7 +801,7 @@ k_vorticity_b(NRef nr, const float4 *__restrict__ B, const float4 *__restrict__ 
     const bool live = i < n;
     const float4 pi = live ? (LOOP ? __ldcg(B + i) : B[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
     float2 ex = make_float2(0.f, 0.f), ey = ex, ez = ex;
-    walk<1, FULL, LOOP>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, [&](const Pair &c, const Pair &, bool v0, bool v1) {
+    walk<1, FULL, LOOP>(tc, dsm, &mbar, B, B, home, runs3, cells, desc, g, i, live, tid, P.canonical != 0, [&](const Pair &c, const Pair &, bool v0, bool v1) {
         const PairGeom q = pair_geom(pi, c, v0, v1);
         const float2 cc = __fmul2_rn(c.w, __fmul2_rn(__fmul2_rn(q.t2, q.t2), q.il));   // |omega_j| * grad factor
         ex = __ffma2_rn(cc, q.dx, ex);
@@ -846,10 +857,10 @@ int launch_plan(pbf_sim *s) {
     if (full(s)) return 0;
     if (s->n_dev)
         k_plan<true><<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
-                                                         s->tiled_sweeps ? 1 : 0);
+                                                         (s->tiled_sweeps ? 1 : 0) | (s->canonical ? 2 : 0));
     else
         k_plan<false><<<ntiles(s->n), TL, 0, s->stream>>>(nref_total(s), s->home, s->runs3, s->cells, s->tile_desc, s->tile_runs, s->grid,
-                                                          s->tiled_sweeps ? 1 : 0);
+                                                          (s->tiled_sweeps ? 1 : 0) | (s->canonical ? 2 : 0));
     return 1;
 }
 

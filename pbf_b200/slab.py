@@ -222,6 +222,10 @@ class VirtualGroup:
         for s in self.ranks:
             s._set(**kw)
 
+    def set_canonical_order(self, on=True):
+        for s in self.ranks:
+            s.set_canonical_order(on)
+
     def Run(self, nsteps=1):
         self.ranks[0].Run(nsteps)
 

@@ -28,6 +28,8 @@ def main():
     s.SetNumSolverIterations(3)
     s.SetVorticityConfinementEnabled(True)
     s.SetExternalForce(True)            # predictpos.glsl:27 compares against GRID_SIZE.z/2 of the WHOLE domain (80 here)
+    canonical = os.environ.get("PBF_TEST_CANONICAL") == "1"      # one summation order everywhere: results must be BIT exact
+    s.set_canonical_order(canonical)
     s.upload_slab(p, v, g)
     # select the particles of one column either side of the first plane: highlight.glsl's marks must cross it
     sel = np.nonzero((np.abs(pos[:, 2] - planes[1]) < 1.0) & (np.abs(pos[:, 0] - 25.0) < 1.0) & (pos[:, 1] < 3.0))[0]
@@ -51,6 +53,7 @@ def main():
         single.SetNumSolverIterations(3)
         single.SetVorticityConfinementEnabled(True)
         single.SetExternalForce(True)
+        single.set_canonical_order(canonical)
         single.upload(pos, vel)
         for i in sel:
             single.toggle_highlight(int(i))
@@ -65,8 +68,11 @@ def main():
         marked = int(np.count_nonzero(ghl & 2))
         ok = bool(np.all(seen == 1) and dp < 2e-4 and dv < 2e-4 / 0.016 and mig > 0 and gh > 0
                   and np.array_equal(shl & 1, ghl & 1) and sel.size >= 4 and marked > sel.size and hl_bad <= 2)
-        print("MGPU_RESULT ok=%s p2p=%s world=%d dp=%.3g dv=%.3g migrated=%d ghosts=%d selected=%d marked=%d hl_mismatch=%d planes=%s"
-              % (ok, p2p, world, dp, dv, mig, gh, sel.size, marked, hl_bad, planes))
+        if canonical:
+            ok = ok and np.array_equal(spos.view(np.uint32), gpos.view(np.uint32)) and np.array_equal(svel.view(np.uint32), gvel.view(np.uint32)) \
+                and hl_bad == 0
+        print("MGPU_RESULT ok=%s canonical=%s p2p=%s world=%d dp=%.3g dv=%.3g migrated=%d ghosts=%d selected=%d marked=%d hl_mismatch=%d planes=%s"
+              % (ok, canonical, p2p, world, dp, dv, mig, gh, sel.size, marked, hl_bad, planes))
     dist.barrier()
     s.close()
     dist.destroy_process_group()

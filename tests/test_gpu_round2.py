@@ -360,6 +360,68 @@ def test_virtual_slabs_device_side_counts(built_lib, mode, monkeypatch):
     grp.close()
 
 
+def test_canonical_order_is_path_independent(built_lib, monkeypatch):
+    """In canonical order the tiled path (shared-memory images, one or several staging phases) and the general path (runs
+    walked from global memory) add a particle's terms in the same order: the same scene through either gives the same bits."""
+    import scenes
+    grid = (128, 64, 128)
+    pos, vel = scenes.splash()
+    out = []
+    for general in ("0", "1"):
+        monkeypatch.setenv("PBF_GENERAL_SWEEPS", general)          # read when the handle is created
+        sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+        sph.SetNumSolverIterations(3)
+        sph.SetVorticityConfinementEnabled(True)
+        sph.set_canonical_order(True)
+        sph.upload(pos, vel)
+        sph.Run(6)
+        out.append(sph.download())
+        tiles, tiled = sph.tile_stats()
+        assert (tiled == 0) == (general == "1") and tiles > 0
+        sph.close()
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_virtual_slabs_canonical_order_is_bit_exact(built_lib, nranks):
+    """SURVEY.md 8e, "bit-exactness across GPU counts": with pbf_set_canonical_order on both sides a slab decomposition
+    reproduces the single-domain run BIT FOR BIT -- on the splash scene (whole layers change owner, ghosts every step), after
+    eight steps with vorticity.  The canonical mode itself stays within the one-step tolerance of the default mode."""
+    import scenes
+    from pbf_b200 import slab
+    grid = (128, 64, 128)
+    pos, vel = scenes.splash()
+
+    def run_single(canonical, steps):
+        sph = pbf_b200.SPH(pos.shape[0], grid, ref_quirks=False)
+        sph.SetNumSolverIterations(3)
+        sph.SetVorticityConfinementEnabled(True)
+        sph.set_canonical_order(canonical)
+        sph.upload(pos, vel)
+        sph.Run(steps)
+        out = sph.download()
+        sph.close()
+        return out
+
+    cpos, cvel = run_single(True, 8)
+    grp = slab.VirtualGroup(pos, vel, nranks, grid, halo_capacity=8192, slack=2.5)
+    grp.set_params(num_solver_iterations=3, vorticity_confinement=1)
+    grp.set_canonical_order(True)
+    grp.Run(5)
+    grp.Run(3)
+    gpos, gvel = grp.gather()
+    st = [s.stats() for s in grp.ranks]
+    grp.close()
+    assert sum(x["migrated"] for x in st) > 500
+    assert np.array_equal(cpos.view(np.uint32), gpos.view(np.uint32))
+    assert np.array_equal(cvel.view(np.uint32), gvel.view(np.uint32))
+    dpos, dvel = run_single(False, 1)
+    c1pos, c1vel = run_single(True, 1)
+    assert 0 < np.max(np.abs(dpos - c1pos)) < POS_TOL          # another summation order, the same physics
+    assert np.max(np.abs(dvel - c1vel)) < VEL_TOL
+
+
 def test_slab_capacity_overflow_is_reported(built_lib):
     """More leavers than the record capacity: the device flags it, the next call reports PBF_ERR_CAPACITY (no silent loss)."""
     import scenes
