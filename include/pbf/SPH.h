@@ -98,6 +98,8 @@ public:
     void SetDensitySelfTerm(bool on) { pbf_options o; pbf_get_options(handle, &o); o.density_self_term = on ? 1 : 0; pbf_shim::check(pbf_set_options(handle, &o), "SPH::SetDensitySelfTerm"); }
     void SetWallRestitution(float e) { pbf_options o; pbf_get_options(handle, &o); o.wall_restitution = e; pbf_shim::check(pbf_set_options(handle, &o), "SPH::SetWallRestitution"); }
     void SetFullSupportSearch(bool on) { pbf_options o; pbf_get_options(handle, &o); o.full_support = on ? 1 : 0; pbf_shim::check(pbf_set_options(handle, &o), "SPH::SetFullSupportSearch"); }
+    /* verification mode: one summation order on every code path (slab runs then equal the single-domain run bit for bit) */
+    void SetCanonicalOrder(bool on) { pbf_shim::check(pbf_set_canonical_order(handle, on ? 1 : 0), "SPH::SetCanonicalOrder"); }
     /* dump / resume (no counterpart in the reference): by-id buffers, parameters, step counter */
     void SaveState(const std::string &path) const { pbf_shim::check(pbf_save_state(handle, path.c_str()), "SPH::SaveState"); }
     void LoadState(const std::string &path) {
