@@ -37,6 +37,13 @@ def test_host_only_entry_points(built_lib):
     assert pbf_b200.sort_bits((128, 64, 128)) == 20       # 10 two-bit passes (src/RadixSort.cpp:127)
     assert pbf_b200.sort_bits((256, 128, 256)) == 24
     assert pbf_b200.sort_bits((512, 256, 512)) == 26
+    # onesweep passes of up to 9 bits over the key bits that can be set at all: no hash exceeds ncell + gx*gz + gx, so a slab
+    # rank's 514-layer window (28 bits by the reference's even-bits rule, 27 live) sorts in three passes like the 512-layer grid
+    assert pbf_b200.sort_passes((512, 256, 512)) == 3
+    assert pbf_b200.sort_passes((512, 256, 514)) == 3
+    assert pbf_b200.sort_passes((1024, 512, 1024)) == 4      # 30 bits
+    assert pbf_b200.sort_passes((128, 64, 128)) == 3         # 20 bits
+    assert pbf_b200.sort_passes((64, 32, 64)) == 2           # 18 bits (the clamped-cell hash may reach 2^17 + ...: still 18)
     a, av = pbf_b200.dam_break(8, 4, 6, seed=99)
     b, bv = oracle.dam_break(8, 4, 6, seed=99)
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and not av.any()
