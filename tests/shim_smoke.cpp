@@ -1,5 +1,6 @@
 // Drives the C++ shim classes (include/pbf/*.h) the way the reference's main loop drives Simulation, headless, and
-// prints a checksum of the particle state after a few frames (compared with the Python path by tests/test_shim.py).
+// prints a checksum of the particle state after a few frames and writes the state itself to argv[2] (both compared with the
+// Python path by tests/test_shim.py).
 #include <cstdio>
 #include <vector>
 
@@ -26,6 +27,14 @@ int main(int argc, char **argv) {
         for (size_t i = 0; i < pos.size(); i++) { sp += pos[i]; sv += vel[i] * vel[i]; }
         printf("SHIM n=%u frames=%d sum_pos=%.6f sum_v2=%.6f rest_density=%.3f iters=%u\n", n, frames + 1, sp, sv,
                sph.GetRestDensity(), sph.GetNumSolverIterations());
+        if (argc > 2) {                       // the whole state, for a particle-by-particle comparison (tests/test_shim.py)
+            FILE *f = fopen(argv[2], "wb");
+            if (!f || fwrite(pos.data(), sizeof(float), pos.size(), f) != pos.size() ||
+                fwrite(vel.data(), sizeof(float), vel.size(), f) != vel.size() || fclose(f) != 0) {
+                printf("SHIM_ERROR cannot write %s\n", argv[2]);
+                return 3;
+            }
+        }
         try {
             SPH bad(1000);                    // not a multiple of 512: must throw like the reference's constructors do
             printf("SHIM_ERROR no exception\n");

@@ -25,10 +25,11 @@ def test_shim_compiles_and_links(built_lib):
 
 
 @pytest.mark.gpu
-def test_shim_matches_python_binding(built_lib):
+def test_shim_matches_python_binding(built_lib, tmp_path):
     import pbf_b200
     exe = build_exe(built_lib)
-    r = subprocess.run([exe, "3"], capture_output=True, text=True, timeout=300)
+    dump = str(tmp_path / "shim_state.bin")
+    r = subprocess.run([exe, "3", dump], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     line = [l for l in r.stdout.splitlines() if l.startswith("SHIM n=")][0]
     vals = dict(kv.split("=") for kv in line.split()[1:])
@@ -44,3 +45,11 @@ def test_shim_matches_python_binding(built_lib):
     pos, vel = sph.download()
     assert abs(float(vals["sum_pos"]) - pos.astype(np.float64).sum()) < 1e-3 * 65536
     assert abs(float(vals["sum_v2"]) - (vel.astype(np.float64) ** 2).sum()) < 1e-3 * float(vals["sum_v2"])
+    # the state itself, particle by particle: three frames through Simulation::Frame (pbf_step) plus one step through the
+    # RadixSort / NeighbourCellFinder shims (the stage entry points) against four pbf_step calls of the Python binding --
+    # the same kernels on the same inputs, so the same bits
+    raw = np.fromfile(dump, np.float32)
+    assert raw.size == 2 * 4 * 65536
+    spos, svel = raw[:4 * 65536].reshape(-1, 4), raw[4 * 65536:].reshape(-1, 4)
+    assert np.array_equal(spos.view(np.uint32), pos.view(np.uint32))
+    assert np.array_equal(svel.view(np.uint32), vel.view(np.uint32))
