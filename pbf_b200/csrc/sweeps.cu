@@ -48,6 +48,10 @@ constexpr int TL_CAP = PBF_TL_CAP;   // records of one shared-memory image, 16 B
                                      // SM; 2.5 % of the headline scene's tiles need a second phase).  Measured on B200 at 8M
                                      // particles, whole step: TL 256 / cap 3328 / 4 blocks 4.69 ms, TL 128 / 1664 / 8 4.63 ms,
                                      // TL 128 / 1920 / 7 4.83 ms, TL 64 / 832 / 16 4.78 ms
+#ifndef PBF_WALK_UNROLL
+#define PBF_WALK_UNROLL 1
+#endif
+constexpr int WALK_UNROLL = PBF_WALK_UNROLL;   // pair iterations unrolled in walk_run (measured: DESIGN.md section 4)
 constexpr int TL_PHASES = 4;     // a tile whose nine ranges exceed one image stages them in up to four phases
 constexpr int TL_DESC = 32;      // ints per tile descriptor: phases, records, nine range starts, nine range lengths, cuts
 constexpr int D_MODE = 0, D_TOTAL = 1, D_S = 2, D_N = 11, D_CUT = 20, D_AT = 21;   // D_AT: image offset of every range (one-image tiles)
@@ -352,18 +356,27 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     c.self_in = ((w[4] >> 16) & 1u) != 0u;
 #if PBF_PREFETCH_DIST > 0
     // One wave ahead: pull what tile blockIdx.x + DIST will need into L2 -- its descriptor (by loading it), its packed
-    // runs and its nine ranges -- so that its own prologue (descriptor -> bulk copies -> data) runs on L2 hits instead of
-    // two DRAM round trips.  Warp 2 does this while the block waits for its own image anyway.
-    constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the ten prefetching threads
-    if (tid >= PF0 && tid < PF0 + 10) {
+    // runs and the range of its OWN row (dy = dz = 0) -- so that its prologue (descriptor -> bulk copies -> data) runs on L2
+    // hits instead of DRAM round trips.  The other eight ranges are the own-row ranges of tiles in the neighbouring rows, which
+    // lie 2 (z +- 1) and ~512 (y +- 1) tiles away -- less than DIST -- and were prefetched by them: every record is prefetched
+    // once, not nine times (PBF_PREFETCH_ALL: the nine ranges, 10 instead of 2 bulk prefetches per tile).
+    constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the prefetching threads (warp 2: idle until the image lands)
+#ifdef PBF_PREFETCH_ALL
+    constexpr int PFN = 10;
+#else
+    constexpr int PFN = 2;
+#endif
+    if (tid >= PF0 && tid < PF0 + PFN) {
         const u32 ft = tile + (u32)PBF_PREFETCH_DIST;
         if (ft < ntiles_) {
             const int *fd = desc + (size_t)ft * TL_DESC;
-            const int o = tid - PF0;
-            if (o < 9) {
+            const int k = tid - PF0;
+            if (k < PFN - 1) {
+                const int o = PFN == 2 ? 4 : k;
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
-                const int at = __ldg(fd + D_AT + o);                 // only to have the descriptor's last sector in L2 as well
-                if (__ldg(fd + D_MODE) && (no > 0) && at >= 0) {
+                // the descriptor's other sectors (lengths, image offsets): loaded only to have them in L2 as well
+                const int a0 = __ldg(fd + D_N + 8), a1 = __ldg(fd + D_AT + 8);
+                if (__ldg(fd + D_MODE) && (no > 0) && (a0 | a1) >= 0) {
                     bulk_prefetch_l2(src0 + so, 16u * (unsigned)no);
                     if (NSRC == 2) bulk_prefetch_l2(src1 + so, 16u * (unsigned)no);
                 }
@@ -433,7 +446,7 @@ __device__ __forceinline__ void walk_run(unsigned a, const unsigned end, F &body
     // second candidate of a pair valid <=> a + 16 < end; inside the loop end >= a + 16 >= 16, so the comparison against
     // end - 16 (hoisted) is the same and saves an add per iteration
     const unsigned last = end - 16u;
-#pragma unroll 1
+#pragma unroll WALK_UNROLL
     for (; a < end; a += 32u) {
         const Pair p = make_pair(lds128(a), lds128(a + 16u));
         if (NSRC == 2) body(p, make_pair(lds128(a + (unsigned)TL_IMG), lds128(a + (unsigned)TL_IMG + 16u)), true, a < last);
