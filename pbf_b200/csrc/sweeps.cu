@@ -356,15 +356,17 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     c.self_in = ((w[4] >> 16) & 1u) != 0u;
 #if PBF_PREFETCH_DIST > 0
     // One wave ahead: pull what tile blockIdx.x + DIST will need into L2 -- its descriptor (by loading it), its packed
-    // runs and the range of its OWN row (dy = dz = 0) -- so that its prologue (descriptor -> bulk copies -> data) runs on L2
-    // hits instead of DRAM round trips.  The other eight ranges are the own-row ranges of tiles in the neighbouring rows, which
-    // lie 2 (z +- 1) and ~512 (y +- 1) tiles away -- less than DIST -- and were prefetched by them: every record is prefetched
-    // once, not nine times (PBF_PREFETCH_ALL: the nine ranges, 10 instead of 2 bulk prefetches per tile).
+    // runs, the range of its OWN row (dy = dz = 0) and the range of the row above it (dy = +1, dz = 0) -- so that its prologue
+    // (descriptor -> bulk copies -> data) runs on L2 hits instead of DRAM round trips.  The other seven ranges are covered by
+    // the same two prefetches of the tiles around it: rows (y, z +- 1) and (y + 1, z +- 1) by the tiles two further on or
+    // back, which prefetch at almost the same time, and the rows of layer y - 1 were staged one layer of tiles ago and are
+    // still in L2.  Every record is prefetched twice, not nine times (PBF_PREFETCH_ALL: all nine ranges, 10 instead of 3
+    // bulk prefetches per tile).
     constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the prefetching threads (warp 2: idle until the image lands)
 #ifdef PBF_PREFETCH_ALL
     constexpr int PFN = 10;
 #else
-    constexpr int PFN = 2;
+    constexpr int PFN = 3;
 #endif
     if (tid >= PF0 && tid < PF0 + PFN) {
         const u32 ft = tile + (u32)PBF_PREFETCH_DIST;
@@ -372,7 +374,7 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
             const int *fd = desc + (size_t)ft * TL_DESC;
             const int k = tid - PF0;
             if (k < PFN - 1) {
-                const int o = PFN == 2 ? 4 : k;
+                const int o = PFN == 3 ? 4 + 3 * k : k;                // 4 = (dy 0, dz 0), 7 = (dy +1, dz 0)
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
                 // the descriptor's other sectors (lengths, image offsets): loaded only to have them in L2 as well
                 const int a0 = __ldg(fd + D_N + 8), a1 = __ldg(fd + D_AT + 8);
