@@ -363,8 +363,10 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
     // still in L2.  Every record is prefetched twice, not nine times (PBF_PREFETCH_ALL: all nine ranges, 10 instead of 3
     // bulk prefetches per tile).
     constexpr int PF0 = TL >= 128 ? 64 : TL / 2;       // first of the prefetching threads (warp 2: idle until the image lands)
-#ifdef PBF_PREFETCH_ALL
+#if defined(PBF_PREFETCH_ALL)
     constexpr int PFN = 10;
+#elif defined(PBF_PREFETCH_OWN_ROW)                   // own row only: enough while a layer of tiles is shorter than DIST
+    constexpr int PFN = 2;
 #else
     constexpr int PFN = 3;
 #endif
@@ -374,7 +376,7 @@ __device__ __forceinline__ TileCtx tile_begin(unsigned char *dsm, unsigned long 
             const int *fd = desc + (size_t)ft * TL_DESC;
             const int k = tid - PF0;
             if (k < PFN - 1) {
-                const int o = PFN == 3 ? 4 + 3 * k : k;                // 4 = (dy 0, dz 0), 7 = (dy +1, dz 0)
+                const int o = PFN <= 3 ? 4 + 3 * k : k;                // 4 = (dy 0, dz 0), 7 = (dy +1, dz 0)
                 const int so = __ldg(fd + D_S + o), no = __ldg(fd + D_N + o);
                 // the descriptor's other sectors (lengths, image offsets): loaded only to have them in L2 as well
                 const int a0 = __ldg(fd + D_N + 8), a1 = __ldg(fd + D_AT + 8);
