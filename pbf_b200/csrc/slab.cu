@@ -14,12 +14,19 @@
 //           -> sort, cells -> K x [lambda, halo lambda (4 B), delta-p, halo position (16 B)]
 //           -> update -> vorticity A, halo |omega| (4 B), vorticity B.
 // Ghost slots are computed like any other particle and then overwritten by the owner's values, so every kernel of the
-// single-GPU path is reused as is.  Two host synchronisations per step (the migration and ghost counts size the
-// launches); everything else is stream ordered.
+// single-GPU path is reused as is.
 //
-// Transport: NCCL send/recv on the handle's stream (one process per GPU, communicator bootstrapped from a unique id the
-// host runtime broadcasts), or -- for tests on one GPU -- "virtual ranks": several handles of one process stepped in
-// lock step with device-to-device copies in place of NCCL.
+// Two implementations of the step share the kernels:
+//  * device-side counts (default with the peer-memory transport, "slab_step_dev" below): migration and ghost records are
+//    stored straight into the neighbour's inbox over NVLink (CUDA IPC), every count lives in pbf_sim::dn, kernels loop up to
+//    the device value (NRef), the halo refreshes run inside the sweeps (HaloPush / HaloPull, sweeps.cu) and the whole step
+//    replays as ONE CUDA graph -- the host never waits for the device;
+//  * count read-back ("slab_step", the round-1 step, kept as the baseline and for the NCCL transport): two host
+//    synchronisations per step size the transfers and the launches.
+//
+// Transport: peer-memory stores with flags (pbf_slab_p2p_connect), NCCL send/recv on the handle's stream (one process per
+// GPU, communicator bootstrapped from a unique id the host runtime broadcasts), or -- for tests on one GPU -- "virtual
+// ranks": several handles of one process stepped in lock step on one stream, mailboxes reached through plain pointers.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdlib.h>

@@ -10,13 +10,14 @@
 //     as in the reference), per tile the nine ranges [S_o, S_o + n_o) that cover them; the runs are stored relative to
 //     the tile's shared-memory image (11-bit start, 5-bit count: 20 B per particle), longest first: a warp walks run
 //     slot k of all its lanes in lock step and pays for the longest, so runs of similar length share a slot.
-//   * every sweep: one thread issues nine 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier) that
+//   * every sweep: nine lanes issue one 1-D bulk copy each (cp.async.bulk -> UBLKCP, completion on an mbarrier) that
 //     bring the tile's nine ranges into shared memory verbatim -- no per-record instructions, no LSU wavefronts for
 //     staging; meanwhile the other threads fetch their runs.  A thread then walks its nine runs in the image, two
 //     candidates per iteration (two LDS.128, packed f32x2 arithmetic).  Neighbouring lanes read neighbouring records
 //     of the same row, so the loads are free of bank conflicts.
 //   * warp 2 of every block meanwhile pulls what the block one wave later (blockIdx.x + PBF_PREFETCH_DIST) will need --
-//     descriptor, packed runs, nine ranges -- into L2 (cp.async.bulk.prefetch.L2).
+//     descriptor, packed runs, the ranges of its own row and of the row above; the other seven ranges are those two of
+//     its neighbours -- into L2 (cp.async.bulk.prefetch.L2).
 // What bounds the sweeps is instruction issue (FP32 + shared-memory loads + run bookkeeping) at the residency the
 // registers allow (32 warps per SM), not HBM: see DESIGN.md section 4 and profiles/ (with the arithmetic removed a
 // sweep still takes 56 % of its time, with the shared-memory loads removed too 45 %).
