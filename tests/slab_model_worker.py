@@ -43,6 +43,10 @@ def main():
     lp, lv, lg = [a.copy() for a in slab.split_scene(pos, vel, planes, grid[2])[rank]]
     z_lo, z_hi = planes[rank], planes[rank + 1]
     migrated = 0
+    # SLAB_MODEL_CANONICAL=1: the composite (cell key, global id) order of SURVEY.md 8e -- every rank files its local and ghost
+    # particles in ascending global id before the stable sort, as the single-domain run does by construction.  The oracle adds a
+    # particle's terms in candidate order, so the slab run must then equal the single-domain run BIT FOR BIT.
+    canonical = os.environ.get("SLAB_MODEL_CANONICAL") == "1"
     for _ in range(steps):
         n = lp.shape[0]
         rec = oracle.predict(lp, lv, P, g)
@@ -58,13 +62,18 @@ def main():
         n = lp.shape[0]
         cz = slab.cell_layer(rec, grid[2])
         b_lo, b_hi = np.nonzero((cz == z_lo) & (rank > 0))[0], np.nonzero((cz == z_hi - 1) & (rank + 1 < world))[0]
-        g_lo, g_hi = exchange(rank, world, (rec[b_lo], lp[b_lo]), (rec[b_hi], lp[b_hi]))
+        g_lo, g_hi = exchange(rank, world, (rec[b_lo], lp[b_lo], lg[b_lo]), (rec[b_hi], lp[b_hi], lg[b_hi]))
         ghosts = [x for x in (g_lo, g_hi) if x is not None]
         ng = [x[0].shape[0] for x in ghosts]
         rec_all = cat(rec, *[x[0] for x in ghosts]).copy()
         pos_all = cat(lp, *[x[1] for x in ghosts]).copy()
         vel_all = np.zeros_like(pos_all); vel_all[:n] = lv
         rec_all[:, 3] = np.arange(rec_all.shape[0], dtype=np.int32).view(np.float32)
+        if canonical:
+            # feed the sort in global-id order: its stability then orders every cell by id (slots keep naming the rows of
+            # pos_all / vel_all, so nothing else changes)
+            gid_all = cat(lg, *[x[2] for x in ghosts])
+            rec_all = rec_all[np.argsort(gid_all, kind="stable")]
         srt, _ = oracle.sort(rec_all, g)
         start, end = oracle.findcells(srt, g)
         rs, rc = oracle.neighbourcells(srt, g, start, end)
@@ -99,7 +108,9 @@ def main():
         dp, dv = np.max(np.abs(gp - pos)), np.max(np.abs(gv - vel))
         mig = sum(p[3] for p in parts)
         ok = bool(np.all(seen == 1) and dp < 1e-4 and dv < 1e-2 and mig > 0)
-        print("SLAB_MODEL ok=%s dp=%.3g dv=%.3g migrated=%d planes=%s" % (ok, dp, dv, mig, planes))
+        if canonical:
+            ok = ok and np.array_equal(gp.view(np.uint32), pos.view(np.uint32)) and np.array_equal(gv.view(np.uint32), vel.view(np.uint32))
+        print("SLAB_MODEL ok=%s canonical=%s dp=%.3g dv=%.3g migrated=%d planes=%s" % (ok, canonical, dp, dv, mig, planes))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

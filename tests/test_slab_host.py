@@ -43,13 +43,16 @@ def test_weak_scene_partitions_are_disjoint(built_lib):
     assert total == n3[0] * n3[1] * n3[2] * 3
 
 
-def test_slab_model_world2_gloo(built_lib):
+@pytest.mark.parametrize("canonical", [False, True])
+def test_slab_model_world2_gloo(built_lib, canonical):
+    """canonical: particles filed in global-id order before the stable sort (the composite (cell key, id) order of SURVEY.md
+    8e) -- the two-rank model must then equal the single-domain oracle BIT FOR BIT, not just within the tolerance."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29631", os.path.join(ROOT, "tests", "slab_model_worker.py")]
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="2", SLAB_MODEL_CANONICAL="1" if canonical else "0")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "SLAB_MODEL ok=True" in r.stdout
+    assert "SLAB_MODEL ok=True canonical=%s" % canonical in r.stdout
 
 
 def test_rebalance_planes_moves_towards_equal_shares():
