@@ -24,8 +24,12 @@
  *        start; start[(0,0,0)] = 0 is always written); ref_quirks=0 writes start[cell(0)] = 0 instead.
  *        In both modes end[cell(N-1)] = N (the reference leaves it stale: undefined behaviour);
  *  (iv)  out-of-grid texel fetches read "empty" (start = -1);
- *  (v)   the cell hash is evaluated in integers; the reference's float dot (counting.glsl:53-57) is
- *        identical while the hash is < 2^24 and undefined beyond.
+ *  (v)   the cell hash is evaluated in integers.  The reference's sort shaders compute it as uint(dot(ivec3, ivec3))
+ *        (counting.glsl:53-57, globalsort.glsl:50-55), and GLSL's dot is a FLOAT operation: identical while the hash is
+ *        < 2^24, rounded beyond (grids of more than 2^24 cells: the low bits of x are lost for large y, neighbouring
+ *        cells share a sort key and the sort is no longer a sort by cell).  ref_quirks bit 1 (value 2 or 3) reproduces
+ *        that literally -- x*1 + y*(gx*gz) + z*gx in binary32, left to right -- so that the oracle can be pinned to the
+ *        compiled shaders on such grids too (tests/test_oracle_ref.py); the product implements the integer hash.
  */
 #include <math.h>
 #include <stdint.h>
@@ -38,7 +42,7 @@
 typedef struct {
     int gx, gy, gz;        /* GRID_SIZE (src/SPH.h:40 default 128,64,128)                        */
     float wall_x, wall_y, wall_z; /* wall offsets, shaders/sph/updatepos.glsl:98 = (16,0,16)     */
-    int ref_quirks;        /* policy (iii)                                                       */
+    int ref_quirks;        /* bit 0: policy (iii); bit 1: policy (v), the sort key through a float dot */
 } ora_grid;
 
 typedef struct {           /* src/SPH.h:252-285 sphparams_t, same order                          */
@@ -171,6 +175,16 @@ uint32_t ora_key_of(const float *p, const ora_grid *G) {
     if (c[0] >= G->gx || c[1] >= G->gy || c[2] >= G->gz) k |= KEY_NOCELL;
     return k;
 }
+/* policy (v): the sort shaders' GetHash, uint(dot(vec3(cell), vec3(1, gx*gz, gx))) evaluated in binary32 */
+static uint32_t sort_key_float_dot(const float *p, const ora_grid *G) {
+    int c[3];
+    cell_clamped(p, G, c);
+    volatile float t = (float)c[0] * 1.0f;                    /* volatile: every operation rounds to binary32 */
+    t = t + (float)c[1] * (float)(G->gx * G->gz);
+    t = t + (float)c[2] * (float)G->gx;
+    return (uint32_t)t;
+}
+
 void ora_keys(int n, const float *rec4, const ora_grid *G, uint32_t *keys) {
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++) keys[i] = ora_key_of(rec4 + 4 * (size_t)i, G);
@@ -194,6 +208,10 @@ void ora_sort(int n, const float *rec_in, const ora_grid *G, float *rec_out, uin
     uint32_t *ka = (uint32_t *)malloc((size_t)n * 4), *kb = (uint32_t *)malloc((size_t)n * 4);
     memcpy(a, rec_in, (size_t)n * 16);
     ora_keys(n, a, G, ka);
+    if (G->ref_quirks & 2) {                                  /* policy (v): sort by the float-dot hash of the shaders */
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; i++) ka[i] = sort_key_float_dot(a + 4 * (size_t)i, G);
+    }
     int nt = ora_num_threads();
     size_t *hist = (size_t *)malloc(sizeof(size_t) * 4 * (size_t)nt);
     for (int pass = 0; pass < passes; pass++) {
@@ -242,7 +260,7 @@ void ora_findcells(int n, const float *rec4, const ora_grid *G, int32_t *start, 
     memset(start, 0xFF, ncell * 4);                                   /* clear to -1 */
     if (n <= 0) return;
     int c0[3];
-    if (G->ref_quirks) {
+    if (G->ref_quirks & 1) {
         start[0] = 0;                                                 /* :39-43, thread 0 */
     } else {
         cell_clamped(rec4, G, c0);

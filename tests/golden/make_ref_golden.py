@@ -11,6 +11,11 @@ ref_small.npz      16^3 = 4,096 particles, same grid, K = 3, vorticity + XSPH on
                    sorted records / cell starts / packed neighbour runs / lambda of step 1, per-step kinetic energy.
 ref_reference_scene.npz  the reference's own scene (two mirrored 32^3 blocks = 65,536 particles, K = 5, its defaults,
                    src/Simulation.cpp:200-246 with a seeded jitter): digests after steps 1 and 5.
+ref_c2_step.npz    BASELINE configs[1]: dam-break 128x64x128 = 1,048,576 particles, grid 256x128x256, K = 3, vorticity +
+                   XSPH on: digests of positions and velocities after steps 1 and 2 (22 s of the reference per step).
+ref_c3_step.npz    BASELINE configs[2], the headline size: dam-break 256x128x256 = 8,388,608 particles, grid 512x256x512, K = 4,
+                   vorticity + XSPH on: digests after step 1 (about three and a half minutes of the reference).  On this
+                   grid (2^26 cells) the shaders' float-dot sort key is inexact: the oracle matches with ref_quirks = 3.
 Schedule of the two racy shaders: Jacobi (oracle/ref_harness.cpp, order 0); `define_last_end` policy on."""
 import hashlib
 import os
@@ -97,9 +102,40 @@ def reference_scene():
     np.savez_compressed(os.path.join(HERE, "ref_reference_scene.npz"), **out)
 
 
+def c2_step():
+    grid = (256, 128, 256)
+    pos, vel = oracle.dam_break(128, 64, 128)
+    r = ref.RefSim(pos.shape[0], grid)
+    r.upload(pos, vel)
+    out = {"n3": np.array([128, 64, 128]), "grid": np.array(grid), "iters": 3, "vorticity": 1, "seed": 12345}
+    for step in (1, 2):
+        r.step(3, vorticity=True)
+        p, v, _ = r.download()
+        out["pos_sha_%d" % step], out["vel_sha_%d" % step] = digest(p), digest(v)
+    np.savez_compressed(os.path.join(HERE, "ref_c2_step.npz"), **out)
+
+
+def c3_step():
+    grid = (512, 256, 512)
+    pos, vel = oracle.dam_break(256, 128, 256)
+    r = ref.RefSim(pos.shape[0], grid)
+    r.upload(pos, vel)
+    out = {"n3": np.array([256, 128, 256]), "grid": np.array(grid), "iters": 4, "vorticity": 1, "seed": 12345}
+    r.step(4, vorticity=True)
+    p, v, _ = r.download()
+    out["pos_sha_1"], out["vel_sha_1"] = digest(p), digest(v)
+    np.savez_compressed(os.path.join(HERE, "ref_c3_step.npz"), **out)
+
+
 if __name__ == "__main__":
     if not ref.available():
         raise SystemExit("needs /root/reference (the shaders are compiled from there)")
-    c1_trace(); small(); reference_scene()
-    for f in ("ref_c1_trace.npz", "ref_small.npz", "ref_reference_scene.npz"):
+    only = sys.argv[1:]
+    for name, fn in (("c1_trace", c1_trace), ("small", small), ("reference_scene", reference_scene), ("c2_step", c2_step),
+                     ("c3_step", c3_step)):
+        if not only or name in only:
+            fn()
+    for f in ("ref_c1_trace.npz", "ref_small.npz", "ref_reference_scene.npz", "ref_c2_step.npz", "ref_c3_step.npz"):
+        if not os.path.exists(os.path.join(HERE, f)):
+            continue
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -67,6 +67,37 @@ def test_oracle_reproduces_reference_two_block_scene():
             assert digest(pos) == str(G["pos_sha_%d" % step]) and digest(vel) == str(G["vel_sha_%d" % step]), step
 
 
+def test_oracle_reproduces_reference_c2_two_steps():
+    """BASELINE configs[1] -- 1,048,576 particles, grid 256x128x256, K = 3, vorticity + XSPH: the oracle reproduces the digests
+    of the reference's shaders (22 s of g++-compiled GLSL per step, minted once) bit for bit at this size too."""
+    G = np.load(os.path.join(HERE, "golden", "ref_c2_step.npz"))
+    pos, vel = oracle.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
+    sim = oracle.Sim(pos.shape[0], oracle.make_grid(*G["grid"].tolist(), ref_quirks=1))
+    P = oracle.default_params()
+    for step in (1, 2):
+        sim.step(pos, vel, P, int(G["iters"]), vorticity=bool(G["vorticity"]))
+        assert digest(pos) == str(G["pos_sha_%d" % step]), step
+        assert digest(vel) == str(G["vel_sha_%d" % step]), step
+
+
+def test_oracle_reproduces_reference_c3_headline_step():
+    """BASELINE configs[2], the size every headline number is quoted on -- 8,388,608 particles, grid 512x256x512, K = 4,
+    vorticity + XSPH: one whole step of the oracle has the digests of the reference's shaders (three and a half minutes of
+    g++-compiled GLSL, minted once).
+
+    On this grid (2^26 cells) the reference's sort key -- uint(dot(ivec3, ivec3)), a FLOAT dot product in GLSL
+    (counting.glsl:53-57, globalsort.glsl:50-55) -- is no longer exact: policy (v) of the oracle, ref_quirks bit 1, evaluates it
+    literally and reproduces the reference bit for bit; with the integer hash (what the product implements, and what the
+    reference computes on every grid of up to 2^24 cells) 7 % of the particles come out differently after this one step, 1.85 % of
+    them by more than the north star's tolerance (tests/golden/float_hash_departure.py)."""
+    G = np.load(os.path.join(HERE, "golden", "ref_c3_step.npz"))
+    pos, vel = oracle.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
+    sim = oracle.Sim(pos.shape[0], oracle.make_grid(*G["grid"].tolist(), ref_quirks=3))
+    sim.step(pos, vel, oracle.default_params(), int(G["iters"]), vorticity=bool(G["vorticity"]))
+    assert digest(pos) == str(G["pos_sha_1"])
+    assert digest(vel) == str(G["vel_sha_1"])
+
+
 def test_oracle_reproduces_reference_small_scene_with_vorticity():
     G = np.load(os.path.join(HERE, "golden", "ref_small.npz"))
     pos, vel = oracle.dam_break(*G["n3"].tolist(), seed=int(G["seed"]))
@@ -210,6 +241,41 @@ def test_other_grid_and_parameters():
     P = oracle.default_params()
     P.one_over_rho_0, P.epsilon, P.timestep, P.tensile_instability_k, P.xsph_viscosity_c = 0.9, 3.0, 0.01, 0.2, 0.05
     stage_by_stage(pos, vel, (100, 50, 90), params=P)
+
+
+@needs_ref
+@pytest.mark.parametrize("origin_y", [0.5, 100.5, 200.5])
+def test_reference_sort_key_is_a_float_dot(origin_y):
+    """The sort shaders hash a cell with uint(dot(ivec3 cell, ivec3 GRID_HASHWEIGHTS)) (counting.glsl:53-57,
+    globalsort.glsl:50-55).  GLSL's dot is a float operation, so the key is exact only below 2^24.  On the headline grid
+    (512x256x512 = 2^26 cells) a block whose ids run against x (the mirrored block of Simulation::ResetParticleBuffer) shows it:
+    at y < 64 cells (hash < 2^24) the compiled shaders sort exactly like the integer hash; higher up neighbouring cells share a
+    key and the reference's order is no longer a sort by cell -- it is exactly the stable sort by the binary32-rounded key.
+    The oracle follows either reading (ref_quirks bit 1 = literal); the product implements the integer hash."""
+    grid = (512, 256, 512)
+    pos, vel = oracle.dam_break(16, 16, 16, origin=(60.5, origin_y, 60.5), mirror=True)
+    P = oracle.default_params()
+    r = ref.RefSim(pos.shape[0], grid)
+    r.upload(pos, vel)
+    r.predict()
+    rec = r.records().copy()
+    r.sort()
+    ids_ref = r.records()[:, 3].view(np.int32)
+    srt_int, _ = oracle.sort(oracle.predict(pos, vel, P, oracle.make_grid(*grid, ref_quirks=1)), oracle.make_grid(*grid, ref_quirks=1))
+    srt_lit, _ = oracle.sort(oracle.predict(pos, vel, P, oracle.make_grid(*grid, ref_quirks=3)), oracle.make_grid(*grid, ref_quirks=3))
+    assert np.array_equal(ids_ref, srt_lit[:, 3].view(np.int32))                      # literal reading: always the reference
+    cell = np.floor(np.clip(rec[:, :3], 0, np.array(grid, np.float32))).astype(np.int64)
+    key_int = cell[:, 0] + cell[:, 2] * grid[0] + cell[:, 1] * grid[0] * grid[2]
+    cf = cell.astype(np.float32)
+    key_f32 = ((cf[:, 0] * np.float32(1) + cf[:, 1] * np.float32(grid[0] * grid[2])).astype(np.float32)
+               + cf[:, 2] * np.float32(grid[0])).astype(np.float32).astype(np.int64)
+    assert np.array_equal(ids_ref, np.argsort(key_f32, kind="stable"))                # ... = stable sort by the rounded key
+    exact = bool(np.all(key_int < (1 << 24)))
+    assert exact == (origin_y < 64)
+    assert np.array_equal(ids_ref, srt_int[:, 3].view(np.int32)) == exact             # integer reading: the same below 2^24
+    assert np.array_equal(key_f32, key_int) == exact
+    if not exact:
+        assert not np.all(np.diff(key_int[ids_ref]) >= 0)                            # the reference's output is not sorted by cell
 
 
 @needs_ref
