@@ -314,3 +314,31 @@ def test_whole_steps_live():
         rp, rv, rh = r.download()
         assert np.array_equal(bits(rp), bits(op)) and np.array_equal(bits(rv), bits(ov)) and np.array_equal(rh, oh), step
         assert np.array_equal(bits(r.vort()), bits(sim.vort)), step
+
+
+@needs_ref
+def test_whole_steps_live_on_the_headline_grid_with_the_literal_key():
+    """Ten whole steps on the 2^26-cell grid with both blocks of the reference's scene (one mirrored) dropped in high up, where
+    the shaders' float-dot sort key is inexact and cells interleave in the sorted order: the oracle with ref_quirks = 3 still
+    equals the compiled shaders bit for bit -- positions, velocities, vorticity, highlight marks -- every step."""
+    grid = (512, 256, 512)
+    p1, v1 = oracle.dam_break(16, 16, 16, origin=(40.5, 100.5, 40.5))
+    p2, v2 = oracle.dam_break(16, 16, 16, origin=(70.5, 100.5, 70.5), mirror=True, id0=4096)
+    pos, vel = np.concatenate([p1, p2]), np.concatenate([v1, v2])
+    hl = np.zeros(pos.shape[0], np.uint32)
+    hl[[7, 4100, 8000]] = 1
+    r = ref.RefSim(pos.shape[0], grid)
+    r.upload(pos, vel, hl)
+    sim = oracle.Sim(pos.shape[0], oracle.make_grid(*grid, ref_quirks=3))
+    integer = oracle.Sim(pos.shape[0], oracle.make_grid(*grid, ref_quirks=1))
+    P = oracle.default_params()
+    op, ov, oh = pos.copy(), vel.copy(), hl.copy()
+    ip, iv, ih = pos.copy(), vel.copy(), hl.copy()
+    for step in range(10):
+        r.step(3, vorticity=True)
+        sim.step(op, ov, P, 3, vorticity=True, highlight=oh)
+        integer.step(ip, iv, P, 3, vorticity=True, highlight=ih)
+        rp, rv, rh = r.download()
+        assert np.array_equal(bits(rp), bits(op)) and np.array_equal(bits(rv), bits(ov)) and np.array_equal(rh, oh), step
+        assert np.array_equal(bits(r.vort()), bits(sim.vort)), step
+    assert not np.array_equal(bits(ip), bits(op))            # the integer hash is another simulation up here
