@@ -228,6 +228,34 @@ def test_every_stage_matches_the_reference_shaders_on_edge_scenes(scene):
 
 
 @needs_ref
+@pytest.mark.parametrize("seed", range(12))
+def test_every_stage_matches_the_reference_shaders_on_random_scenes(seed):
+    """Randomised inputs: particle count, grid, a mixture of a uniform cloud (partly outside the grid), tight clusters and
+    exact duplicates, velocities up to the cell size per step, every simulation parameter, the external force and stale
+    highlight words.  Every stage of the oracle equals the compiled shader bit for bit."""
+    rng = np.random.default_rng(1000 + seed)
+    n = 512 * int(rng.integers(1, 9))
+    grid = [(128, 64, 128), (64, 32, 96), (96, 48, 40), (256, 128, 64)][int(rng.integers(0, 4))]
+    g = np.array(grid, np.float32)
+    pos = np.zeros((n, 4), np.float32)
+    k = n // 2
+    pos[:k, :3] = rng.uniform(-0.05, 1.05, (k, 3)).astype(np.float32) * g                       # cloud, 5 % margin outside
+    centres = rng.uniform(0.2, 0.8, (4, 3)).astype(np.float32) * g
+    pos[k:, :3] = centres[rng.integers(0, 4, n - k)] + rng.normal(0, 1.5, (n - k, 3)).astype(np.float32)   # clusters
+    dup = rng.integers(0, n, n // 64)
+    pos[dup] = pos[rng.integers(0, n, n // 64)]                                                 # exact duplicates
+    vel = np.zeros((n, 4), np.float32)
+    vel[:, :3] = rng.normal(0, float(rng.choice([0.5, 5.0, 30.0])), (n, 3)).astype(np.float32)
+    P = oracle.default_params()
+    P.one_over_rho_0 = float(rng.uniform(0.5, 1.5)); P.epsilon = float(rng.uniform(1.0, 10.0))
+    P.gravity = float(rng.uniform(0.0, 20.0)); P.timestep = float(rng.uniform(0.004, 0.03))
+    P.tensile_instability_k = float(rng.uniform(0.0, 0.3)); P.xsph_viscosity_c = float(rng.uniform(0.0, 0.1))
+    P.vorticity_epsilon = float(rng.uniform(0.0, 10.0))
+    hl = rng.integers(0, 4, n).astype(np.uint32) * (rng.random(n) < 0.01)
+    stage_by_stage(pos, vel, grid, extforce=bool(rng.integers(0, 2)), highlight=hl.astype(np.uint32), iters=int(rng.integers(1, 4)), params=P)
+
+
+@needs_ref
 def test_robust_access_zero_fetches_are_equivalent_inside_the_walls():
     """Policy (iv): the oracle reads an out-of-grid cell as empty; a GL driver with robust buffer access returns 0.  Inside
     the walls (every BASELINE scene) the two differ only in how an EMPTY run is spelled."""
